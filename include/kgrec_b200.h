@@ -1,0 +1,232 @@
+/* kgrec_b200.h -- C ABI of the B200-native scoring engine for joint KG +
+ * recommendation models (TransE / TransH / TransR / TUP / KTUP).
+ *
+ * The reference (TaoMiner/joint-kg-recommender) is pure Python on PyTorch and
+ * has no FFI of its own: its "plugin boundary" for this path is the duck-typed
+ * nn.Module protocol of jTransUP/models/{transE,transH,transR,transUP,jTransUP}.py
+ * (SURVEY.md section 8b).  Each entry point below replaces the chain of stock
+ * torch ops behind one of those methods; the citation on each says which.
+ * The Python mirror of the reference classes (joint-kg-recommender_b200/kgrec_b200)
+ * binds this header with ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - tables are fp32 row-major [rows, ld] with ld >= dim (floats);
+ *  - index arrays are int32 or int64 (idx_bytes = 4 | 8), as the reference's
+ *    drivers pass torch.LongTensor (knowledge_representation.py:179-184);
+ *  - all work is enqueued on `stream` (a cudaStream_t); nothing synchronises;
+ *  - return value: KGREC_OK or an error code; kgrec_last_error() has the text;
+ *  - there is no CPU fallback anywhere behind this header.
+ */
+#ifndef KGREC_B200_H_
+#define KGREC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KGREC_ABI_VERSION 1
+
+typedef void* kgrec_stream_t; /* cudaStream_t */
+
+enum {
+  KGREC_OK = 0,
+  KGREC_ERR_INVALID = 1,     /* bad argument (null table, dim, alignment ...)   */
+  KGREC_ERR_UNSUPPORTED = 2, /* shape outside what the kernels are built for   */
+  KGREC_ERR_CUDA = 3         /* a CUDA runtime call failed                     */
+};
+
+/* -model_type values on the hot path (jTransUP/models/base.py:23-25). */
+enum {
+  KGREC_TRANSE = 0, /* transE.py   score = L(E[h] + R[r] - E[t])                         */
+  KGREC_TRANSH = 1, /* transH.py   hyperplane projection by Norm[r] (misc.py:18-19)      */
+  KGREC_TRANSR = 2, /* transR.py   d x d matrix Proj[r] (misc.py:21-26)                  */
+  KGREC_TUP = 3,    /* transUP.py  user/item + preference induction (transUP.py:105-115) */
+  KGREC_KTUP = 4    /* jTransUP.py rec branch (jTransUP.py:124-143); its KG branch is
+                       KGREC_TRANSH on the same tables                                   */
+};
+
+enum { KGREC_LOSS_MARGIN = 0, /* utils/loss.py:8-16  sum max(pos-neg+margin,0)        */
+       KGREC_LOSS_BPR = 1 };  /* utils/loss.py:29-31 mean -logsigmoid(target*(pos-neg)) */
+
+enum { KGREC_SIDE_HEAD = 0,   /* evaluateHead: c = proj(E[t]) - R[r]                    */
+       KGREC_SIDE_TAIL = 1,   /* evaluateTail: c = proj(E[h]) + R[r]                    */
+       KGREC_SIDE_REC = 2 };  /* evaluate / evaluateRec: users against all items        */
+
+/* The embedding tables of one model instance (the nn.Embedding weights the
+ * reference classes own: transE.py:36-40, transH.py:39-45, transR.py:45-51,
+ * transUP.py:46-60, jTransUP.py:64-103).  Unused tables are NULL. */
+typedef struct kgrec_tables {
+  int32_t dim;        /* embedding_size d                                        */
+  int32_t ld;         /* leading dimension of every [rows, d] table, in floats   */
+  int32_t l1;         /* L1_flag: 1 -> sum|e|, 0 -> sum e^2 (no sqrt)            */
+  int32_t use_gumbel; /* use_st_gumbel (TUP / KTUP)                              */
+  int64_t n_ent;      /* rows of ent (KTUP: entity_total + 1, last = zero pad)   */
+  int64_t n_rel;
+  int64_t n_user;
+  int64_t n_item;
+  int32_t n_pref;     /* preference_total P (KTUP: == n_rel)                     */
+  int32_t reserved;
+  const float* ent;        /* [n_ent, ld]                                        */
+  const float* rel;        /* [n_rel, ld]                                        */
+  const float* norm;       /* [n_rel, ld]     TransH, KTUP                       */
+  const float* proj;       /* [n_rel, d*d]    TransR, row-major M[a,b]           */
+  const float* user;       /* [n_user, ld]                                       */
+  const float* item;       /* [n_item, ld]                                       */
+  const float* pref;       /* [n_pref, ld]                                       */
+  const float* pref_norm;  /* [n_pref, ld]                                       */
+  const int32_t* item2ent; /* [n_item] KTUP item -> aligned entity row, unaligned
+                              items map to the padding row n_ent-1: the device form
+                              of paddingItems (jTransUP.py:114-120)               */
+} kgrec_tables;
+
+/* Where the backward kernels put row gradients.
+ * mode 0 "slots": one gradient row per gathered row, laid out in gather order --
+ *         the value array of an (uncoalesced) sparse COO gradient whose indices
+ *         are the input id arrays themselves.  ent: [2n, d] (head slots then tail
+ *         slots; KTUP: [n, d] aligned-entity slots), rel / norm / user / item: [n, d].
+ * mode 1 "dense": atomically accumulated into caller-zeroed [rows, d] buffers,
+ *         the layout the reference's autograd produces (param.grad).
+ * proj, pref, pref_norm are always accumulated densely ([n_rel, d*d], [P, d]).
+ * For KTUP the gradient of rel / norm equals that of pref / pref_norm
+ * (jTransUP.py:253-258) and is written once, to pref / pref_norm. */
+typedef struct kgrec_grads {
+  int32_t mode;
+  int32_t reserved;
+  float* ent;
+  float* rel;
+  float* norm;
+  float* proj;
+  float* user;
+  float* item;
+  float* pref;
+  float* pref_norm;
+} kgrec_grads;
+
+int kgrec_abi_version(void);
+const char* kgrec_last_error(void);
+/* number of SMs the library sized its grids for on the current device */
+int kgrec_sm_count(void);
+
+/* ---- training path ------------------------------------------------------ */
+
+/* model.forward: transE.py:51-63, transH.py:58-71, transR.py:65-78,
+ * transUP.py:69-82, jTransUP.py:122-161.
+ * KG models: a = h, b = t, c = r.   TUP / KTUP: a = u, b = i, c = NULL.
+ * gumbel_u: [n, P] uniform draws for the ST Gumbel-softmax (transUP.py:159-161)
+ * or NULL -> drawn in-kernel from Philox4x32-10 keyed by `seed` (only read when
+ * tables->use_gumbel).  status (optional, int32[1]) is set non-zero when an
+ * index is out of range. */
+int kgrec_score_fwd(const kgrec_tables* tables, int model,
+                    const void* a, const void* b, const void* c, int idx_bytes, int64_t n,
+                    const float* gumbel_u, uint64_t seed,
+                    float* scores, int32_t* status, kgrec_stream_t stream);
+
+/* The autograd of the above (reference: losses.backward(),
+ * knowledge_representation.py:207): given dLoss/dscore [n] emits row gradients. */
+int kgrec_score_bwd(const kgrec_tables* tables, int model,
+                    const void* a, const void* b, const void* c, int idx_bytes, int64_t n,
+                    const float* gumbel_u, uint64_t seed,
+                    const float* grad_scores, const kgrec_grads* grads,
+                    kgrec_stream_t stream);
+
+/* Fused positive + sampled-negative scoring with the ranking loss:
+ * pos = model(pos ids); neg = model(neg ids); marginLoss / bprLoss
+ * (knowledge_representation.py:189-195, item_recommendation.py:171-175).
+ * Positive j owns negatives [j*n_neg, (j+1)*n_neg).  The loss is reduced per
+ * batch of `batch_pos` positives: loss[b], b < ceil(n_pos / batch_pos) --
+ * margin: sum over the batch's pairs; bpr: mean over them.
+ * gumbel_u (optional): [n_pos + n_pos*n_neg, P], positives first.
+ * workspace: >= kgrec_rank_loss_workspace_bytes(n_pos) bytes. */
+int64_t kgrec_rank_loss_workspace_bytes(int64_t n_pos);
+int kgrec_rank_loss_fwd(const kgrec_tables* tables, int model,
+                        const void* pa, const void* pb, const void* pc,
+                        const void* na, const void* nb, const void* nc,
+                        int idx_bytes, int64_t n_pos, int32_t n_neg, int64_t batch_pos,
+                        int loss_kind, float margin_or_target,
+                        const float* gumbel_u, uint64_t seed,
+                        float* pos_scores, float* neg_scores, float* loss,
+                        void* workspace, int32_t* status, kgrec_stream_t stream);
+
+/* Backward of kgrec_rank_loss_fwd from the saved scores: the per-score
+ * coefficients dLoss/dscore are formed in-kernel (loss.py:16, 30-31), scaled by
+ * grad_loss (host scalar) times grad_loss_dev[batch] (optional device array, one
+ * upstream value per loss batch), and the row gradients written as in
+ * kgrec_score_bwd with the positives' slots first: slot arrays are sized for
+ * n = n_pos * (1 + n_neg). */
+int kgrec_rank_loss_bwd(const kgrec_tables* tables, int model,
+                        const void* pa, const void* pb, const void* pc,
+                        const void* na, const void* nb, const void* nc,
+                        int idx_bytes, int64_t n_pos, int32_t n_neg, int64_t batch_pos,
+                        int loss_kind, float margin_or_target,
+                        const float* gumbel_u, uint64_t seed,
+                        const float* pos_scores, const float* neg_scores, float grad_loss,
+                        const float* grad_loss_dev, const kgrec_grads* grads, kgrec_stream_t stream);
+
+/* ---- full-catalog evaluation path ---------------------------------------- */
+/* Common arguments of the three evaluation modes:
+ *   model / side   which evaluate* method: KG sides score query (t,r) / (h,r) pairs against
+ *                  entities (transE.py:65-105, transH.py:73-121, jTransUP.py:193-247), the
+ *                  rec side scores users against items (transUP.py:84-102, jTransUP.py:163-191).
+ *   q, r           query ids (tail ids for SIDE_HEAD, head ids for SIDE_TAIL, user ids for
+ *                  SIDE_REC) and relation ids (KG sides), nq of them.
+ *   qvec           optional explicit query vectors [nq, 2*dim] = (c | w) replacing q / r on
+ *                  the KG sides: c = proj(E[q]) -/+ R[r] (transE.py:68-71, transH.py:76-82)
+ *                  and the hyperplane normal w.  Required for KGREC_TRANSR, whose catalog
+ *                  must already be projected by the relation matrix (misc.py:29-33).
+ *   cat, cat_ld, n_cat   the catalog (shard): n_cat contiguous rows of the entity / item
+ *                  table (KTUP rec side: the table built by kgrec_ktup_item_table), 16-byte
+ *                  aligned, cat_ld % 4 == 0.
+ *   id_base        global id of catalog row 0 (shards of a row-partitioned table).
+ *   gumbel_u       rec side with use_gumbel: optional explicit uniform draws
+ *                  [nq, n_cat, P] (transUP.py:159-161); NULL -> counter-hash draws from seed. */
+
+/* evaluateHead / evaluateTail / evaluate / evaluateRec producing the full [nq, n_cat]
+ * score matrix the unchanged drivers consume.  out has leading dimension ld_out >= n_cat. */
+int kgrec_eval_scores(const kgrec_tables* tables, int model, int side,
+                      const void* q, const void* r, int idx_bytes, const float* qvec, int64_t nq,
+                      const float* cat, int64_t cat_ld, int64_t n_cat,
+                      const float* gumbel_u, uint64_t seed,
+                      float* out, int64_t ld_out, kgrec_stream_t stream);
+
+/* The same scores reduced on chip to the K best (smallest) per query, replacing the D2H
+ * copy + np.argsort walk of utils/misc.py:125-146, 213-229.  Ordering is (score, id)
+ * lexicographic.  filter_ptr / filter_ids: optional CSR (ptr [nq+1], ascending global ids)
+ * of catalog ids to skip per query (train + other eval files' positives,
+ * item_recommendation.py:108-111).  out_keys: [nq, k] uint64 = score bits << 32 | global id,
+ * ascending; unused places hold UINT64_MAX.  workspace: kgrec_eval_workspace_bytes(nq, k). */
+int64_t kgrec_eval_workspace_bytes(int64_t nq, int32_t k);
+int kgrec_eval_topk(const kgrec_tables* tables, int model, int side,
+                    const void* q, const void* r, int idx_bytes, const float* qvec, int64_t nq,
+                    const float* cat, int64_t cat_ld, int64_t n_cat, int64_t id_base, int32_t k,
+                    const int64_t* filter_ptr, const int32_t* filter_ids,
+                    const float* gumbel_u, uint64_t seed,
+                    uint64_t* out_keys, void* workspace, int64_t workspace_bytes,
+                    kgrec_stream_t stream);
+
+/* K-way merge of per-shard / per-split top-K lists: in [n_lists, nq, k] -> out [nq, k].
+ * Run after the NCCL all-gather of per-GPU candidates (the path's one collective). */
+int kgrec_merge_topk(const uint64_t* in_keys, int32_t n_lists, int64_t nq, int32_t k,
+                     uint64_t* out_keys, kgrec_stream_t stream);
+
+/* Filtered rank of gold ids (getKGPerformance, utils/misc.py:125-146): adds to counts[i]
+ * (caller-zeroed) #{ e in catalog shard : (score(q_i, e), e) < (gold_scores[i], gold_ids[i]) }.
+ * Counts of different shards add (one all-reduce); the filter / other-gold correction is
+ * applied by the caller from the few filtered ids' scores. */
+int kgrec_eval_rank_count(const kgrec_tables* tables, int model, int side,
+                          const void* q, const void* r, int idx_bytes, const float* qvec, int64_t nq,
+                          const float* cat, int64_t cat_ld, int64_t n_cat, int64_t id_base,
+                          const float* gold_scores, const int32_t* gold_ids,
+                          int32_t* counts, kgrec_stream_t stream);
+
+/* KTUP rec-side catalog: out[i] = Item[item_begin + i] + Ent[item2ent[item_begin + i]]
+ * (jTransUP.py:177-181), n_items rows with leading dimension ld_out. */
+int kgrec_ktup_item_table(const kgrec_tables* tables, int64_t item_begin, int64_t n_items,
+                          float* out, int64_t ld_out, kgrec_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGREC_B200_H_ */

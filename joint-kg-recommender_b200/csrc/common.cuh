@@ -1,0 +1,204 @@
+// Shared device helpers for the kgrec_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/kgrec_b200.h"
+
+namespace kgrec {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kMaxPref = 128;             // preference_total limit (staging layout)
+
+// ---- error plumbing (host) -------------------------------------------------
+void set_error(const char* fmt, ...);
+#define KGREC_CUDA_OK(expr)                                                        \
+  do {                                                                             \
+    cudaError_t e__ = (expr);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      kgrec::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),    \
+                       __FILE__, __LINE__);                                        \
+      return KGREC_ERR_CUDA;                                                       \
+    }                                                                              \
+  } while (0)
+int sm_count();
+
+// ---- warp reductions --------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(FULL, a, o);
+    b += __shfl_xor_sync(FULL, b, o);
+  }
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+
+// Reduce-scatter of 8 per-lane partials: on return every lane l holds the full warp sum of
+// v[(l >> 2) & 7].  9 shuffles for 8 reductions (vs 40 with one tree each).
+__device__ __forceinline__ float warp_reduce_scatter8(float (&v)[8], int lane) {
+#pragma unroll
+  for (int o = 16, n = 4; n > 0; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < n) {
+        const float send = up ? v[j] : v[j + n];
+        const float keep = up ? v[j + n] : v[j];
+        v[j] = keep + __shfl_xor_sync(FULL, send, o);
+      }
+    }
+  }
+  float r = v[0];
+  r += __shfl_xor_sync(FULL, r, 2);
+  r += __shfl_xor_sync(FULL, r, 1);
+  return r;
+}
+
+// ---- index loads --------------------------------------------------------------
+__device__ __forceinline__ int64_t load_idx(const void* p, int64_t i, int is64) {
+  return is64 ? __ldg(reinterpret_cast<const long long*>(p) + i)
+              : static_cast<int64_t>(__ldg(reinterpret_cast<const int*>(p) + i));
+}
+__device__ __forceinline__ int64_t checked(int64_t row, int64_t rows, int32_t* status) {
+  if (static_cast<uint64_t>(row) >= static_cast<uint64_t>(rows)) {
+    if (status) *status = 1;
+    return 0;
+  }
+  return row;
+}
+
+// ---- streaming loads / stores ------------------------------------------------------
+__device__ __forceinline__ float4 ldg_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// One embedding row spread over a warp.  VEC: lane owns float4 chunks lane, lane+32, ...
+// (128-bit loads, requires d % 4 == 0 and 16-byte aligned rows); otherwise lane owns
+// scalars lane, lane+32, ...  Lanes / slots past d hold zeros so every reduction can run
+// unmasked.
+template <int NCH, bool VEC>
+struct Row {
+  static constexpr int NE = NCH * 4;
+  __device__ __forceinline__ static int elem(int lane, int e) {
+    return VEC ? ((lane + 32 * (e >> 2)) * 4 + (e & 3)) : (lane + 32 * e);
+  }
+  __device__ __forceinline__ static void load(float (&v)[NE], const float* __restrict__ row, int d, int lane) {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane + 32 * i;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c * 4 < d) t = ldg_f4(reinterpret_cast<const float4*>(row) + c);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int j = lane + 32 * e;
+        v[e] = (j < d) ? __ldg(row + j) : 0.f;
+      }
+    }
+  }
+  // shared-memory variant (tables staged by the CTA)
+  __device__ __forceinline__ static void load_s(float (&v)[NE], const float* row, int d, int lane) {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane + 32 * i;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c * 4 < d) t = reinterpret_cast<const float4*>(row)[c];
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int j = lane + 32 * e;
+        v[e] = (j < d) ? row[j] : 0.f;
+      }
+    }
+  }
+  __device__ __forceinline__ static void store(float* __restrict__ row, const float (&v)[NE], int d, int lane) {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane + 32 * i;
+        if (c * 4 < d)
+          reinterpret_cast<float4*>(row)[c] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int j = lane + 32 * e;
+        if (j < d) row[j] = v[e];
+      }
+    }
+  }
+  __device__ __forceinline__ static void red_add(float* __restrict__ row, const float (&v)[NE], int d, int lane) {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane + 32 * i;
+        if (c * 4 < d) red_add_f4(row + 4 * c, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int j = lane + 32 * e;
+        if (j < d) atomicAdd(row + j, v[e]);
+      }
+    }
+  }
+  __device__ __forceinline__ static float dot(const float (&a)[NE], const float (&b)[NE]) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) s = fmaf(a[e], b[e], s);
+    return s;
+  }
+};
+
+// L(e) partial and its derivative (torch: d|x|/dx = sign(x), sign(0) = 0)
+__device__ __forceinline__ float dist_term(float e, int l1) { return l1 ? fabsf(e) : e * e; }
+__device__ __forceinline__ float ddist_term(float e, int l1) {
+  return l1 ? ((e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f)) : 2.f * e;
+}
+
+// ---- Philox4x32-10 (counter-based; the in-kernel Gumbel uniform source) ---------------
+__device__ __forceinline__ uint32_t philox_uniform_bits(uint64_t seed, uint64_t pair, uint32_t k) {
+  uint32_t c0 = static_cast<uint32_t>(pair), c1 = static_cast<uint32_t>(pair >> 32), c2 = k, c3 = 0x4b47u;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t pair, uint32_t k) {
+  return static_cast<float>(philox_uniform_bits(seed, pair, k) >> 8) * (1.0f / 16777216.0f);  // [0,1)
+}
+// Gumbel noise exactly as transUP.py:159-161 builds it from a uniform draw
+__device__ __forceinline__ float gumbel_from_uniform(float u) {
+  const float eps = 1e-20f;
+  return -logf(-logf(u + eps) + eps);
+}
+
+}  // namespace kgrec

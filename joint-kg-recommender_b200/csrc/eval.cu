@@ -1,0 +1,758 @@
+// Full-catalog evaluation: every query (test (t,r) / (h,r) pair, or test user) scored against
+// every catalog row (entity / item), reduced on chip to the full score matrix, the K best
+// per query, or the count of rows ranked before a gold id.   sm_100a.
+//
+// Reference semantics restated (CPU form: oracle/kg_oracle.py):
+//   transE.py:65-105, transH.py:73-121, transUP.py:84-102, jTransUP.py:163-247 (scores);
+//   utils/misc.py:125-146, 213-229 (ranking walk the top-K / rank modes replace).
+//
+// Structure
+//   * CTA = 8 warps; warp w owns 8 queries whose vectors (c, the hyperplane normal, or the
+//     user row) live in registers for the whole kernel.
+//   * The catalog streams once per 64-query tile: one elected lane moves tiles of TN
+//     contiguous rows global -> shared with cp.async.bulk (TMA 1-D bulk copy) into a
+//     4-stage ring guarded by full/empty mbarriers, two tiles ahead of the consumers.
+//   * A row is spread over the warp (lane c owns float4 chunk c).  For each row the warp
+//     forms the 8 per-query partial sums and folds them with one 8-way reduce-scatter
+//     (9 shuffles): lanes 4q..4q+3 end up holding query q's score.  Rows are processed four
+//     at a time so lane 4q+j holds (query q, row j): one candidate per lane.
+//   * top-K: every lane compares its candidate key = score bits << 32 | id with its
+//     query's current K-th best (a register); the rare survivors are inserted by the whole
+//     warp into that query's sorted list in shared memory ("warp-local top-K").
+#include <algorithm>
+#include "common.cuh"
+
+namespace kgrec {
+
+enum { KIND_DIST = 0, KIND_HYPER = 1, KIND_PREF_HARD = 2, KIND_PREF_SOFT = 3 };
+enum { MODE_FULL = 0, MODE_TOPK = 1, MODE_RANK = 2 };
+
+constexpr int QW = 8;                       // queries per warp
+constexpr int TQ = QW * kWarpsPerCta;       // queries per CTA
+constexpr int kStages = 4;                 // ring depth
+constexpr int kPrefetch = 2;               // tiles in flight ahead of the consumer
+constexpr int kEvalThreads = kThreads;
+constexpr uint64_t KEY_INF = ~0ull;
+
+// ---- mbarrier / bulk-copy PTX ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- keys -------------------------------------------------------------------------------------
+// scores are sums of |.| or squares: non-negative, so the IEEE bit pattern is monotone
+__device__ __forceinline__ uint64_t make_key(float s, uint32_t id) {
+  return (static_cast<uint64_t>(__float_as_uint(s)) << 32) | id;
+}
+
+// warp-cooperative insert of x into the ascending list[0..K) (x < list[K-1] is the caller's job)
+__device__ __forceinline__ void list_insert(uint64_t* list, int K, uint64_t x, int lane) {
+  int p = 0;
+  for (int base = 0; base < K; base += 32) {
+    const int j = base + lane;
+    p += __popc(__ballot_sync(FULL, j < K && list[j] < x));
+  }
+  for (int base = ((K - 1) / 32) * 32; base >= 0; base -= 32) {
+    const int j = base + lane;
+    const uint64_t v = (j >= 1 && j < K) ? list[j - 1] : 0ull;
+    __syncwarp();
+    if (j < K && j > p) list[j] = v;
+    __syncwarp();
+  }
+  if (lane == 0) list[p] = x;
+  __syncwarp();
+}
+
+// is `id` in the ascending id list flt[lo, hi) ?
+__device__ __forceinline__ bool filtered(const int32_t* __restrict__ flt, int64_t lo, int64_t hi, int32_t id) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int32_t v = __ldg(flt + mid);
+    if (v == id) return true;
+    if (v < id) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// cheap counter hash for the eval-time Gumbel draw (one 32-bit word per (query, row, k))
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint32_t q, uint32_t n, uint32_t k) {
+  uint32_t x = static_cast<uint32_t>(seed) ^ (q * 0x9E3779B1u);
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15;
+  x ^= n * 0x85EBCA77u + static_cast<uint32_t>(seed >> 32);
+  x *= 0x735a2d97u; x ^= x >> 15;
+  x ^= k * 0xC2B2AE3Du;
+  x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+  return static_cast<float>(x >> 8) * (1.0f / 16777216.0f);
+}
+
+struct EvalArgs {
+  kgrec_tables T;
+  int ktup;                 // KTUP tables (pref + rel, halves)
+  int side;
+  const void* q;            // query ids (tail / head / user)
+  const void* r;            // relation ids (KG sides)
+  int is64;
+  const float* qvec;        // optional explicit [nq, 2 dim] (c | w), overrides q / r (KG kinds)
+  int64_t nq;
+  const float* cat;         // first catalog row of this shard
+  int64_t cat_ld;
+  int64_t n_cat;
+  int64_t id_base;          // global id of cat row 0
+  int n_splits;             // catalog ranges (gridDim.y)
+  int tn;                   // catalog rows per tile
+  const float* gumbel_u;    // explicit [nq, n_cat, P] (PREF_HARD parity mode)
+  uint64_t seed;
+  // outputs
+  float* out; int64_t ld_out;               // FULL
+  uint64_t* part_keys; int k;               // TOPK: [n_splits][nq][k]
+  const int64_t* filter_ptr; const int32_t* filter_ids;
+  const float* gold_scores; const int32_t* gold_ids; int32_t* counts;   // RANK
+};
+
+// smem carve-up (floats unless noted), in this order:
+//   bars        : 2 * kStages uint64
+//   tiles       : kStages * tn * ld
+//   [PREF] sP,sN: 2 * P * stride ; IP: tn * ppad ; UP: 8 warps * QW * ppad
+//   [SOFT] IA,IB: 2 * tn * ld
+//   [TOPK] lists: TQ * k uint64
+struct EvalSmem {
+  size_t bars, tiles, sP, sN, IP, UP, IA, IB, lists, total;
+};
+__host__ __device__ inline EvalSmem eval_smem_layout(int kind, int mode, int d, int64_t ld, int P, int tn, int k) {
+  EvalSmem s{};
+  size_t off = 0;
+  s.bars = off; off += 2 * kStages * sizeof(uint64_t);
+  off = (off + 127) & ~static_cast<size_t>(127);
+  s.tiles = off; off += static_cast<size_t>(kStages) * tn * ld * sizeof(float);
+  if (kind >= KIND_PREF_HARD) {
+    const int stride = (d + 3) & ~3, ppad = (P + 3) & ~3;
+    s.sP = off; off += static_cast<size_t>(P) * stride * sizeof(float);
+    s.sN = off; off += static_cast<size_t>(P) * stride * sizeof(float);
+    s.IP = off; off += static_cast<size_t>(tn) * ppad * sizeof(float);
+    s.UP = off; off += static_cast<size_t>(kWarpsPerCta) * QW * ppad * sizeof(float);
+    if (kind == KIND_PREF_SOFT) {
+      s.IA = off; off += static_cast<size_t>(tn) * ld * sizeof(float);
+      s.IB = off; off += static_cast<size_t>(tn) * ld * sizeof(float);
+    }
+  }
+  if (mode == MODE_TOPK) {
+    off = (off + 7) & ~static_cast<size_t>(7);
+    s.lists = off; off += static_cast<size_t>(TQ) * k * sizeof(uint64_t);
+  }
+  s.total = off;
+  return s;
+}
+
+template <int KIND, int NCH, int MODE, bool L1>
+__global__ void __launch_bounds__(kEvalThreads)
+k_eval(const EvalArgs A) {
+  using R = Row<NCH, true>;
+  constexpr int NE = NCH * 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const kgrec_tables& T = A.T;
+  const int d = T.dim, P = T.n_pref;
+  constexpr int l1 = L1 ? 1 : 0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tn = A.tn;
+  const int64_t ld = A.cat_ld;
+  const EvalSmem L = eval_smem_layout(KIND, MODE, d, ld, P, tn, A.k);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+  uint64_t* empty = full + kStages;
+  float* tiles = reinterpret_cast<float*>(smem_raw + L.tiles);
+
+  // catalog range of this CTA
+  const int64_t n_tiles_all = (A.n_cat + tn - 1) / tn;
+  const int64_t tiles_per_split = (n_tiles_all + A.n_splits - 1) / A.n_splits;
+  const int64_t tile0 = static_cast<int64_t>(blockIdx.y) * tiles_per_split;
+  const int64_t tile1 = min(n_tiles_all, tile0 + tiles_per_split);
+  const int64_t my_tiles = max(static_cast<int64_t>(0), tile1 - tile0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kWarpsPerCta); }
+    mbar_fence_init();
+  }
+  [[maybe_unused]] float* sP = nullptr;
+  [[maybe_unused]] float* sN = nullptr;
+  [[maybe_unused]] int stride = 0, ppad = 0;
+  if constexpr (KIND >= KIND_PREF_HARD) {
+    stride = (d + 3) & ~3;
+    ppad = (P + 3) & ~3;
+    sP = reinterpret_cast<float*>(smem_raw + L.sP);
+    sN = reinterpret_cast<float*>(smem_raw + L.sN);
+    for (int idx = threadIdx.x; idx < P * stride; idx += blockDim.x) {
+      const int k = idx / stride, j = idx - k * stride;
+      float a = 0.f, b = 0.f;
+      if (j < d) {
+        a = __ldg(T.pref + static_cast<int64_t>(k) * T.ld + j);
+        b = __ldg(T.pref_norm + static_cast<int64_t>(k) * T.ld + j);
+        if (A.ktup) {
+          a += __ldg(T.rel + static_cast<int64_t>(k) * T.ld + j);
+          b += __ldg(T.norm + static_cast<int64_t>(k) * T.ld + j);
+        }
+      }
+      sP[idx] = a;
+      sN[idx] = b;
+    }
+  }
+  __syncthreads();
+
+  // The catalog tiles are moved by TMA bulk copies issued by one lane of warp 0, kPrefetch
+  // tiles ahead; a stage is refilled kStages - kPrefetch tiles after its last reader, so the
+  // issuing lane practically never waits on the empty barrier.
+  auto issue_tile = [&](int64_t t) {
+    const int s = static_cast<int>(t % kStages);
+    if (t >= kStages) mbar_wait(empty + s, static_cast<uint32_t>(((t / kStages) - 1) & 1));
+    const int64_t row0 = (tile0 + t) * tn;
+    const int64_t rows = min(static_cast<int64_t>(tn), A.n_cat - row0);
+    const uint32_t bytes = static_cast<uint32_t>(rows * ld * sizeof(float));
+    mbar_arrive_expect_tx(full + s, bytes);
+    bulk_g2s(tiles + static_cast<size_t>(s) * tn * ld, A.cat + row0 * ld, bytes, full + s);
+  };
+  if (threadIdx.x == 0)
+    for (int64_t t = 0; t < kPrefetch && t < my_tiles; ++t) issue_tile(t);
+
+  // ------------------------------------------------------------------ compute warps
+  const float hf = A.ktup ? 0.5f : 1.f;
+  const int64_t q0 = static_cast<int64_t>(blockIdx.x) * TQ + wid * QW;   // first query of this warp
+  float qa[QW][NE];                    // DIST/HYPER: c ; PREF: user row
+  [[maybe_unused]] float qb[QW][NE];   // HYPER: w ; SOFT: UA
+  [[maybe_unused]] float qc[QW][NE];   // SOFT: UB
+  [[maybe_unused]] float* UPw = nullptr;
+#pragma unroll
+  for (int qi = 0; qi < QW; ++qi) {
+    const int64_t q = q0 + qi;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { qa[qi][e] = 0.f; if (KIND == KIND_HYPER || KIND == KIND_PREF_SOFT) qb[qi][e] = 0.f; if (KIND == KIND_PREF_SOFT) qc[qi][e] = 0.f; }
+    if (q < A.nq) {
+      if constexpr (KIND <= KIND_HYPER) {
+        if (A.qvec) {
+          R::load(qa[qi], A.qvec + q * 2 * d, d, lane);
+          if (KIND == KIND_HYPER) R::load(qb[qi], A.qvec + q * 2 * d + d, d, lane);
+        } else {
+          const int64_t ie = load_idx(A.q, q, A.is64), ir = load_idx(A.r, q, A.is64);
+          float ev[NE], rv[NE];
+          R::load(ev, T.ent + ie * T.ld, d, lane);
+          R::load(rv, T.rel + ir * T.ld, d, lane);
+          if (KIND == KIND_HYPER) {
+            R::load(qb[qi], T.norm + ir * T.ld, d, lane);
+            const float a = warp_sum(R::dot(ev, qb[qi]));
+#pragma unroll
+            for (int e = 0; e < NE; ++e) ev[e] -= a * qb[qi][e];       // proj(E[q], w)
+          }
+#pragma unroll
+          for (int e = 0; e < NE; ++e) qa[qi][e] = (A.side == KGREC_SIDE_HEAD) ? ev[e] - rv[e] : ev[e] + rv[e];
+        }
+      } else {
+        R::load(qa[qi], T.user + load_idx(A.q, q, A.is64) * T.ld, d, lane);
+      }
+    }
+  }
+  if constexpr (KIND >= KIND_PREF_HARD) {
+    // UP[qi][k] = u . P_k / 2 ; SOFT: UA = hf sum_k UP_k P_k, UB = hf sum_k UP_k N_k
+    UPw = reinterpret_cast<float*>(smem_raw + L.UP) + wid * QW * ppad;
+#pragma unroll
+    for (int qi = 0; qi < QW; ++qi) {
+      for (int g = 0; g < P; g += 8) {
+        float vals[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          vals[kk] = 0.f;
+          if (g + kk < P) {
+            float row[NE];
+            R::load_s(row, sP + (g + kk) * stride, d, lane);
+            vals[kk] = R::dot(row, qa[qi]);
+          }
+        }
+        const float rr = warp_reduce_scatter8(vals, lane);
+        const int k = g + (lane >> 2);
+        if ((lane & 3) == 0 && k < P) UPw[qi * ppad + k] = 0.5f * rr;
+      }
+    }
+    __syncwarp();
+    if constexpr (KIND == KIND_PREF_SOFT) {
+#pragma unroll
+      for (int qi = 0; qi < QW; ++qi) {
+        for (int k = 0; k < P; ++k) {
+          const float z = hf * UPw[qi * ppad + k];
+          float row[NE];
+          R::load_s(row, sP + k * stride, d, lane);
+#pragma unroll
+          for (int e = 0; e < NE; ++e) qb[qi][e] = fmaf(z, row[e], qb[qi][e]);
+          R::load_s(row, sN + k * stride, d, lane);
+#pragma unroll
+          for (int e = 0; e < NE; ++e) qc[qi][e] = fmaf(z, row[e], qc[qi][e]);
+        }
+      }
+    }
+  }
+
+  // per-lane candidate bookkeeping: lane 4 qi + j serves (query qi, row j of each 4-row group)
+  const int myq = lane >> 2, myj = lane & 3;
+  const int64_t my_query = q0 + myq;
+  const bool q_valid = my_query < A.nq;
+  [[maybe_unused]] uint64_t thr = KEY_INF;           // TOPK: current K-th best of my query
+  [[maybe_unused]] uint64_t* lists = nullptr;
+  [[maybe_unused]] uint64_t gold_key = 0;            // RANK
+  [[maybe_unused]] int cnt = 0;
+  [[maybe_unused]] int64_t f_lo = 0, f_hi = 0;
+  if constexpr (MODE == MODE_TOPK) {
+    lists = reinterpret_cast<uint64_t*>(smem_raw + L.lists) + static_cast<size_t>(wid) * QW * A.k;
+    for (int i = lane; i < QW * A.k; i += 32) lists[i] = KEY_INF;
+    __syncwarp();
+    if (A.filter_ptr && q_valid) { f_lo = __ldg(A.filter_ptr + my_query); f_hi = __ldg(A.filter_ptr + my_query + 1); }
+  }
+  if constexpr (MODE == MODE_RANK) {
+    if (q_valid) gold_key = make_key(__ldg(A.gold_scores + my_query), static_cast<uint32_t>(__ldg(A.gold_ids + my_query)));
+  }
+
+  for (int64_t t = 0; t < my_tiles; ++t) {
+    const int s = static_cast<int>(t % kStages);
+    const float* tile = tiles + static_cast<size_t>(s) * tn * ld;
+    const int64_t row0 = (tile0 + t) * tn;
+    const int rows = static_cast<int>(min(static_cast<int64_t>(tn), A.n_cat - row0));
+    if (threadIdx.x == 0 && t + kPrefetch < my_tiles) issue_tile(t + kPrefetch);
+    __syncwarp();
+    mbar_wait(full + s, static_cast<uint32_t>((t / kStages) & 1));
+
+    [[maybe_unused]] float* IP = nullptr;
+    [[maybe_unused]] float* IA = nullptr;
+    [[maybe_unused]] float* IB = nullptr;
+    if constexpr (KIND >= KIND_PREF_HARD) {
+      // catalog-side halves of the logits for this tile (rows split over the 8 warps):
+      // IP[row][k] = i_row . P_k / 2 ; SOFT: IA[row] = hf sum_k IP_k P_k, IB likewise with N
+      IP = reinterpret_cast<float*>(smem_raw + L.IP);
+      if (KIND == KIND_PREF_SOFT) { IA = reinterpret_cast<float*>(smem_raw + L.IA); IB = reinterpret_cast<float*>(smem_raw + L.IB); }
+      // all warps must be done with the previous tile's IP / IA / IB
+      asm volatile("bar.sync 1, %0;" ::"r"(kThreads));
+      for (int rr = wid; rr < rows; rr += kWarpsPerCta) {
+        float x[NE];
+        R::load_s(x, tile + rr * ld, d, lane);
+        for (int g = 0; g < P; g += 8) {
+          float vals[8];
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            vals[kk] = 0.f;
+            if (g + kk < P) {
+              float row[NE];
+              R::load_s(row, sP + (g + kk) * stride, d, lane);
+              vals[kk] = R::dot(row, x);
+            }
+          }
+          const float v = warp_reduce_scatter8(vals, lane);
+          const int k = g + (lane >> 2);
+          if ((lane & 3) == 0 && k < P) IP[rr * ppad + k] = 0.5f * v;
+        }
+        if constexpr (KIND == KIND_PREF_SOFT) {
+          __syncwarp();
+          float ia[NE], ib[NE];
+#pragma unroll
+          for (int e = 0; e < NE; ++e) { ia[e] = 0.f; ib[e] = 0.f; }
+          for (int k = 0; k < P; ++k) {
+            const float z = hf * IP[rr * ppad + k];
+            float row[NE];
+            R::load_s(row, sP + k * stride, d, lane);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) ia[e] = fmaf(z, row[e], ia[e]);
+            R::load_s(row, sN + k * stride, d, lane);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) ib[e] = fmaf(z, row[e], ib[e]);
+          }
+          R::store(IA + rr * ld, ia, d, lane);
+          R::store(IB + rr * ld, ib, d, lane);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(kThreads));
+    }
+
+    for (int rg = 0; rg < rows; rg += 4) {
+      float mine = 0.f;     // score of (query myq, row rg + myj)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rr = rg + j;
+        if (rr < rows) {   // warp-uniform
+          float x[NE];
+          R::load_s(x, tile + rr * ld, d, lane);
+          float vals[QW];
+          if constexpr (KIND == KIND_DIST) {
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) {
+              float acc = 0.f;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) acc += dist_term(qa[qi][e] - x[e], l1);
+              vals[qi] = acc;
+            }
+          } else if constexpr (KIND == KIND_HYPER) {
+            // s_q = x . w_q for the 8 queries, reduced together and broadcast back
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) vals[qi] = R::dot(x, qb[qi]);
+            const float sr = warp_reduce_scatter8(vals, lane);
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) {
+              const float sq = __shfl_sync(FULL, sr, qi * 4);
+              float acc = 0.f;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) acc += dist_term(qa[qi][e] - (x[e] - sq * qb[qi][e]), l1);
+              vals[qi] = acc;
+            }
+          } else if constexpr (KIND == KIND_PREF_HARD) {
+            // arg-max preference of (query myq, this row): lane handles k = myj, myj + 4, ...
+            float best = -INFINITY;
+            int bk = 0x7fffffff;
+            const uint32_t gn = static_cast<uint32_t>(A.id_base + row0 + rr);
+            for (int k = myj; k < P; k += 4) {
+              float uu;
+              if (A.gumbel_u) uu = q_valid ? __ldg(A.gumbel_u + (my_query * A.n_cat + (row0 + rr)) * P + k) : 0.5f;
+              else uu = hash_uniform(A.seed, static_cast<uint32_t>(my_query), gn, static_cast<uint32_t>(k));
+              const float v = UPw[myq * ppad + k] + IP[rr * ppad + k] + gumbel_from_uniform(uu);
+              if (v > best) { best = v; bk = k; }
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+              const float ob = __shfl_xor_sync(FULL, best, o);
+              const int ok = __shfl_xor_sync(FULL, bk, o);
+              if (ob > best || (ob == best && ok < bk)) { best = ob; bk = ok; }
+            }
+            // phase 1: s_q = (u_q - x) . N[k*_q] ; phase 2: L((u_q - x) + hf (P[k*] - s N[k*]))
+            int ks[QW];
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) {
+              ks[qi] = __shfl_sync(FULL, bk, qi * 4);
+              float wv[NE];
+              R::load_s(wv, sN + ks[qi] * stride, d, lane);
+              float acc = 0.f;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) acc = fmaf(qa[qi][e] - x[e], wv[e], acc);
+              vals[qi] = acc;
+            }
+            const float sr = warp_reduce_scatter8(vals, lane);
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) {
+              const float sq = hf * __shfl_sync(FULL, sr, qi * 4);      // s = x . (hf N)
+              float wv[NE], pv[NE];
+              R::load_s(wv, sN + ks[qi] * stride, d, lane);
+              R::load_s(pv, sP + ks[qi] * stride, d, lane);
+              float acc = 0.f;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) acc += dist_term((qa[qi][e] - x[e]) + hf * (pv[e] - sq * wv[e]), l1);
+              vals[qi] = acc;
+            }
+          } else {
+            float ia[NE], ib[NE];
+            R::load_s(ia, IA + rr * ld, d, lane);
+            R::load_s(ib, IB + rr * ld, d, lane);
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) {
+              float acc = 0.f;
+#pragma unroll
+              for (int e = 0; e < NE; ++e) acc = fmaf(qa[qi][e] - x[e], qc[qi][e] + ib[e], acc);
+              vals[qi] = acc;
+            }
+            const float sr = warp_reduce_scatter8(vals, lane);
+#pragma unroll
+            for (int qi = 0; qi < QW; ++qi) {
+              const float sq = __shfl_sync(FULL, sr, qi * 4);
+              float acc = 0.f;
+#pragma unroll
+              for (int e = 0; e < NE; ++e)
+                acc += dist_term((qa[qi][e] - x[e]) + (qb[qi][e] + ia[e]) - sq * (qc[qi][e] + ib[e]), l1);
+              vals[qi] = acc;
+            }
+          }
+          const float sc = warp_reduce_scatter8(vals, lane);
+          if (myj == j) mine = sc;
+        }
+      }
+      // one candidate per lane: (my_query, row rg + myj)
+      const int rr = rg + myj;
+      const bool valid = q_valid && rr < rows;
+      const int64_t n_local = row0 + rr;
+      if constexpr (MODE == MODE_FULL) {
+        if (valid) A.out[my_query * A.ld_out + n_local] = mine;
+      } else if constexpr (MODE == MODE_RANK) {
+        if (valid && make_key(mine, static_cast<uint32_t>(A.id_base + n_local)) < gold_key) ++cnt;
+      } else {
+        const uint64_t key = make_key(mine, static_cast<uint32_t>(A.id_base + n_local));
+        bool pass = valid && key < thr;
+        if (pass && f_hi > f_lo) pass = !filtered(A.filter_ids, f_lo, f_hi, static_cast<int32_t>(A.id_base + n_local));
+        unsigned mask = __ballot_sync(FULL, pass);
+        while (mask) {
+          const int src = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const uint64_t ckey = __shfl_sync(FULL, key, src);
+          const int cq = src >> 2;
+          uint64_t* list = lists + cq * A.k;
+          if (ckey < list[A.k - 1]) {        // re-check: the threshold may have tightened
+            list_insert(list, A.k, ckey, lane);
+            const uint64_t nthr = list[A.k - 1];
+            if (myq == cq) thr = nthr;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+
+  if constexpr (MODE == MODE_TOPK) {
+    __syncwarp();
+    // partial lists of this catalog range: part_keys[split][q][k]
+    for (int i = lane; i < QW * A.k; i += 32) {
+      const int64_t q = q0 + i / A.k;
+      if (q < A.nq) A.part_keys[(static_cast<int64_t>(blockIdx.y) * A.nq + q) * A.k + (i % A.k)] = lists[i];
+    }
+  }
+  if constexpr (MODE == MODE_RANK) {
+    cnt += __shfl_xor_sync(FULL, cnt, 1);
+    cnt += __shfl_xor_sync(FULL, cnt, 2);
+    if (myj == 0 && q_valid && cnt) atomicAdd(A.counts + my_query, cnt);
+  }
+}
+
+// K-way merge: in [n_lists][nq][k] ascending lists -> out [nq][k].  One warp per query.
+__global__ void __launch_bounds__(256)
+k_merge_topk(const uint64_t* __restrict__ in, int n_lists, int64_t nq, int k, uint64_t* __restrict__ out) {
+  extern __shared__ __align__(8) unsigned char merge_smem[];
+  uint64_t* lists = reinterpret_cast<uint64_t*>(merge_smem);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t q = static_cast<int64_t>(blockIdx.x) * 8 + wid;
+  if (q >= nq) return;
+  uint64_t* list = lists + wid * k;
+  for (int i = lane; i < k; i += 32) list[i] = KEY_INF;
+  __syncwarp();
+  for (int l = 0; l < n_lists; ++l) {
+    const uint64_t* src = in + (static_cast<int64_t>(l) * nq + q) * k;
+    for (int i = 0; i < k; ++i) {
+      const uint64_t x = __ldg(src + i);
+      if (x >= list[k - 1]) break;     // ascending source: nothing further can enter
+      list_insert(list, k, x, lane);
+    }
+  }
+  for (int i = lane; i < k; i += 32) out[q * k + i] = list[i];
+}
+
+// KTUP catalog for evaluateRec: ie[i] = Item[i] + Ent[item2ent[i]]  (jTransUP.py:177-181)
+__global__ void __launch_bounds__(256)
+k_ktup_items(const kgrec_tables T, int64_t i0, int64_t n, float* __restrict__ out, int64_t ld_out) {
+  const int64_t total = n * T.dim;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t i = idx / T.dim;
+    const int j = static_cast<int>(idx - i * T.dim);
+    const int64_t a = __ldg(T.item2ent + i0 + i);
+    out[i * ld_out + j] = __ldg(T.item + (i0 + i) * T.ld + j) + __ldg(T.ent + a * T.ld + j);
+  }
+}
+
+// ===========================================================================================
+// host side
+// ===========================================================================================
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct EvalPlan {
+  int kind, nch, tn, n_splits;
+  int64_t n_qtiles;
+  size_t smem;
+};
+
+static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const float* cat, int64_t cat_ld,
+                     int64_t nq, int64_t n_cat, int k, bool have_qvec, EvalArgs* A, EvalPlan* pl) {
+  if (!T) { set_error("tables is NULL"); return KGREC_ERR_INVALID; }
+  if (!cat || n_cat <= 0 || nq <= 0) { set_error("empty catalog / query set"); return KGREC_ERR_INVALID; }
+  const int d = T->dim;
+  if (d <= 0 || d > 256) { set_error("eval: embedding_size %d outside [1, 256]", d); return KGREC_ERR_UNSUPPORTED; }
+  if (d % 4 || cat_ld % 4 || cat_ld < d || !aligned16(cat)) {
+    set_error("eval: catalog must be 16-byte aligned with embedding_size and leading dimension multiples of 4");
+    return KGREC_ERR_UNSUPPORTED;
+  }
+  A->ktup = 0;
+  switch (model) {
+    case KGREC_TRANSE: case KGREC_TRANSR: pl->kind = KIND_DIST; break;
+    case KGREC_TRANSH: pl->kind = KIND_HYPER; break;
+    case KGREC_KTUP: A->ktup = 1; /* fallthrough */
+    case KGREC_TUP: pl->kind = (side == KGREC_SIDE_REC) ? (T->use_gumbel ? KIND_PREF_HARD : KIND_PREF_SOFT) : KIND_HYPER; break;
+    default: set_error("unknown model %d", model); return KGREC_ERR_INVALID;
+  }
+  if (model == KGREC_TRANSR && !have_qvec) {
+    set_error("TransR eval needs explicit query vectors and a catalog projected by the relation matrix");
+    return KGREC_ERR_INVALID;
+  }
+  const bool rec = side == KGREC_SIDE_REC;
+  if (rec != (pl->kind >= KIND_PREF_HARD)) { set_error("side %d does not fit model %d", side, model); return KGREC_ERR_INVALID; }
+  bool al = true;
+  auto chk = [&](const void* p) { if (!p || !aligned16(p)) al = false; };
+  if (rec) { chk(T->user); chk(T->pref); chk(T->pref_norm); if (A->ktup) { chk(T->rel); chk(T->norm); } }
+  else if (!have_qvec) { chk(T->ent); chk(T->rel); if (pl->kind == KIND_HYPER) chk(T->norm); }
+  if (!al || T->ld % 4) { set_error("eval: a table this model needs is NULL or not 16-byte aligned"); return KGREC_ERR_INVALID; }
+  if (rec && (T->n_pref <= 0 || T->n_pref > kMaxPref)) { set_error("preference_total out of range"); return KGREC_ERR_UNSUPPORTED; }
+  if (mode == MODE_TOPK && (k <= 0 || k > 128)) { set_error("topn %d outside [1, 128]", k); return KGREC_ERR_UNSUPPORTED; }
+  pl->nch = d <= 128 ? 1 : 2;
+  pl->n_qtiles = (nq + TQ - 1) / TQ;
+  // tile rows: ~16 KB per stage
+  int tn = static_cast<int>((16 * 1024) / (cat_ld * sizeof(float)));
+  tn = tn < 4 ? 4 : (tn > 64 ? 64 : tn);
+  tn &= ~3;
+  pl->tn = tn;
+  const int64_t n_tiles = (n_cat + tn - 1) / tn;
+  int64_t splits = (2 * static_cast<int64_t>(sm_count()) + pl->n_qtiles - 1) / pl->n_qtiles;
+  if (mode == MODE_FULL || mode == MODE_RANK) {
+    // no merge needed: splits are free
+  }
+  splits = splits < 1 ? 1 : (splits > n_tiles ? n_tiles : splits);
+  if (splits > 65535) splits = 65535;
+  pl->n_splits = static_cast<int>(splits);
+  pl->smem = eval_smem_layout(pl->kind, mode, d, cat_ld, T->n_pref, tn, k).total;
+  if (pl->smem > 220 * 1024) { set_error("eval: shared-memory budget exceeded (%zu bytes)", pl->smem); return KGREC_ERR_UNSUPPORTED; }
+  A->T = *T;
+  A->side = side;
+  A->nq = nq;
+  A->cat = cat;
+  A->cat_ld = cat_ld;
+  A->n_cat = n_cat;
+  A->n_splits = pl->n_splits;
+  A->tn = tn;
+  A->k = k;
+  return KGREC_OK;
+}
+
+template <int MODE>
+static int launch_eval(const EvalArgs& A, const EvalPlan& pl, cudaStream_t st) {
+  const dim3 grid(static_cast<unsigned>(pl.n_qtiles), static_cast<unsigned>(pl.n_splits));
+#define KGREC_EVAL_CASE(KINDV, NCHV)                                                                          \
+  {                                                                                                           \
+    auto kern = A.T.l1 ? k_eval<KINDV, NCHV, MODE, true> : k_eval<KINDV, NCHV, MODE, false>;                  \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem))); \
+    kern<<<grid, kEvalThreads, pl.smem, st>>>(A);                                                             \
+  }
+  switch (pl.kind * 2 + (pl.nch - 1)) {
+    case 0: KGREC_EVAL_CASE(KIND_DIST, 1) break;
+    case 1: KGREC_EVAL_CASE(KIND_DIST, 2) break;
+    case 2: KGREC_EVAL_CASE(KIND_HYPER, 1) break;
+    case 3: KGREC_EVAL_CASE(KIND_HYPER, 2) break;
+    case 4: KGREC_EVAL_CASE(KIND_PREF_HARD, 1) break;
+    case 5: KGREC_EVAL_CASE(KIND_PREF_HARD, 2) break;
+    case 6: KGREC_EVAL_CASE(KIND_PREF_SOFT, 1) break;
+    default: KGREC_EVAL_CASE(KIND_PREF_SOFT, 2) break;
+  }
+#undef KGREC_EVAL_CASE
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}
+
+}  // namespace kgrec
+
+using namespace kgrec;
+
+extern "C" int64_t kgrec_eval_workspace_bytes(int64_t nq, int32_t k) {
+  // worst case number of catalog splits is 2 * SMs (eval_plan)
+  const int64_t splits = 2 * static_cast<int64_t>(sm_count());
+  return splits * (nq > 0 ? nq : 1) * (k > 0 ? k : 1) * static_cast<int64_t>(sizeof(uint64_t));
+}
+
+extern "C" int kgrec_eval_scores(const kgrec_tables* tables, int model, int side, const void* q, const void* r,
+                                 int idx_bytes, const float* qvec, int64_t nq, const float* cat, int64_t cat_ld,
+                                 int64_t n_cat, const float* gumbel_u, uint64_t seed, float* out, int64_t ld_out,
+                                 kgrec_stream_t stream) {
+  EvalArgs A{};
+  EvalPlan pl{};
+  int rc = eval_plan(tables, model, side, MODE_FULL, cat, cat_ld, nq, n_cat, 0, qvec != nullptr, &A, &pl);
+  if (rc) return rc;
+  if (!out || ld_out < n_cat) { set_error("bad out / ld_out"); return KGREC_ERR_INVALID; }
+  if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
+  A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
+  A.gumbel_u = gumbel_u; A.seed = seed; A.id_base = 0;
+  A.out = out; A.ld_out = ld_out;
+  return launch_eval<MODE_FULL>(A, pl, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int kgrec_eval_topk(const kgrec_tables* tables, int model, int side, const void* q, const void* r,
+                               int idx_bytes, const float* qvec, int64_t nq, const float* cat, int64_t cat_ld,
+                               int64_t n_cat, int64_t id_base, int32_t k, const int64_t* filter_ptr,
+                               const int32_t* filter_ids, const float* gumbel_u, uint64_t seed, uint64_t* out_keys,
+                               void* workspace, int64_t workspace_bytes, kgrec_stream_t stream) {
+  EvalArgs A{};
+  EvalPlan pl{};
+  int rc = eval_plan(tables, model, side, MODE_TOPK, cat, cat_ld, nq, n_cat, k, qvec != nullptr, &A, &pl);
+  if (rc) return rc;
+  if (!out_keys) { set_error("out_keys is NULL"); return KGREC_ERR_INVALID; }
+  if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
+  if (id_base < 0 || id_base + n_cat > 0xffffffffll) { set_error("catalog ids must fit 32 bits"); return KGREC_ERR_INVALID; }
+  const int64_t need = static_cast<int64_t>(pl.n_splits) * nq * k * static_cast<int64_t>(sizeof(uint64_t));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
+  A.gumbel_u = gumbel_u; A.seed = seed; A.id_base = id_base;
+  A.filter_ptr = filter_ptr; A.filter_ids = filter_ids;
+  if (pl.n_splits == 1) {
+    A.part_keys = out_keys;
+    return launch_eval<MODE_TOPK>(A, pl, st);
+  }
+  if (!workspace || workspace_bytes < need) {
+    set_error("eval_topk workspace too small (%lld < %lld bytes)", static_cast<long long>(workspace_bytes), static_cast<long long>(need));
+    return KGREC_ERR_INVALID;
+  }
+  A.part_keys = static_cast<uint64_t*>(workspace);
+  if ((rc = launch_eval<MODE_TOPK>(A, pl, st))) return rc;
+  return kgrec_merge_topk(A.part_keys, pl.n_splits, nq, k, out_keys, stream);
+}
+
+extern "C" int kgrec_merge_topk(const uint64_t* in_keys, int32_t n_lists, int64_t nq, int32_t k, uint64_t* out_keys,
+                                kgrec_stream_t stream) {
+  if (!in_keys || !out_keys || n_lists < 1 || nq < 0 || k < 1 || k > 128) { set_error("merge_topk: bad arguments"); return KGREC_ERR_INVALID; }
+  if (nq == 0) return KGREC_OK;
+  k_merge_topk<<<static_cast<unsigned>((nq + 7) / 8), 256, 8 * k * sizeof(uint64_t), static_cast<cudaStream_t>(stream)>>>(
+      in_keys, n_lists, nq, k, out_keys);
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}
+
+extern "C" int kgrec_eval_rank_count(const kgrec_tables* tables, int model, int side, const void* q, const void* r,
+                                     int idx_bytes, const float* qvec, int64_t nq, const float* cat, int64_t cat_ld,
+                                     int64_t n_cat, int64_t id_base, const float* gold_scores, const int32_t* gold_ids,
+                                     int32_t* counts, kgrec_stream_t stream) {
+  EvalArgs A{};
+  EvalPlan pl{};
+  int rc = eval_plan(tables, model, side, MODE_RANK, cat, cat_ld, nq, n_cat, 0, qvec != nullptr, &A, &pl);
+  if (rc) return rc;
+  if (!gold_scores || !gold_ids || !counts) { set_error("rank_count: NULL argument"); return KGREC_ERR_INVALID; }
+  if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
+  A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
+  A.id_base = id_base; A.seed = 0;
+  A.gold_scores = gold_scores; A.gold_ids = gold_ids; A.counts = counts;
+  return launch_eval<MODE_RANK>(A, pl, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int kgrec_ktup_item_table(const kgrec_tables* tables, int64_t item_begin, int64_t n_items, float* out,
+                                     int64_t ld_out, kgrec_stream_t stream) {
+  if (!tables || !tables->item || !tables->ent || !tables->item2ent || !out || ld_out < tables->dim) {
+    set_error("ktup_item_table: bad arguments");
+    return KGREC_ERR_INVALID;
+  }
+  if (n_items <= 0) return KGREC_OK;
+  const int64_t total = n_items * tables->dim;
+  const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
+  k_ktup_items<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*tables, item_begin, n_items, out, ld_out);
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}

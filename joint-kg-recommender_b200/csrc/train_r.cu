@@ -1,0 +1,5 @@
+// kernels of family R (one translation unit per family so they compile in parallel)
+#include "train_dev.cuh"
+namespace kgrec {
+KGREC_INSTANTIATE_FAMILY(FAM_R)
+}

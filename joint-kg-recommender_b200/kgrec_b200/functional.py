@@ -1,0 +1,248 @@
+"""torch.autograd glue over the C ABI (include/kgrec_b200.h).
+
+Everything here runs the CUDA kernels; tensors on the CPU are rejected with a
+RuntimeError (there is no CPU path).  PyTorch supplies device memory, the
+current stream and autograd bookkeeping -- nothing else.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Grads, Tables
+
+_TABLE_FIELDS = ("ent", "rel", "norm", "proj", "user", "item", "pref", "pref_norm")
+# which tables each model reads, in the order autograd sees them
+MODEL_TABLES = {
+    _lib.TRANSE: ("ent", "rel"),
+    _lib.TRANSH: ("ent", "rel", "norm"),
+    _lib.TRANSR: ("ent", "rel", "proj"),
+    _lib.TUP: ("user", "item", "pref", "pref_norm"),
+    _lib.KTUP: ("user", "item", "ent", "rel", "norm", "pref", "pref_norm"),
+}
+# tables whose gradient is a gathered-row ("slot") gradient; the others are small dense tables
+_SLOT_TABLES = {
+    _lib.TRANSE: ("ent", "rel"),
+    _lib.TRANSH: ("ent", "rel", "norm"),
+    _lib.TRANSR: ("ent", "rel"),
+    _lib.TUP: ("user", "item"),
+    _lib.KTUP: ("user", "item", "ent"),
+}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _check_table(name, w):
+    if not w.is_cuda:
+        raise RuntimeError("kgrec_b200: table '%s' is on %s; the engine has no CPU path -- move the module "
+                           "to a CUDA device" % (name, w.device))
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        raise RuntimeError("kgrec_b200: table '%s' must be contiguous float32" % name)
+
+
+def make_tables(weights, dim, l1, use_gumbel=False, item2ent=None):
+    """Build the kgrec_tables struct from a {name: tensor} dict of [rows, d] tables."""
+    t = Tables()
+    t.dim = dim
+    t.ld = dim
+    t.l1 = int(bool(l1))
+    t.use_gumbel = int(bool(use_gumbel))
+    for name in _TABLE_FIELDS:
+        w = weights.get(name)
+        if w is None:
+            continue
+        _check_table(name, w)
+        setattr(t, name, w.data_ptr())
+    for name, field in (("ent", "n_ent"), ("rel", "n_rel"), ("user", "n_user"), ("item", "n_item")):
+        if weights.get(name) is not None:
+            setattr(t, field, weights[name].shape[0])
+    if weights.get("pref") is not None:
+        t.n_pref = weights["pref"].shape[0]
+    if item2ent is not None:
+        if item2ent.dtype != torch.int32 or not item2ent.is_cuda:
+            raise RuntimeError("kgrec_b200: item2ent must be an int32 CUDA tensor")
+        t.item2ent = item2ent.data_ptr()
+    return t
+
+
+def as_index(x, device):
+    """Index arrays arrive as the drivers build them (LongTensor, maybe on the host)."""
+    if not torch.is_tensor(x):
+        x = torch.as_tensor(x)
+    if x.dtype not in (torch.int64, torch.int32):
+        x = x.long()
+    if x.device != device:
+        x = x.to(device, non_blocking=True)
+    return x.contiguous().view(-1)
+
+
+def _idx_bytes(*xs):
+    sizes = {x.element_size() for x in xs if x is not None}
+    if len(sizes) != 1:
+        raise RuntimeError("kgrec_b200: index arrays must share one integer width")
+    return sizes.pop()
+
+
+def _alloc_grads(model, weights, n, mode, dim):
+    """Gradient buffers for one backward call.  Returns (Grads struct, {name: tensor})."""
+    dev = weights[MODEL_TABLES[model][0]].device
+    g = Grads()
+    g.mode = 1 if mode == "dense" else 0
+    bufs = {}
+    slots = {"ent": 2 * n if model != _lib.KTUP else n, "rel": n, "norm": n, "user": n, "item": n}
+    for name in MODEL_TABLES[model]:
+        w = weights[name]
+        if model == _lib.KTUP and name in ("rel", "norm"):
+            continue                       # shares the pref / pref_norm gradient
+        if name in _SLOT_TABLES[model] and mode != "dense":
+            buf = torch.empty((slots[name], dim), dtype=torch.float32, device=dev)
+        else:
+            buf = torch.zeros_like(w)
+        bufs[name] = buf
+        setattr(g, name, buf.data_ptr())
+    return g, bufs
+
+
+def _finish_grads(model, weights, bufs, idx, mode, needs):
+    """Turn kernel outputs into what autograd returns for each table."""
+    out = {}
+    for name in MODEL_TABLES[model]:
+        if not needs.get(name, False):
+            out[name] = None
+            continue
+        if model == _lib.KTUP and name in ("rel", "norm"):
+            out[name] = bufs["pref" if name == "rel" else "pref_norm"]
+            continue
+        buf = bufs[name]
+        if name in _SLOT_TABLES[model] and mode != "dense":
+            w = weights[name]
+            out[name] = torch.sparse_coo_tensor(idx[name].view(1, -1), buf, size=tuple(w.shape))
+        else:
+            out[name] = buf
+    return out
+
+
+class _Ctx:
+    """Per-call constants shared by forward and backward."""
+
+    def __init__(self, model, dim, l1, use_gumbel, item2ent, grad_mode, seed):
+        self.model, self.dim, self.l1, self.use_gumbel = model, dim, l1, use_gumbel
+        self.item2ent, self.grad_mode, self.seed = item2ent, grad_mode, seed
+
+
+def _slot_indices(model, a, b, c, item2ent):
+    if model in (_lib.TRANSE, _lib.TRANSH, _lib.TRANSR):
+        idx = {"ent": torch.cat([a, b]).long(), "rel": c.long()}
+        if model == _lib.TRANSH:
+            idx["norm"] = idx["rel"]
+        return idx
+    idx = {"user": a.long(), "item": b.long()}
+    if model == _lib.KTUP:
+        idx["ent"] = item2ent[b.long()].long()
+    return idx
+
+
+class ScoreFunction(torch.autograd.Function):
+    """scores = model(a, b, c): kgrec_score_fwd / kgrec_score_bwd."""
+
+    @staticmethod
+    def forward(ctx, cfg, a, b, c, gumbel_u, status, *tables):
+        names = MODEL_TABLES[cfg.model]
+        weights = dict(zip(names, tables))
+        T = make_tables(weights, cfg.dim, cfg.l1, cfg.use_gumbel, cfg.item2ent)
+        n = a.numel()
+        scores = torch.empty(n, dtype=torch.float32, device=a.device)
+        lib = _lib.load()
+        _lib.check(lib.kgrec_score_fwd(C.byref(T), cfg.model, _ptr(a), _ptr(b), _ptr(c), _idx_bytes(a, b, c), n,
+                                       _ptr(gumbel_u), cfg.seed, _ptr(scores), _ptr(status), _stream()))
+        ctx.cfg = cfg
+        ctx.idx = (a, b, c, gumbel_u)
+        ctx.save_for_backward(*tables)
+        return scores
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        cfg = ctx.cfg
+        a, b, c, gumbel_u = ctx.idx
+        tables = ctx.saved_tensors
+        names = MODEL_TABLES[cfg.model]
+        weights = dict(zip(names, tables))
+        needs = dict(zip(names, ctx.needs_input_grad[6:]))
+        n = a.numel()
+        T = make_tables(weights, cfg.dim, cfg.l1, cfg.use_gumbel, cfg.item2ent)
+        G, bufs = _alloc_grads(cfg.model, weights, n, cfg.grad_mode, cfg.dim)
+        gs = grad_scores.contiguous().float()
+        lib = _lib.load()
+        _lib.check(lib.kgrec_score_bwd(C.byref(T), cfg.model, _ptr(a), _ptr(b), _ptr(c), _idx_bytes(a, b, c), n,
+                                       _ptr(gumbel_u), cfg.seed, _ptr(gs), C.byref(G), _stream()))
+        idx = _slot_indices(cfg.model, a, b, c, cfg.item2ent) if cfg.grad_mode != "dense" else {}
+        out = _finish_grads(cfg.model, weights, bufs, idx, cfg.grad_mode, needs)
+        return (None, None, None, None, None, None) + tuple(out[nm] for nm in names)
+
+
+class RankLossFunction(torch.autograd.Function):
+    """loss[b], pos, neg = fused pos + K-negative scoring and margin / BPR loss."""
+
+    @staticmethod
+    def forward(ctx, cfg, pos, neg, n_neg, batch_pos, loss_kind, param, gumbel_u, status, *tables):
+        names = MODEL_TABLES[cfg.model]
+        weights = dict(zip(names, tables))
+        T = make_tables(weights, cfg.dim, cfg.l1, cfg.use_gumbel, cfg.item2ent)
+        pa, pb, pc = pos
+        na, nb, nc = neg
+        n_pos = pa.numel()
+        dev = pa.device
+        lib = _lib.load()
+        pos_s = torch.empty(n_pos, dtype=torch.float32, device=dev)
+        neg_s = torch.empty(n_pos * n_neg, dtype=torch.float32, device=dev)
+        n_batches = (n_pos + batch_pos - 1) // batch_pos
+        loss = torch.empty(n_batches, dtype=torch.float32, device=dev)
+        ws = torch.empty(max(1, n_pos), dtype=torch.float32, device=dev)
+        _lib.check(lib.kgrec_rank_loss_fwd(
+            C.byref(T), cfg.model, _ptr(pa), _ptr(pb), _ptr(pc), _ptr(na), _ptr(nb), _ptr(nc),
+            _idx_bytes(pa, pb, pc, na, nb, nc), n_pos, n_neg, batch_pos, loss_kind, float(param),
+            _ptr(gumbel_u), cfg.seed, _ptr(pos_s), _ptr(neg_s), _ptr(loss), _ptr(ws), _ptr(status), _stream()))
+        ctx.cfg = cfg
+        ctx.args = (pos, neg, n_neg, batch_pos, loss_kind, float(param), gumbel_u, pos_s, neg_s)
+        ctx.save_for_backward(*tables)
+        ctx.mark_non_differentiable(pos_s, neg_s)
+        return loss, pos_s, neg_s
+
+    @staticmethod
+    def backward(ctx, grad_loss, _gp, _gn):
+        cfg = ctx.cfg
+        pos, neg, n_neg, batch_pos, loss_kind, param, gumbel_u, pos_s, neg_s = ctx.args
+        pa, pb, pc = pos
+        na, nb, nc = neg
+        tables = ctx.saved_tensors
+        names = MODEL_TABLES[cfg.model]
+        weights = dict(zip(names, tables))
+        needs = dict(zip(names, ctx.needs_input_grad[9:]))
+        n_pos = pa.numel()
+        n = n_pos * (1 + n_neg)
+        gl = grad_loss.reshape(-1).contiguous().float()     # upstream per loss batch, stays on the device
+        T = make_tables(weights, cfg.dim, cfg.l1, cfg.use_gumbel, cfg.item2ent)
+        G, bufs = _alloc_grads(cfg.model, weights, n, cfg.grad_mode, cfg.dim)
+        lib = _lib.load()
+        _lib.check(lib.kgrec_rank_loss_bwd(
+            C.byref(T), cfg.model, _ptr(pa), _ptr(pb), _ptr(pc), _ptr(na), _ptr(nb), _ptr(nc),
+            _idx_bytes(pa, pb, pc, na, nb, nc), n_pos, n_neg, batch_pos, loss_kind, param,
+            _ptr(gumbel_u), cfg.seed, _ptr(pos_s), _ptr(neg_s), 1.0, _ptr(gl), C.byref(G), _stream()))
+        idx = {}
+        if cfg.grad_mode != "dense":
+            pi = _slot_indices(cfg.model, pa, pb, pc, cfg.item2ent)
+            ni = _slot_indices(cfg.model, na, nb, nc, cfg.item2ent)
+            for k in pi:
+                if k == "ent" and cfg.model != _lib.KTUP:
+                    # slot order: heads of all n triples, then tails
+                    idx[k] = torch.cat([pa, na, pb, nb]).long()
+                else:
+                    idx[k] = torch.cat([pi[k], ni[k]])
+        out = _finish_grads(cfg.model, weights, bufs, idx, cfg.grad_mode, needs)
+        return (None,) * 9 + tuple(out[nm] for nm in names)

@@ -1,0 +1,145 @@
+"""Shared machinery of the drop-in model classes.
+
+The five classes in this package keep the constructors, attribute modules,
+method names and ``state_dict`` keys of the reference classes
+(jTransUP/models/{transE,transH,transR,transUP,jTransUP}.py) so the
+reference's drivers can call them unchanged, but every method body is one call
+into the CUDA library: there are no torch ops on the scoring path.
+
+Extensions over the reference (all optional, defaults reproduce the reference):
+  * ``grad_mode``  'dense' (default: ``param.grad`` exactly as the reference's
+    autograd lays it out, works with the unchanged ModelTrainer) or 'sparse'
+    (row gradients as uncoalesced sparse COO tensors, no O(table) work);
+  * ``rank_loss`` the fused positive + K-negative + margin/BPR loss;
+  * ``topk`` / ``rank_counts`` on-chip reductions of the evaluate* matrices;
+  * explicit Gumbel noise (``gumbel_u=``) for bit-reproducible parity runs.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .. import functional as KF
+from .. import evaluation as KE
+
+
+def _init_table(rows, dim, normalize=True):
+    """xavier_uniform then row-wise L2 normalisation (transE.py:31-46 and peers)."""
+    w = torch.empty(rows, dim, dtype=torch.float32)
+    nn.init.xavier_uniform_(w)
+    if normalize:
+        w = torch.nn.functional.normalize(w, p=2, dim=1)
+    return w
+
+
+def _embedding(weight, **kw):
+    emb = nn.Embedding(weight.shape[0], weight.shape[1], **kw)
+    emb.weight = nn.Parameter(weight)
+    return emb
+
+
+class KGRecModule(nn.Module):
+    """Common base: table registry, grad switches, device handling, counters."""
+
+    MODEL = None            # _lib.TRANSE ...
+    TABLES = {}             # kernel table name -> attribute name of the nn.Embedding
+
+    def __init__(self):
+        super().__init__()
+        self.is_pretrained = False
+        self.grad_mode = os.environ.get("KGREC_GRAD_MODE", "dense")
+        self.use_st_gumbel = False
+        self._seed_counter = 0
+        self._status = None
+        self._item2ent = None
+        self.kernel_launches = 0        # kernels of this library enqueued through the module
+
+    # -- reference API --------------------------------------------------------
+    def disable_grad(self):
+        for _, param in self.named_parameters():
+            param.requires_grad = False
+
+    def enable_grad(self):
+        for _, param in self.named_parameters():
+            param.requires_grad = True
+
+    # -- plumbing -------------------------------------------------------------
+    def _finish_init(self):
+        """The reference moves every table to the GPU when one is visible (misc.py:11-16)."""
+        if torch.cuda.is_available():
+            self.cuda()
+
+    def _weights(self):
+        return {k: getattr(self, attr).weight for k, attr in self.TABLES.items()}
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _require_cuda(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                "kgrec_b200: %s lives on %s.  The scoring engine is CUDA-only (sm_100a); "
+                "there is no CPU or PyTorch fallback." % (type(self).__name__, dev))
+        return dev
+
+    def _status_buf(self, dev):
+        if self._status is None or self._status.device != dev:
+            self._status = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self._status
+
+    def check_indices(self):
+        """Raise if any kernel since the last check saw an out-of-range id (device sync)."""
+        if self._status is not None and int(self._status.item()) != 0:
+            self._status.zero_()
+            raise IndexError("kgrec_b200: an index was out of range for its table")
+
+    def _next_seed(self):
+        self._seed_counter += 1
+        return (int(torch.initial_seed()) * 1000003 + self._seed_counter) & 0xFFFFFFFFFFFFFFFF
+
+    def _cfg(self, model=None, seed=0):
+        return KF._Ctx(self.MODEL if model is None else model, self.embedding_size, self.L1_flag,
+                       self.use_st_gumbel, self._item2ent, self.grad_mode, seed)
+
+    def _tables_for(self, model):
+        w = self._weights()
+        return [w[name] for name in KF.MODEL_TABLES[model]]
+
+    def _score(self, model, a, b, c, gumbel_u=None):
+        dev = self._require_cuda()
+        a, b = KF.as_index(a, dev), KF.as_index(b, dev)
+        c = KF.as_index(c, dev) if c is not None else None
+        if gumbel_u is not None:
+            gumbel_u = gumbel_u.to(dev, torch.float32).contiguous()
+        seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
+        self.kernel_launches += 1
+        return KF.ScoreFunction.apply(self._cfg(model, seed), a, b, c, gumbel_u, self._status_buf(dev),
+                                      *self._tables_for(model))
+
+    def _rank_loss(self, model, pos, neg, loss, param, batch_pos=None, gumbel_u=None):
+        dev = self._require_cuda()
+        pos = tuple(KF.as_index(x, dev) if x is not None else None for x in pos)
+        neg = tuple(KF.as_index(x, dev) if x is not None else None for x in neg)
+        n_pos = pos[0].numel()
+        if n_pos == 0 or neg[0].numel() % n_pos:
+            raise ValueError("negatives must be a whole multiple of the positives")
+        n_neg = neg[0].numel() // n_pos
+        kind = {"margin": _lib.LOSS_MARGIN, "bpr": _lib.LOSS_BPR}[loss]
+        if gumbel_u is not None:
+            gumbel_u = gumbel_u.to(dev, torch.float32).contiguous()
+        seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
+        self.kernel_launches += 2
+        return KF.RankLossFunction.apply(self._cfg(model, seed), pos, neg, n_neg, batch_pos or n_pos, kind, param,
+                                         gumbel_u, self._status_buf(dev), *self._tables_for(model))
+
+    # -- evaluation helpers ------------------------------------------------------
+    def _eval(self, model, side, q, r, mode, **kw):
+        dev = self._require_cuda()
+        q = KF.as_index(q, dev) if q is not None else None
+        r = KF.as_index(r, dev) if r is not None else None
+        T = KF.make_tables(self._weights(), self.embedding_size, self.L1_flag, self.use_st_gumbel, self._item2ent)
+        self.kernel_launches += 1
+        return KE.run(T, model, side, q, r, mode, **kw)

@@ -1,0 +1,121 @@
+"""KTUP (`-model_type jtransup`) on the CUDA engine.  Mirrors jTransUP/models/jTransUP.py
+(constructor 25-112, paddingItems 114-120, forward 122-161, evaluateRec 163-191,
+evaluateHead/Tail 193-247, getPreferences 250-260)."""
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from .. import functional as KF
+from .base import _embedding, _init_table
+from .transUP import RecModelBase
+
+
+def build_model(FLAGS, user_total, item_total, entity_total, relation_total, i_map=None, e_map=None, new_map=None):
+    return jTransUPModel(L1_flag=FLAGS.L1_flag, embedding_size=FLAGS.embedding_size, user_total=user_total,
+                         item_total=item_total, entity_total=entity_total, relation_total=relation_total,
+                         i_map=i_map, new_map=new_map, isShare=FLAGS.share_embeddings,
+                         use_st_gumbel=FLAGS.use_st_gumbel)
+
+
+class jTransUPModel(RecModelBase):
+    MODEL = _lib.KTUP
+    TABLES = {"user": "user_embeddings", "item": "item_embeddings", "ent": "ent_embeddings",
+              "rel": "rel_embeddings", "norm": "norm_embeddings",
+              "pref": "pref_embeddings", "pref_norm": "pref_norm_embeddings"}
+
+    def __init__(self, L1_flag, embedding_size, user_total, item_total, entity_total, relation_total,
+                 i_map, new_map, isShare, use_st_gumbel):
+        super().__init__()
+        self.L1_flag = L1_flag
+        self.is_share = isShare
+        self.use_st_gumbel = use_st_gumbel
+        self.embedding_size = embedding_size
+        self.user_total = user_total
+        self.item_total = item_total
+        self.ent_total = entity_total + 1          # + zero padding row for unaligned items
+        self.rel_total = relation_total
+        self.i_map = i_map
+        self.new_map = new_map
+        d = embedding_size
+        self.user_embeddings = _embedding(_init_table(user_total, d))
+        self.item_embeddings = _embedding(_init_table(item_total, d))
+        self.pref_embeddings = _embedding(_init_table(relation_total, d))
+        self.pref_norm_embeddings = _embedding(_init_table(relation_total, d))
+        ent = torch.cat([_init_table(entity_total, d), torch.zeros(1, d)], dim=0)
+        self.ent_embeddings = _embedding(ent, padding_idx=self.ent_total - 1)
+        self.rel_embeddings = _embedding(_init_table(relation_total, d))
+        self.norm_embeddings = _embedding(_init_table(relation_total, d))
+        # paddingItems (jTransUP.py:114-120) as a device lookup table built once:
+        # item -> aligned entity row, unaligned -> the padding row
+        pad = self.ent_total - 1
+        table = torch.full((item_total,), pad, dtype=torch.int32)
+        if i_map is not None and new_map is not None:
+            for it in range(item_total):
+                if it in i_map:
+                    ent_id = new_map[i_map[it]][0]
+                    table[it] = ent_id if ent_id != -1 else pad
+        self.register_buffer("item2ent", table, persistent=False)
+        self._finish_init()
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._item2ent = self.item2ent           # follow .cuda() / .to()
+        return out
+
+    def paddingItems(self, i_ids, pad_index):
+        """Reference helper kept for API parity; the kernels use the device table."""
+        t = self.item2ent.cpu()
+        return [int(t[int(i)]) for i in i_ids]
+
+    def _mix_tables(self):
+        return (self.pref_embeddings.weight + self.rel_embeddings.weight,
+                self.pref_norm_embeddings.weight + self.norm_embeddings.weight, 0.5)
+
+    def _pair_vectors(self, u_id, i_ids):
+        u, i_e = super()._pair_vectors(u_id, i_ids)
+        dev = self.device
+        e = self.ent_embeddings.weight[self.item2ent[KF.as_index(i_ids, dev).long()].long()]
+        return u, i_e + e
+
+    def forward(self, ratings, triples, is_rec=True, gumbel_u=None):
+        if is_rec and ratings is not None:
+            u_ids, i_ids = ratings
+            return self._score(_lib.KTUP, u_ids, i_ids, None, gumbel_u)
+        if not is_rec and triples is not None:
+            h, t, r = triples
+            return self._score(_lib.TRANSH, h, t, r)         # jTransUP.py:144-157
+        raise NotImplementedError
+
+    def kg_rank_loss(self, pos, neg, margin=1.0, loss="margin", batch_pos=None):
+        """Fused KG branch: TransH on (ent, rel, norm)."""
+        return self._rank_loss(_lib.TRANSH, pos, neg, loss, margin, batch_pos)
+
+    # -- evaluation ----------------------------------------------------------------------------
+    def _rec_catalog(self):
+        """ie = Item + Ent[item2ent] for every item (jTransUP.py:177-181), built on the device."""
+        import ctypes as C
+        dev = self._require_cuda()
+        T = KF.make_tables(self._weights(), self.embedding_size, self.L1_flag, self.use_st_gumbel, self._item2ent)
+        out = torch.empty((self.item_total, self.embedding_size), dtype=torch.float32, device=dev)
+        lib = _lib.load()
+        _lib.check(lib.kgrec_ktup_item_table(C.byref(T), 0, self.item_total, C.c_void_p(out.data_ptr()),
+                                             out.stride(0), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.kernel_launches += 1
+        return out
+
+    def evaluateRec(self, u_ids, all_i_ids=None, gumbel_u=None):
+        return self._rec_scores(u_ids, gumbel_u)
+
+    def _ent_catalog(self):
+        return self.ent_embeddings.weight.detach()      # includes the padding row (jTransUP.py:195)
+
+    def evaluateHead(self, t, r, all_e_ids=None):
+        return self._eval(_lib.TRANSH, _lib.SIDE_HEAD, t, r, "scores", catalog=self._ent_catalog())
+
+    def evaluateTail(self, h, r, all_e_ids=None):
+        return self._eval(_lib.TRANSH, _lib.SIDE_TAIL, h, r, "scores", catalog=self._ent_catalog())
+
+    def topk(self, side, q, r, k=10, filter_csr=None, catalog=None, id_base=0):
+        s = _lib.SIDE_HEAD if side == "head" else _lib.SIDE_TAIL
+        cat = self._ent_catalog() if catalog is None else catalog
+        return self._eval(_lib.TRANSH, s, q, r, "topk", catalog=cat, id_base=id_base, k=k, filter_csr=filter_csr)

@@ -1,0 +1,90 @@
+"""TUP (`-model_type transup`) on the CUDA engine.  Mirrors jTransUP/models/transUP.py
+(constructor 19-67, forward 69-82, evaluate 84-102, getPreferences 105-115,
+st_gumbel_softmax 143-170, reportPreference 172-180)."""
+import torch
+
+from .. import _lib
+from .. import functional as KF
+from .base import KGRecModule, _embedding, _init_table
+
+
+def build_model(FLAGS, user_total, item_total, entity_total, relation_total, i_map=None, e_map=None, new_map=None):
+    return TransUPModel(L1_flag=FLAGS.L1_flag, embedding_size=FLAGS.embedding_size, user_total=user_total,
+                        item_total=item_total, preference_total=FLAGS.num_preferences,
+                        use_st_gumbel=FLAGS.use_st_gumbel)
+
+
+class RecModelBase(KGRecModule):
+    """What TUP and KTUP share on the recommendation side."""
+
+    def _rec_catalog(self):
+        return self.item_embeddings.weight.detach()
+
+    def _rec_scores(self, u_ids, gumbel_u=None):
+        seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
+        return self._eval(self.MODEL, _lib.SIDE_REC, u_ids, None, "scores", catalog=self._rec_catalog(),
+                          gumbel_u=gumbel_u, seed=seed)
+
+    def topk_items(self, u_ids, k=10, filter_csr=None, catalog=None, id_base=0, gumbel_u=None):
+        """K best items per user as uint64 keys (int64 storage): score bits << 32 | item id."""
+        seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
+        cat = self._rec_catalog() if catalog is None else catalog
+        return self._eval(self.MODEL, _lib.SIDE_REC, u_ids, None, "topk", catalog=cat, id_base=id_base, k=k,
+                          filter_csr=filter_csr, gumbel_u=gumbel_u, seed=seed)
+
+    def rank_loss(self, pos, neg, target=-1.0, loss="bpr", batch_pos=None, gumbel_u=None):
+        """Fused pos + K negatives + ranking loss: pos = (u, i), neg = (u repeated, ni)."""
+        pos = (pos[0], pos[1], None)
+        neg = (neg[0], neg[1], None)
+        return self._rank_loss(self.MODEL, pos, neg, loss, target, batch_pos, gumbel_u)
+
+    def _mix_tables(self):
+        """(P, N, half): the preference tables the mixing uses."""
+        return self.pref_embeddings.weight, self.pref_norm_embeddings.weight, 1.0
+
+    def _pair_vectors(self, u_id, i_ids):
+        dev = self._require_cuda()
+        i_ids = KF.as_index(i_ids, dev).long()
+        u = self.user_embeddings.weight[KF.as_index(u_id, dev).long().view(-1)[:1]].expand(i_ids.numel(), -1)
+        return u, self.item_embeddings.weight[i_ids]
+
+    def reportPreference(self, u_id, i_ids):
+        """(pre_probs, r_e, norm) for logging (-is_report; item_recommendation.py:68).
+        A diagnostics path, not the hot path: a handful of rows through library ops."""
+        u_e, i_e = self._pair_vectors(u_id, i_ids)
+        P, N, hf = self._mix_tables()
+        with torch.no_grad():
+            probs = (u_e + i_e) @ P.t() / 2
+            if self.use_st_gumbel:
+                g = -torch.log(-torch.log(torch.rand_like(probs) + 1e-20) + 1e-20)
+                probs = torch.nn.functional.one_hot((probs + g).argmax(-1), probs.shape[-1]).float()
+            return probs, probs @ P * hf, probs @ N * hf
+
+
+class TransUPModel(RecModelBase):
+    MODEL = _lib.TUP
+    TABLES = {"user": "user_embeddings", "item": "item_embeddings",
+              "pref": "pref_embeddings", "pref_norm": "pref_norm_embeddings"}
+
+    def __init__(self, L1_flag, embedding_size, user_total, item_total, preference_total, use_st_gumbel):
+        super().__init__()
+        self.L1_flag = L1_flag
+        self.embedding_size = embedding_size
+        self.user_total = user_total
+        self.item_total = item_total
+        self.preference_total = preference_total
+        self.use_st_gumbel = use_st_gumbel
+        self.user_embeddings = _embedding(_init_table(user_total, embedding_size))
+        self.item_embeddings = _embedding(_init_table(item_total, embedding_size))
+        self.pref_embeddings = _embedding(_init_table(preference_total, embedding_size))
+        self.pref_norm_embeddings = _embedding(_init_table(preference_total, embedding_size))
+        self._finish_init()
+
+    def forward(self, u_ids, i_ids, gumbel_u=None):
+        """score[b] of the pairs (u_ids[b], i_ids[b]).  gumbel_u: optional [B, P] uniform draws
+        replacing the in-kernel generator (parity runs)."""
+        return self._score(self.MODEL, u_ids, i_ids, None, gumbel_u)
+
+    def evaluate(self, u_ids, gumbel_u=None):
+        """[B, item_total] scores of every (user, item) pair; gumbel_u optional [B, I, P]."""
+        return self._rec_scores(u_ids, gumbel_u)

@@ -160,3 +160,22 @@ def test_invariants():
         close(O.transh_score(ent, rel, 0 * nrm, h, t, r, l1), s, 1e-12, 1e-12)
         eye = np.tile(np.eye(d).reshape(1, -1), (R, 1))
         close(O.transr_score(ent, rel, eye, h, t, r, l1), s, 1e-12, 1e-12)
+
+
+@pytest.mark.parametrize("name,with_norm", [("transe", False), ("transh", True)])
+@pytest.mark.parametrize("tag", ["l2", "l1"])
+def test_torch_port_matches_golden(golden, name, with_norm, tag):
+    """oracle/torch_port.py (the CPU-baseline arm of bench.py) against the same vectors."""
+    import torch
+    from oracle import torch_port as TP
+    g = golden(f"{name}_{tag}")
+    E, D = g["w_ent_embeddings"].shape
+    m = TP.TransPort(bool(g["l1"]), D, E, g["w_rel_embeddings"].shape[0], with_norm)
+    m.load_state_dict({k[2:] + ".weight": torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")})
+    LT = lambda x: torch.from_numpy(x).long()  # noqa: E731
+    loss = TP.train_step(m, (LT(g["ph"]), LT(g["pt"]), LT(g["pr"])), (LT(g["nh"]), LT(g["nt"]), LT(g["nr"])))
+    close(loss.item(), g["loss"])
+    for k in ("ent", "rel") + (("norm",) if with_norm else ()):
+        close(getattr(m, k + "_embeddings").weight.grad.numpy(), g[f"grad_{k}_embeddings"], rtol=1e-4, atol=1e-6)
+    close(m.evaluate_side(LT(g["q"]), LT(g["qr"]), True).detach().numpy(), g["eval_head"])
+    close(m.evaluate_side(LT(g["q"]), LT(g["qr"]), False).detach().numpy(), g["eval_tail"])
