@@ -180,6 +180,9 @@ int kgrec_rank_loss_bwd(const kgrec_tables* tables, int model,
  *                  table (KTUP rec side: the table built by kgrec_ktup_item_table), 16-byte
  *                  aligned, cat_ld % 4 == 0.
  *   id_base        global id of catalog row 0 (shards of a row-partitioned table).
+ *   cat_ids        (kgrec_eval_scores, KG sides) optional explicit global id of every catalog
+ *                  row, for gathered sub-catalogs (the reference's all_e_ids); a pair's score
+ *                  is bit-identical wherever the row sits, given its id.
  *   gumbel_u       rec side with use_gumbel: optional explicit uniform draws
  *                  [nq, n_cat, P] (transUP.py:159-161); NULL -> counter-hash draws from seed. */
 
@@ -187,8 +190,8 @@ int kgrec_rank_loss_bwd(const kgrec_tables* tables, int model,
  * score matrix the unchanged drivers consume.  out has leading dimension ld_out >= n_cat. */
 int kgrec_eval_scores(const kgrec_tables* tables, int model, int side,
                       const void* q, const void* r, int idx_bytes, const float* qvec, int64_t nq,
-                      const float* cat, int64_t cat_ld, int64_t n_cat,
-                      const float* gumbel_u, uint64_t seed,
+                      const float* cat, int64_t cat_ld, int64_t n_cat, int64_t id_base,
+                      const int32_t* cat_ids, const float* gumbel_u, uint64_t seed,
                       float* out, int64_t ld_out, kgrec_stream_t stream);
 
 /* The same scores reduced on chip to the K best (smallest) per query, replacing the D2H

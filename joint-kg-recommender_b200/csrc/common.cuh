@@ -150,6 +150,24 @@ struct Row {
       }
     }
   }
+  // streaming store: gradient rows are written once and never re-read by the kernels, so they
+  // should not displace the embedding tables from L2
+  __device__ __forceinline__ static void store_cs(float* __restrict__ row, const float (&v)[NE], int d, int lane) {
+    if (VEC) {
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        const int c = lane + 32 * i;
+        if (c * 4 < d)
+          __stcs(reinterpret_cast<float4*>(row) + c, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const int j = lane + 32 * e;
+        if (j < d) __stcs(row + j, v[e]);
+      }
+    }
+  }
   __device__ __forceinline__ static void red_add(float* __restrict__ row, const float (&v)[NE], int d, int lane) {
     if (VEC) {
 #pragma unroll

@@ -46,14 +46,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t suspend_ns) {
+  uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(suspend_ns) : "memory");
+  return ok != 0;
+}
+// Wait with a hardware suspend hint: a warp that finds the phase incomplete is parked by the
+// barrier unit instead of re-issuing TRYWAIT back to back (which starves the async proxy).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity, 20000u)) {}
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -121,6 +126,7 @@ struct EvalArgs {
   int64_t cat_ld;
   int64_t n_cat;
   int64_t id_base;          // global id of cat row 0
+  const int32_t* cat_ids;   // optional explicit global id per catalog row (gathered sub-catalogs)
   int n_splits;             // catalog ranges (gridDim.y)
   int tn;                   // catalog rows per tile
   const float* gumbel_u;    // explicit [nq, n_cat, P] (PREF_HARD parity mode)
@@ -531,6 +537,340 @@ k_eval(const EvalArgs A) {
   }
 }
 
+// =============================================================================================
+// Register-tiled kernel for the KG kinds (DIST: TransE / projected TransR; HYPER: TransH, KTUP).
+//
+// Every lane owns whole (query, row) pairs: warp w holds 8 queries, lane l holds rows
+// l, l + 32, ... of the tile, so a thread accumulates an 8 x RN tile of distances over the
+// d dimensions with NO cross-lane reduction and no idle lanes: 2 FP32 instructions per
+// (pair, dim) for L1 / L2, 4 for the hyperplane form -- the issue-rate bound of the path.
+// Query vectors sit in shared memory and are read as warp-wide broadcasts; catalog rows are
+// read as one 128-bit load per lane.  Rows whose length in 16-byte units is even (d = 128)
+// would put a quarter-warp on one bank group, so the lanes then walk the dimensions in a
+// skewed order (chunk k + lane % 8): conflict-free on dense rows, no padding needed.
+//
+// Work distribution: the (query tile x catalog tile) units are laid out query-tile-major and
+// cut into gridDim.x equal contiguous ranges (one resident CTA per SM each), so every CTA
+// streams the same number of tiles -- no tail wave.  A range may cross into the next query
+// tile once; per-range top-K lists go to part_keys[piece][q][k] and are merged afterwards.
+// =============================================================================================
+constexpr int RQ = 8;                         // queries per warp
+
+struct TiledSmem {
+  size_t bars, q, w, gold, tiles, lists, total;
+};
+__host__ __device__ inline TiledSmem tiled_smem_layout(int kind, int mode, int d, int tn, int stages, int k, int warps) {
+  TiledSmem s{};
+  const int TQT = RQ * warps;
+  size_t off = 0;
+  s.bars = off; off += 2 * 8 * sizeof(uint64_t);
+  off = (off + 127) & ~static_cast<size_t>(127);
+  s.q = off; off += static_cast<size_t>(TQT) * d * sizeof(float);
+  if (kind == KIND_HYPER) { s.w = off; off += static_cast<size_t>(TQT) * d * sizeof(float); }
+  if (mode == MODE_RANK) { s.gold = off; off += static_cast<size_t>(TQT) * 2 * sizeof(uint32_t); }
+  off = (off + 127) & ~static_cast<size_t>(127);
+  s.tiles = off; off += static_cast<size_t>(stages) * tn * d * sizeof(float);
+  if (mode == MODE_TOPK) { s.lists = off; off += static_cast<size_t>(TQT) * k * sizeof(uint64_t); }
+  s.total = off;
+  return s;
+}
+
+template <int KIND, int MODE, bool L1, int RN, int W, bool IDS>
+__global__ void __launch_bounds__(W * 32, 1)
+k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int TN = 32 * RN;
+  constexpr int TQT = RQ * W;
+  constexpr int kTiledWarps = W;
+  const kgrec_tables& T = A.T;
+  const int d = T.dim;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const TiledSmem L = tiled_smem_layout(KIND, MODE, d, TN, stages, A.k, W);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+  uint64_t* empty = full + 8;
+  float* sQ = reinterpret_cast<float*>(smem_raw + L.q);
+  [[maybe_unused]] float* sW = reinterpret_cast<float*>(smem_raw + L.w);
+  [[maybe_unused]] uint32_t* sGold = reinterpret_cast<uint32_t*>(smem_raw + L.gold);
+  float* tiles = reinterpret_cast<float*>(smem_raw + L.tiles);
+  const bool dense = A.cat_ld == d;           // strided catalogs need one copy per row
+
+  const int64_t n_tiles = (A.n_cat + TN - 1) / TN;
+  const int64_t n_qtiles = (A.nq + TQT - 1) / TQT;
+  const int64_t total_units = n_tiles * n_qtiles;
+  const int64_t u_begin = min(total_units, static_cast<int64_t>(blockIdx.x) * units_per_cta);
+  const int64_t u_end = min(total_units, u_begin + units_per_cta);
+  const int64_t my_units = u_end - u_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kTiledWarps); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (my_units <= 0) return;
+
+  // unit g (0-based within this CTA) -> catalog tile (u_begin + g) % n_tiles -> stage g % stages
+  auto issue_tile = [&](int64_t g) {          // called by all lanes of warp 0
+    const int s = static_cast<int>(g % stages);
+    const int64_t row0 = ((u_begin + g) % n_tiles) * TN;
+    const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
+    float* dst = tiles + static_cast<size_t>(s) * TN * d;
+    if (lane == 0) {
+      if (g >= stages) mbar_wait(empty + s, static_cast<uint32_t>(((g / stages) - 1) & 1));
+      mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(rows) * d * sizeof(float));
+    }
+    __syncwarp();
+    if (dense) {
+      if (lane == 0) bulk_g2s(dst, A.cat + row0 * A.cat_ld, static_cast<uint32_t>(rows) * d * sizeof(float), full + s);
+    } else {
+      for (int r = lane; r < rows; r += 32)
+        bulk_g2s(dst + r * d, A.cat + (row0 + r) * A.cat_ld, d * sizeof(float), full + s);
+    }
+  };
+  const int prefetch = stages - 1;
+  if (wid == 0)
+    for (int64_t g = 0; g < prefetch && g < my_units; ++g) issue_tile(g);
+
+  [[maybe_unused]] uint32_t thr_hi[RQ];       // TOPK: score bits of the current K-th best
+  [[maybe_unused]] uint64_t* lists = nullptr;
+  [[maybe_unused]] int cnt[RQ];
+  if constexpr (MODE == MODE_TOPK)
+    lists = reinterpret_cast<uint64_t*>(smem_raw + L.lists) + static_cast<size_t>(wid) * RQ * A.k;
+  const float* cq = sQ + wid * RQ * d;
+  [[maybe_unused]] const float* wq = sW + wid * RQ * d;
+  [[maybe_unused]] const uint32_t* gq = sGold + wid * RQ * 2;
+  const int nk4 = d >> 2;
+  // Dimension walk of row n starts at chunk (n & 7) when rows are an even number of 16-byte
+  // units long: conflict-free (8 consecutive rows -> 8 bank groups) AND a function of the row's
+  // global id only, so a (query, row) score is bit-identical wherever the row sits (tile, lane,
+  // shard, gathered sub-catalog).  Tiles start at multiples of 32 rows, so for contiguous
+  // catalogs the start chunk is a per-lane constant.
+  const bool use_skew = (nk4 & 1) == 0;
+  const int skew0 = use_skew ? static_cast<int>((A.id_base + lane) & 7) : 0;
+  int64_t cur_qt = -1, q0 = 0;
+
+  // (re)load this warp's 8 query vectors and reset its per-query state
+  auto begin_qtile = [&](int64_t qt) {
+    using R = Row<2, true>;                   // d <= 256
+    cur_qt = qt;
+    q0 = qt * TQT + wid * RQ;
+    __syncwarp();
+    for (int qi = 0; qi < RQ; ++qi) {
+      const int64_t q = q0 + qi;
+      float cv[8], wv[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { cv[e] = 0.f; wv[e] = 0.f; }
+      if (q < A.nq) {
+        if (A.qvec) {
+          R::load(cv, A.qvec + q * 2 * d, d, lane);
+          if (KIND == KIND_HYPER) R::load(wv, A.qvec + q * 2 * d + d, d, lane);
+        } else {
+          const int64_t ie = load_idx(A.q, q, A.is64), ir = load_idx(A.r, q, A.is64);
+          float rv[8];
+          R::load(cv, T.ent + ie * T.ld, d, lane);
+          R::load(rv, T.rel + ir * T.ld, d, lane);
+          if (KIND == KIND_HYPER) {
+            R::load(wv, T.norm + ir * T.ld, d, lane);
+            const float a = warp_sum(R::dot(cv, wv));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cv[e] -= a * wv[e];       // proj(E[q], w)
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) cv[e] = (A.side == KGREC_SIDE_HEAD) ? cv[e] - rv[e] : cv[e] + rv[e];
+        }
+      }
+      R::store(sQ + (wid * RQ + qi) * d, cv, d, lane);
+      if (KIND == KIND_HYPER) R::store(sW + (wid * RQ + qi) * d, wv, d, lane);
+      if constexpr (MODE == MODE_RANK) {
+        if (lane == 0) {
+          sGold[(wid * RQ + qi) * 2] = q < A.nq ? __float_as_uint(__ldg(A.gold_scores + q)) : 0u;
+          sGold[(wid * RQ + qi) * 2 + 1] = q < A.nq ? static_cast<uint32_t>(__ldg(A.gold_ids + q)) : 0u;
+        }
+      }
+    }
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi) { thr_hi[qi] = 0xffffffffu; cnt[qi] = 0; }
+    if constexpr (MODE == MODE_TOPK)
+      for (int i = lane; i < RQ * A.k; i += 32) lists[i] = KEY_INF;
+    __syncwarp();
+  };
+  // write out what this warp accumulated for the query tile it is leaving
+  auto end_qtile = [&]() {
+    if constexpr (MODE == MODE_TOPK) {
+      __syncwarp();
+      // piece = index of this CTA among the CTAs that touch query tile cur_qt
+      const int64_t first_cta = (cur_qt * n_tiles) / units_per_cta;
+      const int64_t piece = static_cast<int64_t>(blockIdx.x) - first_cta;
+      for (int i = lane; i < RQ * A.k; i += 32) {
+        const int64_t q = q0 + i / A.k;
+        if (q < A.nq) A.part_keys[(piece * A.nq + q) * A.k + (i % A.k)] = lists[i];
+      }
+    }
+    if constexpr (MODE == MODE_RANK) {
+#pragma unroll
+      for (int qi = 0; qi < RQ; ++qi) {
+        int c = cnt[qi];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+        if (lane == 0 && q0 + qi < A.nq && c) atomicAdd(A.counts + q0 + qi, c);
+      }
+    }
+  };
+
+  for (int64_t g = 0; g < my_units; ++g) {
+    const int64_t u = u_begin + g;
+    const int64_t qt = u / n_tiles, ti = u - qt * n_tiles;
+    if (qt != cur_qt) {
+      if (cur_qt >= 0) end_qtile();
+      begin_qtile(qt);
+    }
+    const int s = static_cast<int>(g % stages);
+    if (wid == 0 && g + prefetch < my_units) issue_tile(g + prefetch);
+    const float* tile = tiles + static_cast<size_t>(s) * TN * d;
+    const int64_t row0 = ti * TN;
+    const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
+    mbar_wait(full + s, static_cast<uint32_t>((g / stages) & 1));
+
+    float acc[RQ][RN];
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi)
+#pragma unroll
+      for (int j = 0; j < RN; ++j) acc[qi][j] = 0.f;
+    const float* xrow = tile + lane * d;
+    [[maybe_unused]] int skj[RN];
+#pragma unroll
+    for (int j = 0; j < RN; ++j) {
+      skj[j] = skew0;
+      if constexpr (IDS) {
+        const int r = lane + 32 * j;
+        skj[j] = (use_skew && r < rows) ? (__ldg(A.cat_ids + row0 + r) & 7) : 0;
+      }
+    }
+
+    if constexpr (KIND == KIND_HYPER) {
+      float sd[RQ][RN];                        // phase 1: sd[q][n] = x_n . w_q
+#pragma unroll
+      for (int qi = 0; qi < RQ; ++qi)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) sd[qi][j] = 0.f;
+#pragma unroll 1
+      for (int k4 = 0; k4 < nk4; ++k4) {
+        int kk = k4 + skew0; if (kk >= nk4) kk -= nk4;
+        float4 xv[RN];
+        int kj[RN];
+#pragma unroll
+        for (int j = 0; j < RN; ++j) {
+          kj[j] = kk;
+          if constexpr (IDS) { kj[j] = k4 + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }
+          xv[j] = *reinterpret_cast<const float4*>(xrow + j * 32 * d + 4 * kj[j]);
+        }
+#pragma unroll
+        for (int qi = 0; qi < RQ; ++qi) {
+          float4 wv = *reinterpret_cast<const float4*>(wq + qi * d + 4 * kk);
+#pragma unroll
+          for (int j = 0; j < RN; ++j) {
+            if constexpr (IDS) wv = *reinterpret_cast<const float4*>(wq + qi * d + 4 * kj[j]);
+            sd[qi][j] = fmaf(xv[j].x, wv.x, fmaf(xv[j].y, wv.y, fmaf(xv[j].z, wv.z, fmaf(xv[j].w, wv.w, sd[qi][j]))));
+          }
+        }
+      }
+#pragma unroll 1
+      for (int k4 = 0; k4 < nk4; ++k4) {         // phase 2: L(c_q - x_n + s w_q)
+        int kk = k4 + skew0; if (kk >= nk4) kk -= nk4;
+        float4 xv[RN];
+        int kj[RN];
+#pragma unroll
+        for (int j = 0; j < RN; ++j) {
+          kj[j] = kk;
+          if constexpr (IDS) { kj[j] = k4 + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }
+          xv[j] = *reinterpret_cast<const float4*>(xrow + j * 32 * d + 4 * kj[j]);
+        }
+#pragma unroll
+        for (int qi = 0; qi < RQ; ++qi) {
+          float4 cv = *reinterpret_cast<const float4*>(cq + qi * d + 4 * kk);
+          float4 wv = *reinterpret_cast<const float4*>(wq + qi * d + 4 * kk);
+#pragma unroll
+          for (int j = 0; j < RN; ++j) {
+            if constexpr (IDS) {
+              cv = *reinterpret_cast<const float4*>(cq + qi * d + 4 * kj[j]);
+              wv = *reinterpret_cast<const float4*>(wq + qi * d + 4 * kj[j]);
+            }
+            const float sj = sd[qi][j];
+            const float e0 = fmaf(sj, wv.x, cv.x - xv[j].x), e1 = fmaf(sj, wv.y, cv.y - xv[j].y);
+            const float e2 = fmaf(sj, wv.z, cv.z - xv[j].z), e3 = fmaf(sj, wv.w, cv.w - xv[j].w);
+            if (L1) acc[qi][j] += fabsf(e0) + fabsf(e1) + fabsf(e2) + fabsf(e3);
+            else acc[qi][j] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, acc[qi][j]))));
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int k4 = 0; k4 < nk4; ++k4) {
+        int kk = k4 + skew0; if (kk >= nk4) kk -= nk4;
+        float4 xv[RN];
+        int kj[RN];
+#pragma unroll
+        for (int j = 0; j < RN; ++j) {
+          kj[j] = kk;
+          if constexpr (IDS) { kj[j] = k4 + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }
+          xv[j] = *reinterpret_cast<const float4*>(xrow + j * 32 * d + 4 * kj[j]);
+        }
+#pragma unroll
+        for (int qi = 0; qi < RQ; ++qi) {
+          float4 cv = *reinterpret_cast<const float4*>(cq + qi * d + 4 * kk);
+#pragma unroll
+          for (int j = 0; j < RN; ++j) {
+            if constexpr (IDS) cv = *reinterpret_cast<const float4*>(cq + qi * d + 4 * kj[j]);
+            const float e0 = cv.x - xv[j].x, e1 = cv.y - xv[j].y, e2 = cv.z - xv[j].z, e3 = cv.w - xv[j].w;
+            if (L1) acc[qi][j] += fabsf(e0) + fabsf(e1) + fabsf(e2) + fabsf(e3);
+            else acc[qi][j] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, acc[qi][j]))));
+          }
+        }
+      }
+    }
+    // the tile is consumed: release the stage before the (register-only) epilogue
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi) {
+      const int64_t q = q0 + qi;
+      if (q >= A.nq) continue;                 // warp-uniform
+#pragma unroll
+      for (int j = 0; j < RN; ++j) {
+        const int r = lane + 32 * j;
+        const bool valid = r < rows;
+        const int64_t n_local = row0 + r;
+        const uint32_t sb = __float_as_uint(acc[qi][j]);
+        if constexpr (MODE == MODE_FULL) {
+          if (valid) __stcs(A.out + q * A.ld_out + n_local, acc[qi][j]);
+        } else if constexpr (MODE == MODE_RANK) {
+          const uint32_t id = static_cast<uint32_t>(A.id_base + n_local);
+          const uint32_t gh = gq[qi * 2], gi = gq[qi * 2 + 1];
+          if (valid && (sb < gh || (sb == gh && id < gi))) ++cnt[qi];
+        } else {
+          unsigned mask = __ballot_sync(FULL, valid && sb <= thr_hi[qi]);
+          while (mask) {                         // rare once the lists have warmed up
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t cid = static_cast<uint32_t>(A.id_base + row0 + src + 32 * j);
+            const uint64_t ckey = (static_cast<uint64_t>(__shfl_sync(FULL, sb, src)) << 32) | cid;
+            uint64_t* list = lists + qi * A.k;
+            if (ckey < list[A.k - 1]) {
+              bool skip = false;
+              if (A.filter_ptr) skip = filtered(A.filter_ids, __ldg(A.filter_ptr + q), __ldg(A.filter_ptr + q + 1), static_cast<int32_t>(cid));
+              if (!skip) {
+                list_insert(list, A.k, ckey, lane);
+                thr_hi[qi] = static_cast<uint32_t>(list[A.k - 1] >> 32);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  end_qtile();
+}
+
 // K-way merge: in [n_lists][nq][k] ascending lists -> out [nq][k].  One warp per query.
 __global__ void __launch_bounds__(256)
 k_merge_topk(const uint64_t* __restrict__ in, int n_lists, int64_t nq, int k, uint64_t* __restrict__ out) {
@@ -575,6 +915,9 @@ struct EvalPlan {
   int kind, nch, tn, n_splits;
   int64_t n_qtiles;
   size_t smem;
+  bool tiled;       // register-tiled kernel (KG kinds)
+  int rn, stages, grid, warps;
+  int64_t units_per_cta;
 };
 
 static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const float* cat, int64_t cat_ld,
@@ -610,16 +953,42 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
   if (mode == MODE_TOPK && (k <= 0 || k > 128)) { set_error("topn %d outside [1, 128]", k); return KGREC_ERR_UNSUPPORTED; }
   pl->nch = d <= 128 ? 1 : 2;
   pl->n_qtiles = (nq + TQ - 1) / TQ;
+  pl->tiled = pl->kind <= KIND_HYPER;
+  if (pl->tiled) {
+    // register tile 8 x RN per thread, W warps per CTA.  d <= 128: 16 warps, DIST 8x4 / HYPER 8x2
+    // (HYPER keeps two tiles: dots and distances); wider rows: 8 warps, 8x2 / 8x1 to fit smem.
+    const bool wide = d > 128;
+    pl->warps = wide ? 8 : 16;
+    pl->rn = (pl->kind == KIND_DIST ? 4 : 2) / (wide ? 2 : 1);
+    const int tn_t = 32 * pl->rn;
+    int stages = 4;
+    while (stages > 2 && tiled_smem_layout(pl->kind, mode, d, tn_t, stages, k, pl->warps).total > 210 * 1024) --stages;
+    pl->stages = stages;
+    pl->tn = tn_t;
+    pl->smem = tiled_smem_layout(pl->kind, mode, d, tn_t, stages, k, pl->warps).total;
+    if (pl->smem > 225 * 1024) { set_error("eval: shared-memory budget exceeded (%zu bytes)", pl->smem); return KGREC_ERR_UNSUPPORTED; }
+    const int64_t n_tiles_t = (n_cat + tn_t - 1) / tn_t;
+    const int tqt = RQ * pl->warps;
+    pl->n_qtiles = (nq + tqt - 1) / tqt;
+    const int64_t total_units = n_tiles_t * pl->n_qtiles;
+    int64_t ctas = sm_count();                       // one resident CTA per SM
+    if (ctas > total_units) ctas = total_units;
+    pl->units_per_cta = (total_units + ctas - 1) / ctas;
+    pl->grid = static_cast<int>((total_units + pl->units_per_cta - 1) / pl->units_per_cta);
+    // pieces of partial top-K lists per query tile: CTAs whose ranges touch one query tile
+    pl->n_splits = static_cast<int>((n_tiles_t + pl->units_per_cta - 1) / pl->units_per_cta + 1);
+    A->T = *T; A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
+    A->n_splits = pl->n_splits; A->tn = tn_t; A->k = k;
+    return KGREC_OK;
+  }
   // tile rows: ~16 KB per stage
   int tn = static_cast<int>((16 * 1024) / (cat_ld * sizeof(float)));
   tn = tn < 4 ? 4 : (tn > 64 ? 64 : tn);
   tn &= ~3;
   pl->tn = tn;
   const int64_t n_tiles = (n_cat + tn - 1) / tn;
-  int64_t splits = (2 * static_cast<int64_t>(sm_count()) + pl->n_qtiles - 1) / pl->n_qtiles;
-  if (mode == MODE_FULL || mode == MODE_RANK) {
-    // no merge needed: splits are free
-  }
+  // catalog ranges per query tile: fill the resident CTA slots (3 per SM) without a second wave
+  int64_t splits = (3 * static_cast<int64_t>(sm_count())) / pl->n_qtiles;
   splits = splits < 1 ? 1 : (splits > n_tiles ? n_tiles : splits);
   if (splits > 65535) splits = 65535;
   pl->n_splits = static_cast<int>(splits);
@@ -640,6 +1009,22 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
 template <int MODE>
 static int launch_eval(const EvalArgs& A, const EvalPlan& pl, cudaStream_t st) {
   const dim3 grid(static_cast<unsigned>(pl.n_qtiles), static_cast<unsigned>(pl.n_splits));
+  if (pl.tiled) {
+#define KGREC_TILED_CASE(KINDV, RNV, WV)                                                                      \
+  {                                                                                                           \
+    auto kern = A.T.l1 ? k_eval_tiled<KINDV, MODE, true, RNV, WV, false> : k_eval_tiled<KINDV, MODE, false, RNV, WV, false>; \
+    if constexpr (MODE == MODE_FULL) {                                                                        \
+      if (A.cat_ids) kern = A.T.l1 ? k_eval_tiled<KINDV, MODE, true, RNV, WV, true> : k_eval_tiled<KINDV, MODE, false, RNV, WV, true>; \
+    }                                                                                                         \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem))); \
+    kern<<<pl.grid, WV * 32, pl.smem, st>>>(A, pl.stages, pl.units_per_cta);                                  \
+  }
+    if (pl.kind == KIND_DIST) { if (pl.warps == 16) KGREC_TILED_CASE(KIND_DIST, 4, 16) else KGREC_TILED_CASE(KIND_DIST, 2, 8) }
+    else { if (pl.warps == 16) KGREC_TILED_CASE(KIND_HYPER, 2, 16) else KGREC_TILED_CASE(KIND_HYPER, 1, 8) }
+#undef KGREC_TILED_CASE
+    KGREC_CUDA_OK(cudaGetLastError());
+    return KGREC_OK;
+  }
 #define KGREC_EVAL_CASE(KINDV, NCHV)                                                                          \
   {                                                                                                           \
     auto kern = A.T.l1 ? k_eval<KINDV, NCHV, MODE, true> : k_eval<KINDV, NCHV, MODE, false>;                  \
@@ -647,10 +1032,6 @@ static int launch_eval(const EvalArgs& A, const EvalPlan& pl, cudaStream_t st) {
     kern<<<grid, kEvalThreads, pl.smem, st>>>(A);                                                             \
   }
   switch (pl.kind * 2 + (pl.nch - 1)) {
-    case 0: KGREC_EVAL_CASE(KIND_DIST, 1) break;
-    case 1: KGREC_EVAL_CASE(KIND_DIST, 2) break;
-    case 2: KGREC_EVAL_CASE(KIND_HYPER, 1) break;
-    case 3: KGREC_EVAL_CASE(KIND_HYPER, 2) break;
     case 4: KGREC_EVAL_CASE(KIND_PREF_HARD, 1) break;
     case 5: KGREC_EVAL_CASE(KIND_PREF_HARD, 2) break;
     case 6: KGREC_EVAL_CASE(KIND_PREF_SOFT, 1) break;
@@ -667,14 +1048,14 @@ using namespace kgrec;
 
 extern "C" int64_t kgrec_eval_workspace_bytes(int64_t nq, int32_t k) {
   // worst case number of catalog splits is 2 * SMs (eval_plan)
-  const int64_t splits = 2 * static_cast<int64_t>(sm_count());
+  const int64_t splits = 3 * static_cast<int64_t>(sm_count());
   return splits * (nq > 0 ? nq : 1) * (k > 0 ? k : 1) * static_cast<int64_t>(sizeof(uint64_t));
 }
 
 extern "C" int kgrec_eval_scores(const kgrec_tables* tables, int model, int side, const void* q, const void* r,
                                  int idx_bytes, const float* qvec, int64_t nq, const float* cat, int64_t cat_ld,
-                                 int64_t n_cat, const float* gumbel_u, uint64_t seed, float* out, int64_t ld_out,
-                                 kgrec_stream_t stream) {
+                                 int64_t n_cat, int64_t id_base, const int32_t* cat_ids, const float* gumbel_u,
+                                 uint64_t seed, float* out, int64_t ld_out, kgrec_stream_t stream) {
   EvalArgs A{};
   EvalPlan pl{};
   int rc = eval_plan(tables, model, side, MODE_FULL, cat, cat_ld, nq, n_cat, 0, qvec != nullptr, &A, &pl);
@@ -682,7 +1063,8 @@ extern "C" int kgrec_eval_scores(const kgrec_tables* tables, int model, int side
   if (!out || ld_out < n_cat) { set_error("bad out / ld_out"); return KGREC_ERR_INVALID; }
   if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
   A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
-  A.gumbel_u = gumbel_u; A.seed = seed; A.id_base = 0;
+  A.gumbel_u = gumbel_u; A.seed = seed; A.id_base = id_base; A.cat_ids = cat_ids;
+  if (cat_ids && !pl.tiled) { set_error("eval_scores: cat_ids is for the KG sides only"); return KGREC_ERR_INVALID; }
   A.out = out; A.ld_out = ld_out;
   return launch_eval<MODE_FULL>(A, pl, static_cast<cudaStream_t>(stream));
 }
@@ -704,7 +1086,7 @@ extern "C" int kgrec_eval_topk(const kgrec_tables* tables, int model, int side, 
   A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
   A.gumbel_u = gumbel_u; A.seed = seed; A.id_base = id_base;
   A.filter_ptr = filter_ptr; A.filter_ids = filter_ids;
-  if (pl.n_splits == 1) {
+  if (pl.n_splits == 1 && !pl.tiled) {
     A.part_keys = out_keys;
     return launch_eval<MODE_TOPK>(A, pl, st);
   }
@@ -713,6 +1095,7 @@ extern "C" int kgrec_eval_topk(const kgrec_tables* tables, int model, int side, 
     return KGREC_ERR_INVALID;
   }
   A.part_keys = static_cast<uint64_t*>(workspace);
+  if (pl.tiled) KGREC_CUDA_OK(cudaMemsetAsync(workspace, 0xff, static_cast<size_t>(need), st));   // unused pieces = empty lists
   if ((rc = launch_eval<MODE_TOPK>(A, pl, st))) return rc;
   return kgrec_merge_topk(A.part_keys, pl.n_splits, nq, k, out_keys, stream);
 }

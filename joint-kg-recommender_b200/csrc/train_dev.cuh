@@ -180,7 +180,7 @@ struct KgTriple {
         gx[i] = eps[i] - ew * w[i];
         gw[i] = -(ew * (h[i] - t[i]) + xw * eps[i]);
       }
-      if (G.mode == 0) R::store(G.norm + slot * d, gw, d, lane);
+      if (G.mode == 0) R::store_cs(G.norm + slot * d, gw, d, lane);
       else R::red_add(G.norm + ir * d, gw, d, lane);
     } else {
       // gx = M^T eps ; grad_M[a, :] += eps_a * (h - t)
@@ -201,14 +201,14 @@ struct KgTriple {
         R::red_add(gm + static_cast<int64_t>(a) * d, o, d, lane);
       }
     }
-    if (G.mode == 0) R::store(G.rel + slot * d, eps, d, lane);
+    if (G.mode == 0) R::store_cs(G.rel + slot * d, eps, d, lane);
     else R::red_add(G.rel + ir * d, eps, d, lane);
     float ngx[NE];
 #pragma unroll
     for (int i = 0; i < NE; ++i) ngx[i] = -gx[i];
     if (G.mode == 0) {
-      R::store(G.ent + slot * d, gx, d, lane);
-      R::store(G.ent + (n + slot) * d, ngx, d, lane);
+      R::store_cs(G.ent + slot * d, gx, d, lane);
+      R::store_cs(G.ent + (n + slot) * d, ngx, d, lane);
     } else {
       R::red_add(G.ent + ih * d, gx, d, lane);
       R::red_add(G.ent + it * d, ngx, d, lane);
@@ -603,14 +603,14 @@ k_score_bwd(const kgrec_tables T, const int ktup, const IdxArgs I, const int64_t
         float gu[NE], gi[NE];
         p.backward(T, pv, g, scr, lane, gu, gi, sv_all + wid * 3 * dpad, sc_all + wid * 2 * kMaxPref, dpad);
         if (G.mode == 0) {
-          R::store(G.user + i * d, gu, d, lane);
-          R::store(G.item + i * d, gi, d, lane);
+          R::store_cs(G.user + i * d, gu, d, lane);
+          R::store_cs(G.item + i * d, gi, d, lane);
           if (ktup) {
             if (ia == T.n_ent - 1) {  // padding row: no gradient (jTransUP.py:96)
 #pragma unroll
               for (int e = 0; e < NE; ++e) gi[e] = 0.f;
             }
-            R::store(G.ent + i * d, gi, d, lane);
+            R::store_cs(G.ent + i * d, gi, d, lane);
           }
         } else {
           R::red_add(G.user + iu * d, gu, d, lane);

@@ -55,8 +55,8 @@ _SIGNATURES = {
                                       C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_uint64,
                                       C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(Grads), C.c_void_p]),
     "kgrec_eval_scores": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
-                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
-                                    C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]),
+                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]),
     "kgrec_eval_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int32]),
     "kgrec_eval_topk": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,

@@ -53,7 +53,7 @@ def build_filter_csr(query_keys, dicts, device, id_lo=0, id_hi=None):
 
 
 def run(T, model, side, q, r, mode, catalog, id_base=0, k=10, filter_csr=None, gumbel_u=None, seed=0,
-        qvec=None, gold_scores=None, gold_ids=None, out=None):
+        qvec=None, gold_scores=None, gold_ids=None, out=None, cat_ids=None):
     """One call into the evaluation kernels.
 
     mode 'scores' -> [nq, n_cat] float32; 'topk' -> int64-viewed uint64 keys [nq, k];
@@ -73,8 +73,9 @@ def run(T, model, side, q, r, mode, catalog, id_base=0, k=10, filter_csr=None, g
     if mode == "scores":
         res = torch.empty((nq, n_cat), dtype=torch.float32, device=dev) if out is None else out
         _lib.check(lib.kgrec_eval_scores(C.byref(T), model, side, _ptr(q), _ptr(r), ib, _ptr(qvec), nq,
-                                         _ptr(catalog), cat_ld, n_cat, _ptr(gumbel_u), seed, _ptr(res),
-                                         res.stride(0), stream))
+                                         _ptr(catalog), cat_ld, n_cat, id_base,
+                                         _ptr(cat_ids.to(torch.int32).contiguous() if cat_ids is not None else None),
+                                         _ptr(gumbel_u), seed, _ptr(res), res.stride(0), stream))
         return res
     if mode == "topk":
         keys = torch.empty((nq, k), dtype=torch.int64, device=dev)

@@ -75,7 +75,7 @@ class KGModelBase(KGRecModule):
         q, r = KF.as_index(q, dev), KF.as_index(r, dev)
         for lo in range(0, g.numel(), 512):
             hi = min(g.numel(), lo + 512)
-            m = self._eval(self.MODEL, s, q[lo:hi], r[lo:hi], "scores", catalog=rows[lo:hi])
+            m = self._eval(self.MODEL, s, q[lo:hi], r[lo:hi], "scores", catalog=rows[lo:hi], cat_ids=g[lo:hi])
             out[lo:hi] = m.diagonal()
         return out
 
