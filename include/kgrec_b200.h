@@ -165,6 +165,28 @@ int kgrec_rank_loss_bwd(const kgrec_tables* tables, int model,
                         const float* pos_scores, const float* neg_scores, float grad_loss,
                         const float* grad_loss_dev, const kgrec_grads* grads, kgrec_stream_t stream);
 
+/* The same fused ranking loss in the group-compact negative format (TransE / TransH and the
+ * KTUP KG branch).  The reference draws a negative by corrupting the head OR the tail of its
+ * positive (utils/data.py:12-56), so negative k of positive j is one int32:
+ *     corrupt[j*n_neg + k] >= 0 : (h_j, r_j, corrupt)      tail replaced
+ *     corrupt[j*n_neg + k] <  0 : (~corrupt, r_j, t_j)     head replaced
+ * Scores and losses equal kgrec_rank_loss_fwd on the expanded triples.  The backward reads
+ * (3 + n_neg) rows per group and writes (3 + n_neg) gradient rows, accumulating the shared
+ * rows' gradients in registers.  Slot layout (grads->mode 0): ent [n_pos * (2 + n_neg), d],
+ * per group: head, tail, corrupted_1 .. corrupted_K; rel and norm [n_pos, d]. */
+int kgrec_corrupt_loss_fwd(const kgrec_tables* tables, int model,
+                           const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
+                           const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
+                           int loss_kind, float margin_or_target,
+                           float* pos_scores, float* neg_scores, float* loss,
+                           void* workspace, int32_t* status, kgrec_stream_t stream);
+int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model,
+                           const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
+                           const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
+                           int loss_kind, float margin_or_target,
+                           const float* pos_scores, const float* neg_scores, float grad_loss,
+                           const float* grad_loss_dev, const kgrec_grads* grads, kgrec_stream_t stream);
+
 /* ---- full-catalog evaluation path ---------------------------------------- */
 /* Common arguments of the three evaluation modes:
  *   model / side   which evaluate* method: KG sides score query (t,r) / (h,r) pairs against

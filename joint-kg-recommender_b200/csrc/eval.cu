@@ -537,6 +537,26 @@ k_eval(const EvalArgs A) {
   }
 }
 
+// Cold path of the tiled kernel's top-K epilogue, kept out of line so the hot loop and the
+// 32 unrolled threshold tests stay small enough for the instruction cache.  Returns the new
+// score-bits threshold of the query.
+__device__ __noinline__ uint32_t topk_insert_candidates(unsigned mask, uint32_t sb, uint32_t id_lane0, uint64_t* list, int k,
+                                                        const int64_t* __restrict__ filter_ptr,
+                                                        const int32_t* __restrict__ filter_ids, int64_t q, int lane) {
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const uint32_t cid = id_lane0 + static_cast<uint32_t>(src);
+    const uint64_t ckey = (static_cast<uint64_t>(__shfl_sync(FULL, sb, src)) << 32) | cid;
+    if (ckey < list[k - 1]) {
+      bool skip = false;
+      if (filter_ptr) skip = filtered(filter_ids, __ldg(filter_ptr + q), __ldg(filter_ptr + q + 1), static_cast<int32_t>(cid));
+      if (!skip) list_insert(list, k, ckey, lane);
+    }
+  }
+  return static_cast<uint32_t>(list[k - 1] >> 32);
+}
+
 // =============================================================================================
 // Register-tiled kernel for the KG kinds (DIST: TransE / projected TransR; HYPER: TransH, KTUP).
 //
@@ -848,22 +868,10 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
           const uint32_t gh = gq[qi * 2], gi = gq[qi * 2 + 1];
           if (valid && (sb < gh || (sb == gh && id < gi))) ++cnt[qi];
         } else {
-          unsigned mask = __ballot_sync(FULL, valid && sb <= thr_hi[qi]);
-          while (mask) {                         // rare once the lists have warmed up
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const uint32_t cid = static_cast<uint32_t>(A.id_base + row0 + src + 32 * j);
-            const uint64_t ckey = (static_cast<uint64_t>(__shfl_sync(FULL, sb, src)) << 32) | cid;
-            uint64_t* list = lists + qi * A.k;
-            if (ckey < list[A.k - 1]) {
-              bool skip = false;
-              if (A.filter_ptr) skip = filtered(A.filter_ids, __ldg(A.filter_ptr + q), __ldg(A.filter_ptr + q + 1), static_cast<int32_t>(cid));
-              if (!skip) {
-                list_insert(list, A.k, ckey, lane);
-                thr_hi[qi] = static_cast<uint32_t>(list[A.k - 1] >> 32);
-              }
-            }
-          }
+          const unsigned mask = __ballot_sync(FULL, valid && sb <= thr_hi[qi]);
+          if (mask)                              // rare once the lists have warmed up
+            thr_hi[qi] = topk_insert_candidates(mask, sb, static_cast<uint32_t>(A.id_base + row0 + 32 * j), lists + qi * A.k,
+                                                A.k, A.filter_ptr, A.filter_ids, q, lane);
         }
       }
     }

@@ -99,25 +99,6 @@ static int check_grads(const Plan& pl, const kgrec_grads* G) {
   return KGREC_OK;
 }
 
-// per-batch deterministic reduction of the group terms (one CTA per loss batch)
-__global__ void __launch_bounds__(256)
-k_batch_loss(const float* __restrict__ group_loss, const LossCfg L, float* __restrict__ loss) {
-  __shared__ float part[8];
-  const int64_t b0 = static_cast<int64_t>(blockIdx.x) * L.batch_pos;
-  const int64_t cnt = min(L.batch_pos, L.n_pos - b0);
-  float s = 0.f;
-  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) s += group_loss[b0 + i];
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += part[w];
-    if (L.kind == KGREC_LOSS_BPR) t /= (static_cast<float>(cnt) * static_cast<float>(L.n_neg));
-    loss[blockIdx.x] = t;
-  }
-}
-
 }  // namespace kgrec
 
 using namespace kgrec;

@@ -1,0 +1,337 @@
+// Group-compact fused training kernels for the KG families (TransE, TransH / KTUP KG branch).
+//
+// The reference samples each negative by corrupting the head OR the tail of a positive
+// (utils/data.py:12-56), so a negative shares its relation and one entity with its positive.
+// Here that is the data format: negative k of positive j is ONE int32,
+//     corrupt[j*K + k] >= 0 : tail replaced by entity  corrupt
+//     corrupt[j*K + k] <  0 : head replaced by entity ~corrupt
+// One warp owns one positive and its K negatives.  The positive's rows are read once and kept
+// in registers (as h + r and r - t, projected for TransH), each negative costs ONE row read, and
+// in the backward the gradients of the shared rows are accumulated in registers across the
+// group: (3 + K) rows read and (3 + K) rows written per group of (1 + K) scored triples --
+// 481 + 481 bytes per triple at d = 100, K = 10 instead of 1216 + 1200.
+//
+// Reference arithmetic: transE.py:51-63, transH.py:58-71 (+ utils/misc.py:18-19),
+// utils/loss.py:8-16, 29-31; CPU restatement: oracle/kg_oracle.py.
+#include "train_dev.cuh"
+
+namespace kgrec {
+
+struct GroupArgs {
+  kgrec_tables T;
+  const void *ph, *pt, *pr;
+  int is64;
+  const int32_t* corrupt;
+  LossCfg L;
+};
+
+__device__ __forceinline__ const float* row_ptr(const float* base, uint32_t row, uint32_t ld) {
+  return base + static_cast<uint64_t>(row) * ld;        // one IMAD.WIDE.U32
+}
+
+template <int FAM, int NCH>
+struct GroupPos {           // the positive of a group, reduced to what its negatives need
+  using R = Row<NCH, true>;
+  static constexpr int NE = R::NE;
+  float h[NE], t[NE], w[NE];
+  float base_h[NE];         // proj(h) + r
+  float base_t[NE];         // r - proj(t)
+  float a, b;               // h.w, t.w (TransH)
+  float epos[NE];
+
+  __device__ __forceinline__ void load(const kgrec_tables& T, uint32_t ih, uint32_t it, uint32_t ir, int lane) {
+    const int d = T.dim;
+    float r[NE];
+    R::load(h, row_ptr(T.ent, ih, T.ld), d, lane);
+    R::load(t, row_ptr(T.ent, it, T.ld), d, lane);
+    R::load(r, row_ptr(T.rel, ir, T.ld), d, lane);
+    a = b = 0.f;
+    if (FAM == FAM_H) {
+      R::load(w, row_ptr(T.norm, ir, T.ld), d, lane);
+      a = R::dot(h, w);
+      b = R::dot(t, w);
+      warp_sum2(a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const float ph = (FAM == FAM_H) ? h[i] - a * w[i] : h[i];
+      const float pt = (FAM == FAM_H) ? t[i] - b * w[i] : t[i];
+      base_h[i] = ph + r[i];
+      base_t[i] = r[i] - pt;
+      epos[i] = base_h[i] - pt;                 // (proj h + r) - proj t, the reference's order
+    }
+  }
+  // residual of the negative whose corrupted row is x; ax = x.w (TransH, already reduced)
+  __device__ __forceinline__ void residual(const float (&x)[NE], bool head, float ax, float (&e)[NE]) const {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) {
+      const float px = (FAM == FAM_H) ? x[i] - ax * w[i] : x[i];
+      e[i] = head ? px + base_t[i] : base_h[i] - px;
+    }
+  }
+};
+
+template <int NE>
+__device__ __forceinline__ float dist_sum(const float (&e)[NE], int l1) {
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) acc += dist_term(e[i], l1);
+  return warp_sum(acc);
+}
+
+__device__ __forceinline__ uint32_t group_idx(const void* p, int j, int is64, int64_t rows, int32_t* status) {
+  const int64_t v = is64 ? __ldg(reinterpret_cast<const long long*>(p) + j)
+                         : static_cast<int64_t>(__ldg(reinterpret_cast<const int*>(p) + j));
+  if (static_cast<uint64_t>(v) >= static_cast<uint64_t>(rows)) {
+    if (status) *status = 1;
+    return 0u;
+  }
+  return static_cast<uint32_t>(v);
+}
+
+template <int FAM, int NCH>
+__global__ void __launch_bounds__(kThreads)
+k_group_fwd(const GroupArgs G, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
+            float* __restrict__ group_loss, int32_t* status) {
+  using R = Row<NCH, true>;
+  constexpr int NE = NCH * 4;
+  const kgrec_tables& T = G.T;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K = G.L.n_neg, d = T.dim, l1 = T.l1;
+  const int n_pos = static_cast<int>(G.L.n_pos);
+  const uint32_t n_ent = static_cast<uint32_t>(T.n_ent), ld = static_cast<uint32_t>(T.ld);
+  for (int j = blockIdx.x * kWarpsPerCta + wid; j < n_pos; j += gridDim.x * kWarpsPerCta) {
+    const int32_t* cj = G.corrupt + static_cast<int64_t>(j) * K;
+    int32_t c = K > 0 ? __ldg(cj) : 0;                       // first negative's id, in flight with the rows
+    const uint32_t ih = group_idx(G.ph, j, G.is64, T.n_ent, status);
+    const uint32_t it = group_idx(G.pt, j, G.is64, T.n_ent, status);
+    const uint32_t ir = group_idx(G.pr, j, G.is64, T.n_rel, status);
+    GroupPos<FAM, NCH> P;
+    P.load(T, ih, it, ir, lane);
+    const float sp = dist_sum(P.epos, l1);
+    float lsum = 0.f;
+    // software pipeline over the negatives: row k+1 is requested before row k is consumed
+    float x[NE], xn[NE];
+    bool head = c < 0;
+    uint32_t id = static_cast<uint32_t>(head ? ~c : c);
+    if (id >= n_ent) { if (status) *status = 1; id = 0; }
+    if (K > 0) R::load(x, row_ptr(T.ent, id, ld), d, lane);
+    for (int k = 0; k < K; ++k) {
+      bool headn = false;
+      if (k + 1 < K) {
+        const int32_t cn = __ldg(cj + k + 1);
+        headn = cn < 0;
+        uint32_t idn = static_cast<uint32_t>(headn ? ~cn : cn);
+        if (idn >= n_ent) { if (status) *status = 1; idn = 0; }
+        R::load(xn, row_ptr(T.ent, idn, ld), d, lane);
+      }
+      float ax = 0.f;
+      if (FAM == FAM_H) ax = warp_sum(R::dot(x, P.w));
+      float e[NE];
+      P.residual(x, head, ax, e);
+      const float sn = dist_sum(e, l1);
+      if (lane == 0) neg_scores[static_cast<int64_t>(j) * K + k] = sn;
+      lsum += loss_term(G.L, sp, sn);
+      head = headn;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) x[i] = xn[i];
+    }
+    if (lane == 0) {
+      pos_scores[j] = sp;
+      group_loss[j] = lsum;
+    }
+  }
+}
+
+// slots (mode 0): ent [n_pos * (2 + K), d] per group: h, t, c_1 .. c_K ; rel / norm [n_pos, d]
+template <int FAM, int NCH>
+__global__ void __launch_bounds__(kThreads)
+k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float* __restrict__ neg_scores,
+            const float grad_loss, const float* __restrict__ grad_loss_dev, const kgrec_grads Gr) {
+  using R = Row<NCH, true>;
+  constexpr int NE = NCH * 4;
+  const kgrec_tables& T = G.T;
+  const LossCfg& L = G.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K = L.n_neg, d = T.dim, l1 = T.l1;
+  const int n_pos = static_cast<int>(L.n_pos);
+  const uint32_t n_ent = static_cast<uint32_t>(T.n_ent), ld = static_cast<uint32_t>(T.ld);
+  const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
+  for (int j = blockIdx.x * kWarpsPerCta + wid; j < n_pos; j += gridDim.x * kWarpsPerCta) {
+    const int32_t* cj = G.corrupt + static_cast<int64_t>(j) * K;
+    const float* snj = neg_scores + static_cast<int64_t>(j) * K;
+    int32_t c = K > 0 ? __ldg(cj) : 0;
+    const uint32_t ih = group_idx(G.ph, j, G.is64, T.n_ent, nullptr);
+    const uint32_t it = group_idx(G.pt, j, G.is64, T.n_ent, nullptr);
+    const uint32_t ir = group_idx(G.pr, j, G.is64, T.n_rel, nullptr);
+    GroupPos<FAM, NCH> P;
+    P.load(T, ih, it, ir, lane);
+    // upstream of this group: dLoss/d(loss term) = grad_loss * grad_loss_dev[batch] * (1 | 1/(cnt K))
+    const int b = j / bp;
+    float up = grad_loss * (grad_loss_dev ? __ldg(grad_loss_dev + b) : 1.f);
+    if (L.kind == KGREC_LOSS_BPR) {
+      const int cnt = min(bp, n_pos - b * bp);
+      up /= static_cast<float>(cnt) * static_cast<float>(K);
+    }
+    const float sp = __ldg(pos_scores + j);
+    float cpos = 0.f;
+    for (int k = lane; k < K; k += 32) cpos += loss_dpos(L, sp, __ldg(snj + k));
+    cpos = warp_sum(cpos) * up;
+
+    float gh[NE], gt[NE], gr[NE], gw[NE];
+    {
+      float eps[NE];
+#pragma unroll
+      for (int i = 0; i < NE; ++i) eps[i] = cpos * ddist_term(P.epos[i], l1);
+      float ew = 0.f;
+      if (FAM == FAM_H) ew = warp_sum(R::dot(eps, P.w));
+      const float xw = P.a - P.b;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const float gx = (FAM == FAM_H) ? eps[i] - ew * P.w[i] : eps[i];
+        gh[i] = gx;
+        gt[i] = -gx;
+        gr[i] = eps[i];
+        gw[i] = (FAM == FAM_H) ? -(ew * (P.h[i] - P.t[i]) + xw * eps[i]) : 0.f;
+      }
+    }
+    const int64_t slot0 = static_cast<int64_t>(j) * (2 + K);
+    float x[NE], xn[NE];
+    bool head = c < 0;
+    uint32_t id = static_cast<uint32_t>(head ? ~c : c);
+    if (id >= n_ent) id = 0;
+    if (K > 0) R::load(x, row_ptr(T.ent, id, ld), d, lane);
+    for (int k = 0; k < K; ++k) {
+      bool headn = false;
+      uint32_t idn = 0;
+      if (k + 1 < K) {
+        const int32_t cn = __ldg(cj + k + 1);
+        headn = cn < 0;
+        idn = static_cast<uint32_t>(headn ? ~cn : cn);
+        if (idn >= n_ent) idn = 0;
+        R::load(xn, row_ptr(T.ent, idn, ld), d, lane);
+      }
+      const float ck = -loss_dpos(L, sp, __ldg(snj + k)) * up;     // dLoss/d(neg score)
+      float gc[NE];
+      if (ck != 0.f) {                                             // warp-uniform: inactive hinges cost nothing
+        float ax = 0.f;
+        if (FAM == FAM_H) ax = warp_sum(R::dot(x, P.w));
+        float e[NE], eps[NE];
+        P.residual(x, head, ax, e);
+#pragma unroll
+        for (int i = 0; i < NE; ++i) eps[i] = ck * ddist_term(e[i], l1);
+        float ew = 0.f;
+        if (FAM == FAM_H) ew = warp_sum(R::dot(eps, P.w));
+        const float xw = head ? ax - P.b : P.a - ax;               // (h' - t).w or (h - t').w
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          const float gx = (FAM == FAM_H) ? eps[i] - ew * P.w[i] : eps[i];
+          gr[i] += eps[i];
+          if (head) { gc[i] = gx; gt[i] -= gx; }
+          else { gc[i] = -gx; gh[i] += gx; }
+          if (FAM == FAM_H) {
+            const float xd = head ? x[i] - P.t[i] : P.h[i] - x[i];
+            gw[i] -= ew * xd + xw * eps[i];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) gc[i] = 0.f;
+      }
+      if (Gr.mode == 0) R::store_cs(Gr.ent + (slot0 + 2 + k) * d, gc, d, lane);
+      else if (ck != 0.f) R::red_add(Gr.ent + static_cast<uint64_t>(id) * d, gc, d, lane);
+      head = headn;
+      id = idn;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) x[i] = xn[i];
+    }
+    if (Gr.mode == 0) {
+      R::store_cs(Gr.ent + slot0 * d, gh, d, lane);
+      R::store_cs(Gr.ent + (slot0 + 1) * d, gt, d, lane);
+      R::store_cs(Gr.rel + static_cast<int64_t>(j) * d, gr, d, lane);
+      if (FAM == FAM_H) R::store_cs(Gr.norm + static_cast<int64_t>(j) * d, gw, d, lane);
+    } else {
+      R::red_add(Gr.ent + static_cast<uint64_t>(ih) * d, gh, d, lane);
+      R::red_add(Gr.ent + static_cast<uint64_t>(it) * d, gt, d, lane);
+      R::red_add(Gr.rel + static_cast<uint64_t>(ir) * d, gr, d, lane);
+      if (FAM == FAM_H) R::red_add(Gr.norm + static_cast<uint64_t>(ir) * d, gw, d, lane);
+    }
+  }
+}
+
+int make_plan(const kgrec_tables* T, int model, Plan* pl);
+
+static int group_check(const kgrec_tables* T, int model, Plan* pl, const void* ph, const void* pt, const void* pr,
+                       int idx_bytes, int64_t n_pos, const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
+                       int loss_kind) {
+  int rc = make_plan(T, model, pl);
+  if (rc) return rc;
+  if (pl->fam != FAM_E && pl->fam != FAM_H) {
+    set_error("corrupt-format ranking loss is built for TransE / TransH (model %d)", model);
+    return KGREC_ERR_UNSUPPORTED;
+  }
+  if (!pl->vec) { set_error("corrupt-format ranking loss needs embedding_size %% 4 == 0 and 16-byte aligned tables"); return KGREC_ERR_UNSUPPORTED; }
+  if (idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 4 or 8"); return KGREC_ERR_INVALID; }
+  if (!ph || !pt || !pr || !corrupt) { set_error("index array is NULL"); return KGREC_ERR_INVALID; }
+  if (loss_kind != KGREC_LOSS_MARGIN && loss_kind != KGREC_LOSS_BPR) { set_error("unknown loss %d", loss_kind); return KGREC_ERR_INVALID; }
+  if (n_pos < 0 || n_pos > 0x7fffffff || n_neg < 1 || batch_pos < 1) { set_error("bad n_pos / n_neg / batch_pos"); return KGREC_ERR_INVALID; }
+  if (T->n_ent > 0x7fffffffll) { set_error("corrupt format holds entity ids in 31 bits"); return KGREC_ERR_UNSUPPORTED; }
+  return KGREC_OK;
+}
+
+}  // namespace kgrec
+
+using namespace kgrec;
+
+#define KGREC_GROUP_DISPATCH(CALL)                                            \
+  if (pl.fam == FAM_E) {                                                      \
+    if (pl.nch == 1) { CALL(FAM_E, 1) } else if (pl.nch == 2) { CALL(FAM_E, 2) } else { CALL(FAM_E, 4) } \
+  } else {                                                                    \
+    if (pl.nch == 1) { CALL(FAM_H, 1) } else if (pl.nch == 2) { CALL(FAM_H, 2) } else { CALL(FAM_H, 4) } \
+  }
+
+extern "C" int kgrec_corrupt_loss_fwd(const kgrec_tables* tables, int model, const void* ph, const void* pt,
+                                      const void* pr, int idx_bytes, int64_t n_pos, const int32_t* corrupt,
+                                      int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
+                                      float* pos_scores, float* neg_scores, float* loss, void* workspace,
+                                      int32_t* status, kgrec_stream_t stream) {
+  Plan pl;
+  int rc = group_check(tables, model, &pl, ph, pt, pr, idx_bytes, n_pos, corrupt, n_neg, batch_pos, loss_kind);
+  if (rc) return rc;
+  if (!pos_scores || !neg_scores || !loss || !workspace) { set_error("output / workspace pointer is NULL"); return KGREC_ERR_INVALID; }
+  if (n_pos == 0) return KGREC_OK;
+  const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos}};
+  float* group_loss = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL(FAMV, NCHV) k_group_fwd<FAMV, NCHV><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, group_loss, status);
+  KGREC_GROUP_DISPATCH(CALL)
+#undef CALL
+  KGREC_CUDA_OK(cudaGetLastError());
+  const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
+  k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(group_loss, G.L, loss);
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}
+
+extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, const void* ph, const void* pt,
+                                      const void* pr, int idx_bytes, int64_t n_pos, const int32_t* corrupt,
+                                      int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
+                                      const float* pos_scores, const float* neg_scores, float grad_loss,
+                                      const float* grad_loss_dev, const kgrec_grads* grads, kgrec_stream_t stream) {
+  Plan pl;
+  int rc = group_check(tables, model, &pl, ph, pt, pr, idx_bytes, n_pos, corrupt, n_neg, batch_pos, loss_kind);
+  if (rc) return rc;
+  if (!pos_scores || !neg_scores) { set_error("saved scores are NULL"); return KGREC_ERR_INVALID; }
+  if (!grads || (grads->mode != 0 && grads->mode != 1) || !grads->ent || !grads->rel || (pl.fam == FAM_H && !grads->norm)) {
+    set_error("bad grads descriptor");
+    return KGREC_ERR_INVALID;
+  }
+  if (n_pos == 0) return KGREC_OK;
+  const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos}};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL(FAMV, NCHV) k_group_bwd<FAMV, NCHV><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, grad_loss, grad_loss_dev, *grads);
+  KGREC_GROUP_DISPATCH(CALL)
+#undef CALL
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}

@@ -246,3 +246,84 @@ class RankLossFunction(torch.autograd.Function):
                     idx[k] = torch.cat([pi[k], ni[k]])
         out = _finish_grads(cfg.model, weights, bufs, idx, cfg.grad_mode, needs)
         return (None,) * 9 + tuple(out[nm] for nm in names)
+
+
+class CorruptLossFunction(torch.autograd.Function):
+    """Fused ranking loss in the group-compact negative format (kgrec_corrupt_loss_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, cfg, pos, corrupt, n_neg, batch_pos, loss_kind, param, status, *tables):
+        names = MODEL_TABLES[cfg.model]
+        weights = dict(zip(names, tables))
+        T = make_tables(weights, cfg.dim, cfg.l1, cfg.use_gumbel, cfg.item2ent)
+        ph, pt, pr = pos
+        n_pos = ph.numel()
+        dev = ph.device
+        lib = _lib.load()
+        pos_s = torch.empty(n_pos, dtype=torch.float32, device=dev)
+        neg_s = torch.empty(n_pos * n_neg, dtype=torch.float32, device=dev)
+        loss = torch.empty((n_pos + batch_pos - 1) // batch_pos, dtype=torch.float32, device=dev)
+        ws = torch.empty(max(1, n_pos), dtype=torch.float32, device=dev)
+        _lib.check(lib.kgrec_corrupt_loss_fwd(
+            C.byref(T), cfg.model, _ptr(ph), _ptr(pt), _ptr(pr), _idx_bytes(ph, pt, pr), n_pos, _ptr(corrupt),
+            n_neg, batch_pos, loss_kind, float(param), _ptr(pos_s), _ptr(neg_s), _ptr(loss), _ptr(ws),
+            _ptr(status), _stream()))
+        ctx.cfg = cfg
+        ctx.args = (pos, corrupt, n_neg, batch_pos, loss_kind, float(param), pos_s, neg_s)
+        ctx.save_for_backward(*tables)
+        ctx.mark_non_differentiable(pos_s, neg_s)
+        return loss, pos_s, neg_s
+
+    @staticmethod
+    def backward(ctx, grad_loss, _gp, _gn):
+        cfg = ctx.cfg
+        pos, corrupt, n_neg, batch_pos, loss_kind, param, pos_s, neg_s = ctx.args
+        ph, pt, pr = pos
+        tables = ctx.saved_tensors
+        names = MODEL_TABLES[cfg.model]
+        weights = dict(zip(names, tables))
+        needs = dict(zip(names, ctx.needs_input_grad[8:]))
+        n_pos = ph.numel()
+        dev = ph.device
+        gl = grad_loss.reshape(-1).contiguous().float()
+        T = make_tables(weights, cfg.dim, cfg.l1, cfg.use_gumbel, cfg.item2ent)
+        g = Grads()
+        bufs = {}
+        dense = cfg.grad_mode == "dense"
+        g.mode = 1 if dense else 0
+        shapes = {"ent": n_pos * (2 + n_neg), "rel": n_pos, "norm": n_pos}
+        for name in names:
+            buf = torch.zeros_like(weights[name]) if dense else \
+                torch.empty((shapes[name], cfg.dim), dtype=torch.float32, device=dev)
+            bufs[name] = buf
+            setattr(g, name, buf.data_ptr())
+        lib = _lib.load()
+        _lib.check(lib.kgrec_corrupt_loss_bwd(
+            C.byref(T), cfg.model, _ptr(ph), _ptr(pt), _ptr(pr), _idx_bytes(ph, pt, pr), n_pos, _ptr(corrupt),
+            n_neg, batch_pos, loss_kind, param, _ptr(pos_s), _ptr(neg_s), 1.0, _ptr(gl), C.byref(g), _stream()))
+        out = []
+        for name in names:
+            if not needs.get(name, False):
+                out.append(None)
+            elif dense:
+                out.append(bufs[name])
+            else:
+                if name == "ent":
+                    cid = torch.where(corrupt < 0, ~corrupt, corrupt).view(n_pos, n_neg).long()
+                    idx = torch.cat([ph.long().view(-1, 1), pt.long().view(-1, 1), cid], dim=1).reshape(1, -1)
+                else:
+                    idx = pr.long().view(1, -1)
+                out.append(torch.sparse_coo_tensor(idx, bufs[name], size=tuple(weights[name].shape)))
+        return (None,) * 8 + tuple(out)
+
+
+def encode_corrupt(pos, neg):
+    """(nh, nt, nr) -> the int32 corrupt format, for negatives that differ from their positive
+    in exactly the head or the tail (what utils/data.py:12-56 produces).  Not validated here:
+    use only on sampler output."""
+    ph, pt, _ = pos
+    nh, nt, _ = neg
+    k = nh.numel() // ph.numel()
+    head = nh.view(-1, k) != ph.view(-1, 1)
+    c = torch.where(head, ~nh.view(-1, k).to(torch.int32), nt.view(-1, k).to(torch.int32))
+    return c.contiguous().view(-1)

@@ -135,6 +135,19 @@ class KGRecModule(nn.Module):
         return KF.RankLossFunction.apply(self._cfg(model, seed), pos, neg, n_neg, batch_pos or n_pos, kind, param,
                                          gumbel_u, self._status_buf(dev), *self._tables_for(model))
 
+    def _rank_loss_corrupt(self, model, pos, corrupt, loss, param, batch_pos=None):
+        dev = self._require_cuda()
+        pos = tuple(KF.as_index(x, dev) for x in pos)
+        corrupt = corrupt.to(dev, torch.int32, non_blocking=True).contiguous().view(-1)
+        n_pos = pos[0].numel()
+        if n_pos == 0 or corrupt.numel() % n_pos:
+            raise ValueError("corrupt ids must be a whole multiple of the positives")
+        kind = {"margin": _lib.LOSS_MARGIN, "bpr": _lib.LOSS_BPR}[loss]
+        self.kernel_launches += 2
+        return KF.CorruptLossFunction.apply(self._cfg(model, 0), pos, corrupt, corrupt.numel() // n_pos,
+                                            batch_pos or n_pos, kind, param, self._status_buf(dev),
+                                            *self._tables_for(model))
+
     # -- evaluation helpers ------------------------------------------------------
     def _eval(self, model, side, q, r, mode, **kw):
         dev = self._require_cuda()

@@ -90,6 +90,9 @@ class jTransUPModel(RecModelBase):
         """Fused KG branch: TransH on (ent, rel, norm)."""
         return self._rank_loss(_lib.TRANSH, pos, neg, loss, margin, batch_pos)
 
+    def kg_rank_loss_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None):
+        return self._rank_loss_corrupt(_lib.TRANSH, pos, corrupt, loss, margin, batch_pos)
+
     # -- evaluation ----------------------------------------------------------------------------
     def _rec_catalog(self):
         """ie = Item + Ent[item2ent] for every item (jTransUP.py:177-181), built on the device."""

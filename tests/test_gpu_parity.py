@@ -438,3 +438,59 @@ def test_eval_scores_independent_of_row_position(d):
         fnp = full.cpu().numpy()
         for b in range(0, Q, 17):
             assert cnt[b] == O.sort_order(fnp[b]).tolist().index(int(gold[b]))
+
+
+@pytest.mark.parametrize("cls_name", ["TransEModel", "TransHModel"])
+@pytest.mark.parametrize("l1", [False, True])
+@pytest.mark.parametrize("loss,param", [("margin", 1.0), ("bpr", -1.0)])
+@pytest.mark.parametrize("d", [100, 200])
+def test_corrupt_format_matches_expanded_triples(cls_name, l1, loss, param, d):
+    """The group-compact negative format gives the same scores, losses and gradients as the
+    expanded (nh, nt, nr) triples, and both match the oracle."""
+    import kgrec_b200 as K
+    from kgrec_b200 import functional as KF
+    torch.manual_seed(3)
+    rng = np.random.RandomState(d + int(l1))
+    E, R, B, KN = 4000, 9, 203, 5
+    m = getattr(K, cls_name)(l1, d, E, R)
+    W = np_tables(m)
+    T = (W["ent"], W["rel"]) + ((W["norm"],) if "norm" in W else ())
+    score, grads = (O.transe_score, O.transe_grads) if cls_name == "TransEModel" else (O.transh_score, O.transh_grads)
+    h, t, r = rng.randint(0, E, B), rng.randint(0, E, B), rng.randint(0, R, B)
+    cid = rng.randint(0, E, B * KN)
+    head = rng.rand(B * KN) < 0.5
+    corrupt = np.where(head, ~cid, cid).astype(np.int32)
+    nh = np.where(head, cid, np.repeat(h, KN))
+    nt = np.where(head, np.repeat(t, KN), cid)
+    nr = np.repeat(r, KN)
+    pos, neg = (lt(h), lt(t), lt(r)), (lt(nh), lt(nt), lt(nr))
+    tc = torch.from_numpy(corrupt).cuda()
+    enc = KF.encode_corrupt(pos, neg)
+    same = (nh == np.repeat(h, KN)) & (nt == np.repeat(t, KN))          # corrupted id happened to equal the original
+    assert torch.equal(enc[torch.from_numpy(~same).cuda()], tc[torch.from_numpy(~same).cuda()])
+    op, on = score(*T, h, t, r, l1), score(*T, nh, nt, nr, l1)
+    if loss == "margin":
+        want_loss = [O.margin_loss(np.repeat(op[b:b + 64], KN), on[b * KN:(b + 64) * KN], param) for b in range(0, B, 64)]
+        gp, gn = O.margin_loss_grads(np.repeat(op, KN), on, param)
+    else:
+        want_loss = [O.bpr_loss(np.repeat(op[b:b + 64], KN), on[b * KN:(b + 64) * KN], param) for b in range(0, B, 64)]
+        gp = np.concatenate([O.bpr_loss_grads(np.repeat(op[b:b + 64], KN), on[b * KN:(b + 64) * KN], param)[0] for b in range(0, B, 64)])
+        gn = -gp
+    a = grads(*T, np.repeat(h, KN), np.repeat(t, KN), np.repeat(r, KN), l1, gp)
+    b2 = grads(*T, nh, nt, nr, l1, gn)
+    for gm in ("dense", "sparse"):
+        m.grad_mode = gm
+        m.zero_grad()
+        cl, cp, cn = m.rank_loss_corrupt(pos, tc, margin=param, loss=loss, batch_pos=64)
+        close(cp, op)
+        close(cn, on)
+        close(cl, want_loss, rtol=2e-4)
+        cl.sum().backward()
+        got = grads_by_name(m)
+        for k in a:
+            close(got[k + "_embeddings"], a[k] + b2[k], rtol=2e-3, atol=2e-4)
+        m.zero_grad()
+        fl, fp, fn = m.rank_loss(pos, neg, margin=param, loss=loss, batch_pos=64)
+        close(fl, cl.detach().cpu().numpy(), rtol=1e-5)
+        close(fn, cn.detach().cpu().numpy(), rtol=1e-5)
+    m.check_indices()
