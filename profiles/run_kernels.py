@@ -17,7 +17,7 @@ if what in ("train", "all"):
     ix = [x.to(dev) for x in bench.make_indices(torch, gen, 256)]
     for _ in range(2):
         m.zero_grad(set_to_none=True)
-        loss, _, _ = m.rank_loss(tuple(ix[:3]), tuple(ix[3:]), margin=1.0, batch_pos=bench.BATCH)
+        loss, _, _ = m.rank_loss_corrupt(tuple(ix[:3]), ix[6], margin=1.0, batch_pos=bench.BATCH)
         loss.sum().backward()
     torch.cuda.synchronize()
 if what in ("eval", "all"):
