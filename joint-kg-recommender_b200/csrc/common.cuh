@@ -23,6 +23,7 @@ void set_error(const char* fmt, ...);
     }                                                                              \
   } while (0)
 int sm_count();
+float l2_keep_fraction(double table_bytes);   // share of a table's lines worth pinning in L2
 
 // ---- warp reductions --------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -89,6 +90,32 @@ __device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, 
                : "memory");
 }
 
+// ---- L2 cache policies ---------------------------------------------------------------------
+// Embedding rows are re-read (by other triples, by the backward, by the next step) while
+// gradient rows are written once and consumed later by a different kernel: table loads carry an
+// evict_last policy on a fraction of their lines sized to fit L2, gradient stores evict_first,
+// so the write stream does not push the tables out of the 126 MB L2.
+__device__ __forceinline__ uint64_t policy_evict_last(float fraction) {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_unchanged.b64 %0, %1;" : "=l"(p) : "f"(fraction));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg_f4_hint(const float4* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void stg_f4_hint(float4* p, float a, float b, float c, float d, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "l"(pol)
+               : "memory");
+}
+
 // One embedding row spread over a warp.  VEC: lane owns float4 chunks lane, lane+32, ...
 // (128-bit loads, requires d % 4 == 0 and 16-byte aligned rows); otherwise lane owns
 // scalars lane, lane+32, ...  Lanes / slots past d hold zeros so every reduction can run
@@ -114,6 +141,25 @@ struct Row {
         const int j = lane + 32 * e;
         v[e] = (j < d) ? __ldg(row + j) : 0.f;
       }
+    }
+  }
+  // vector path with an L2 cache policy (see policy_evict_last)
+  __device__ __forceinline__ static void load_hint(float (&v)[NE], const float* __restrict__ row, int d, int lane, uint64_t pol) {
+    static_assert(VEC, "cache-hinted loads are built for the 128-bit path");
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c * 4 < d) t = ldg_f4_hint(reinterpret_cast<const float4*>(row) + c, pol);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  }
+  __device__ __forceinline__ static void store_hint(float* __restrict__ row, const float (&v)[NE], int d, int lane, uint64_t pol) {
+    static_assert(VEC, "cache-hinted stores are built for the 128-bit path");
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c * 4 < d) stg_f4_hint(reinterpret_cast<float4*>(row) + c, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3], pol);
     }
   }
   // shared-memory variant (tables staged by the CTA)

@@ -537,6 +537,16 @@ k_eval(const EvalArgs A) {
   }
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: one instruction, two lanes of the FMA pipe) ----------
+typedef unsigned long long f32x2;     // two floats in one 64-bit register pair
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 splat2(float v) { f32x2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float sum2(f32x2 v) { return lo2(v) + hi2(v); }
+__device__ __forceinline__ float abssum2(f32x2 v) { return fabsf(lo2(v)) + fabsf(hi2(v)); }
+
 // Cold path of the tiled kernel's top-K epilogue, kept out of line so the hot loop and the
 // 32 unrolled threshold tests stay small enough for the instruction cache.  Returns the new
 // score-bits threshold of the query.
@@ -750,11 +760,12 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
     mbar_wait(full + s, static_cast<uint32_t>((g / stages) & 1));
 
-    float acc[RQ][RN];
+    // accumulators hold two partial sums each (even / odd dimension of every 8-byte pair)
+    f32x2 acc2[RQ][RN];
 #pragma unroll
     for (int qi = 0; qi < RQ; ++qi)
 #pragma unroll
-      for (int j = 0; j < RN; ++j) acc[qi][j] = 0.f;
+      for (int j = 0; j < RN; ++j) acc2[qi][j] = 0ull;
     const float* xrow = tile + lane * d;
     [[maybe_unused]] int skj[RN];
 #pragma unroll
@@ -765,88 +776,92 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
         skj[j] = (use_skew && r < rows) ? (__ldg(A.cat_ids + row0 + r) & 7) : 0;
       }
     }
+    // chunk (16 bytes = two packed pairs) of row j / of query vector v at walk step k4
+#define KGREC_LOAD_X(k4)                                                                   \
+    int kk = (k4) + skew0; if (kk >= nk4) kk -= nk4;                                        \
+    ulonglong2 xv[RN];                                                                      \
+    int kj[RN];                                                                             \
+    _Pragma("unroll")                                                                       \
+    for (int j = 0; j < RN; ++j) {                                                          \
+      kj[j] = kk;                                                                           \
+      if constexpr (IDS) { kj[j] = (k4) + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }         \
+      xv[j] = *reinterpret_cast<const ulonglong2*>(xrow + j * 32 * d + 4 * kj[j]);          \
+    }
+#define KGREC_QVEC(base, qi, j) (*reinterpret_cast<const ulonglong2*>((base) + (qi) * d + 4 * (IDS ? kj[j] : kk)))
 
     if constexpr (KIND == KIND_HYPER) {
-      float sd[RQ][RN];                        // phase 1: sd[q][n] = x_n . w_q
+      f32x2 sd2[RQ][RN];                       // phase 1: sd[q][n] = x_n . w_q
 #pragma unroll
       for (int qi = 0; qi < RQ; ++qi)
 #pragma unroll
-        for (int j = 0; j < RN; ++j) sd[qi][j] = 0.f;
+        for (int j = 0; j < RN; ++j) sd2[qi][j] = 0ull;
 #pragma unroll 1
       for (int k4 = 0; k4 < nk4; ++k4) {
-        int kk = k4 + skew0; if (kk >= nk4) kk -= nk4;
-        float4 xv[RN];
-        int kj[RN];
-#pragma unroll
-        for (int j = 0; j < RN; ++j) {
-          kj[j] = kk;
-          if constexpr (IDS) { kj[j] = k4 + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }
-          xv[j] = *reinterpret_cast<const float4*>(xrow + j * 32 * d + 4 * kj[j]);
-        }
+        KGREC_LOAD_X(k4)
 #pragma unroll
         for (int qi = 0; qi < RQ; ++qi) {
-          float4 wv = *reinterpret_cast<const float4*>(wq + qi * d + 4 * kk);
+          ulonglong2 wv = KGREC_QVEC(wq, qi, 0);
 #pragma unroll
           for (int j = 0; j < RN; ++j) {
-            if constexpr (IDS) wv = *reinterpret_cast<const float4*>(wq + qi * d + 4 * kj[j]);
-            sd[qi][j] = fmaf(xv[j].x, wv.x, fmaf(xv[j].y, wv.y, fmaf(xv[j].z, wv.z, fmaf(xv[j].w, wv.w, sd[qi][j]))));
+            if constexpr (IDS) wv = KGREC_QVEC(wq, qi, j);
+            sd2[qi][j] = fma2(xv[j].x, wv.x, fma2(xv[j].y, wv.y, sd2[qi][j]));
           }
         }
       }
+      float sd[RQ][RN];
+#pragma unroll
+      for (int qi = 0; qi < RQ; ++qi)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) sd[qi][j] = sum2(sd2[qi][j]);
 #pragma unroll 1
       for (int k4 = 0; k4 < nk4; ++k4) {         // phase 2: L(c_q - x_n + s w_q)
-        int kk = k4 + skew0; if (kk >= nk4) kk -= nk4;
-        float4 xv[RN];
-        int kj[RN];
-#pragma unroll
-        for (int j = 0; j < RN; ++j) {
-          kj[j] = kk;
-          if constexpr (IDS) { kj[j] = k4 + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }
-          xv[j] = *reinterpret_cast<const float4*>(xrow + j * 32 * d + 4 * kj[j]);
-        }
+        KGREC_LOAD_X(k4)
 #pragma unroll
         for (int qi = 0; qi < RQ; ++qi) {
-          float4 cv = *reinterpret_cast<const float4*>(cq + qi * d + 4 * kk);
-          float4 wv = *reinterpret_cast<const float4*>(wq + qi * d + 4 * kk);
+          ulonglong2 cv = KGREC_QVEC(cq, qi, 0), wv = KGREC_QVEC(wq, qi, 0);
 #pragma unroll
           for (int j = 0; j < RN; ++j) {
-            if constexpr (IDS) {
-              cv = *reinterpret_cast<const float4*>(cq + qi * d + 4 * kj[j]);
-              wv = *reinterpret_cast<const float4*>(wq + qi * d + 4 * kj[j]);
+            if constexpr (IDS) { cv = KGREC_QVEC(cq, qi, j); wv = KGREC_QVEC(wq, qi, j); }
+            const f32x2 s2 = splat2(sd[qi][j]);
+            const f32x2 e01 = fma2(s2, wv.x, sub2(cv.x, xv[j].x));
+            const f32x2 e23 = fma2(s2, wv.y, sub2(cv.y, xv[j].y));
+            if (L1) {
+              const float t = abssum2(e01) + abssum2(e23);
+              acc2[qi][j] = static_cast<f32x2>(__float_as_uint(__uint_as_float(static_cast<uint32_t>(acc2[qi][j])) + t));
+            } else {
+              acc2[qi][j] = fma2(e01, e01, fma2(e23, e23, acc2[qi][j]));
             }
-            const float sj = sd[qi][j];
-            const float e0 = fmaf(sj, wv.x, cv.x - xv[j].x), e1 = fmaf(sj, wv.y, cv.y - xv[j].y);
-            const float e2 = fmaf(sj, wv.z, cv.z - xv[j].z), e3 = fmaf(sj, wv.w, cv.w - xv[j].w);
-            if (L1) acc[qi][j] += fabsf(e0) + fabsf(e1) + fabsf(e2) + fabsf(e3);
-            else acc[qi][j] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, acc[qi][j]))));
           }
         }
       }
     } else {
 #pragma unroll 1
       for (int k4 = 0; k4 < nk4; ++k4) {
-        int kk = k4 + skew0; if (kk >= nk4) kk -= nk4;
-        float4 xv[RN];
-        int kj[RN];
-#pragma unroll
-        for (int j = 0; j < RN; ++j) {
-          kj[j] = kk;
-          if constexpr (IDS) { kj[j] = k4 + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }
-          xv[j] = *reinterpret_cast<const float4*>(xrow + j * 32 * d + 4 * kj[j]);
-        }
+        KGREC_LOAD_X(k4)
 #pragma unroll
         for (int qi = 0; qi < RQ; ++qi) {
-          float4 cv = *reinterpret_cast<const float4*>(cq + qi * d + 4 * kk);
+          ulonglong2 cv = KGREC_QVEC(cq, qi, 0);
 #pragma unroll
           for (int j = 0; j < RN; ++j) {
-            if constexpr (IDS) cv = *reinterpret_cast<const float4*>(cq + qi * d + 4 * kj[j]);
-            const float e0 = cv.x - xv[j].x, e1 = cv.y - xv[j].y, e2 = cv.z - xv[j].z, e3 = cv.w - xv[j].w;
-            if (L1) acc[qi][j] += fabsf(e0) + fabsf(e1) + fabsf(e2) + fabsf(e3);
-            else acc[qi][j] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, acc[qi][j]))));
+            if constexpr (IDS) cv = KGREC_QVEC(cq, qi, j);
+            const f32x2 e01 = sub2(cv.x, xv[j].x), e23 = sub2(cv.y, xv[j].y);
+            if (L1) {
+              const float t = abssum2(e01) + abssum2(e23);
+              acc2[qi][j] = static_cast<f32x2>(__float_as_uint(__uint_as_float(static_cast<uint32_t>(acc2[qi][j])) + t));
+            } else {
+              acc2[qi][j] = fma2(e01, e01, fma2(e23, e23, acc2[qi][j]));
+            }
           }
         }
       }
     }
+#undef KGREC_LOAD_X
+#undef KGREC_QVEC
+    float acc[RQ][RN];
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi)
+#pragma unroll
+      for (int j = 0; j < RN; ++j) acc[qi][j] = sum2(acc2[qi][j]);
     // the tile is consumed: release the stage before the (register-only) epilogue
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);

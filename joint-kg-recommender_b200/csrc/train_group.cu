@@ -23,6 +23,7 @@ struct GroupArgs {
   int is64;
   const int32_t* corrupt;
   LossCfg L;
+  float keep;               // fraction of table lines loaded with the evict_last policy
 };
 
 __device__ __forceinline__ const float* row_ptr(const float* base, uint32_t row, uint32_t ld) {
@@ -39,15 +40,15 @@ struct GroupPos {           // the positive of a group, reduced to what its nega
   float a, b;               // h.w, t.w (TransH)
   float epos[NE];
 
-  __device__ __forceinline__ void load(const kgrec_tables& T, uint32_t ih, uint32_t it, uint32_t ir, int lane) {
+  __device__ __forceinline__ void load(const kgrec_tables& T, uint32_t ih, uint32_t it, uint32_t ir, int lane, uint64_t pol) {
     const int d = T.dim;
     float r[NE];
-    R::load(h, row_ptr(T.ent, ih, T.ld), d, lane);
-    R::load(t, row_ptr(T.ent, it, T.ld), d, lane);
-    R::load(r, row_ptr(T.rel, ir, T.ld), d, lane);
+    R::load_hint(h, row_ptr(T.ent, ih, T.ld), d, lane, pol);
+    R::load_hint(t, row_ptr(T.ent, it, T.ld), d, lane, pol);
+    R::load_hint(r, row_ptr(T.rel, ir, T.ld), d, lane, pol);
     a = b = 0.f;
     if (FAM == FAM_H) {
-      R::load(w, row_ptr(T.norm, ir, T.ld), d, lane);
+      R::load_hint(w, row_ptr(T.norm, ir, T.ld), d, lane, pol);
       a = R::dot(h, w);
       b = R::dot(t, w);
       warp_sum2(a, b);
@@ -100,6 +101,7 @@ k_group_fwd(const GroupArgs G, float* __restrict__ pos_scores, float* __restrict
   const int K = G.L.n_neg, d = T.dim, l1 = T.l1;
   const int n_pos = static_cast<int>(G.L.n_pos);
   const uint32_t n_ent = static_cast<uint32_t>(T.n_ent), ld = static_cast<uint32_t>(T.ld);
+  const uint64_t pol_keep = policy_evict_last(G.keep);
   for (int j = blockIdx.x * kWarpsPerCta + wid; j < n_pos; j += gridDim.x * kWarpsPerCta) {
     const int32_t* cj = G.corrupt + static_cast<int64_t>(j) * K;
     int32_t c = K > 0 ? __ldg(cj) : 0;                       // first negative's id, in flight with the rows
@@ -107,7 +109,7 @@ k_group_fwd(const GroupArgs G, float* __restrict__ pos_scores, float* __restrict
     const uint32_t it = group_idx(G.pt, j, G.is64, T.n_ent, status);
     const uint32_t ir = group_idx(G.pr, j, G.is64, T.n_rel, status);
     GroupPos<FAM, NCH> P;
-    P.load(T, ih, it, ir, lane);
+    P.load(T, ih, it, ir, lane, pol_keep);
     const float sp = dist_sum(P.epos, l1);
     float lsum = 0.f;
     // software pipeline over the negatives: row k+1 is requested before row k is consumed
@@ -115,7 +117,7 @@ k_group_fwd(const GroupArgs G, float* __restrict__ pos_scores, float* __restrict
     bool head = c < 0;
     uint32_t id = static_cast<uint32_t>(head ? ~c : c);
     if (id >= n_ent) { if (status) *status = 1; id = 0; }
-    if (K > 0) R::load(x, row_ptr(T.ent, id, ld), d, lane);
+    if (K > 0) R::load_hint(x, row_ptr(T.ent, id, ld), d, lane, pol_keep);
     for (int k = 0; k < K; ++k) {
       bool headn = false;
       if (k + 1 < K) {
@@ -123,7 +125,7 @@ k_group_fwd(const GroupArgs G, float* __restrict__ pos_scores, float* __restrict
         headn = cn < 0;
         uint32_t idn = static_cast<uint32_t>(headn ? ~cn : cn);
         if (idn >= n_ent) { if (status) *status = 1; idn = 0; }
-        R::load(xn, row_ptr(T.ent, idn, ld), d, lane);
+        R::load_hint(xn, row_ptr(T.ent, idn, ld), d, lane, pol_keep);
       }
       float ax = 0.f;
       if (FAM == FAM_H) ax = warp_sum(R::dot(x, P.w));
@@ -157,6 +159,7 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
   const int n_pos = static_cast<int>(L.n_pos);
   const uint32_t n_ent = static_cast<uint32_t>(T.n_ent), ld = static_cast<uint32_t>(T.ld);
   const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
+  const uint64_t pol_keep = policy_evict_last(G.keep), pol_stream = policy_evict_first();
   for (int j = blockIdx.x * kWarpsPerCta + wid; j < n_pos; j += gridDim.x * kWarpsPerCta) {
     const int32_t* cj = G.corrupt + static_cast<int64_t>(j) * K;
     const float* snj = neg_scores + static_cast<int64_t>(j) * K;
@@ -165,7 +168,7 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
     const uint32_t it = group_idx(G.pt, j, G.is64, T.n_ent, nullptr);
     const uint32_t ir = group_idx(G.pr, j, G.is64, T.n_rel, nullptr);
     GroupPos<FAM, NCH> P;
-    P.load(T, ih, it, ir, lane);
+    P.load(T, ih, it, ir, lane, pol_keep);
     // upstream of this group: dLoss/d(loss term) = grad_loss * grad_loss_dev[batch] * (1 | 1/(cnt K))
     const int b = j / bp;
     float up = grad_loss * (grad_loss_dev ? __ldg(grad_loss_dev + b) : 1.f);
@@ -200,7 +203,7 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
     bool head = c < 0;
     uint32_t id = static_cast<uint32_t>(head ? ~c : c);
     if (id >= n_ent) id = 0;
-    if (K > 0) R::load(x, row_ptr(T.ent, id, ld), d, lane);
+    if (K > 0) R::load_hint(x, row_ptr(T.ent, id, ld), d, lane, pol_keep);
     for (int k = 0; k < K; ++k) {
       bool headn = false;
       uint32_t idn = 0;
@@ -209,7 +212,7 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
         headn = cn < 0;
         idn = static_cast<uint32_t>(headn ? ~cn : cn);
         if (idn >= n_ent) idn = 0;
-        R::load(xn, row_ptr(T.ent, idn, ld), d, lane);
+        R::load_hint(xn, row_ptr(T.ent, idn, ld), d, lane, pol_keep);
       }
       const float ck = -loss_dpos(L, sp, __ldg(snj + k)) * up;     // dLoss/d(neg score)
       float gc[NE];
@@ -238,7 +241,7 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
 #pragma unroll
         for (int i = 0; i < NE; ++i) gc[i] = 0.f;
       }
-      if (Gr.mode == 0) R::store_cs(Gr.ent + (slot0 + 2 + k) * d, gc, d, lane);
+      if (Gr.mode == 0) R::store_hint(Gr.ent + (slot0 + 2 + k) * d, gc, d, lane, pol_stream);
       else if (ck != 0.f) R::red_add(Gr.ent + static_cast<uint64_t>(id) * d, gc, d, lane);
       head = headn;
       id = idn;
@@ -246,10 +249,10 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
       for (int i = 0; i < NE; ++i) x[i] = xn[i];
     }
     if (Gr.mode == 0) {
-      R::store_cs(Gr.ent + slot0 * d, gh, d, lane);
-      R::store_cs(Gr.ent + (slot0 + 1) * d, gt, d, lane);
-      R::store_cs(Gr.rel + static_cast<int64_t>(j) * d, gr, d, lane);
-      if (FAM == FAM_H) R::store_cs(Gr.norm + static_cast<int64_t>(j) * d, gw, d, lane);
+      R::store_hint(Gr.ent + slot0 * d, gh, d, lane, pol_stream);
+      R::store_hint(Gr.ent + (slot0 + 1) * d, gt, d, lane, pol_stream);
+      R::store_hint(Gr.rel + static_cast<int64_t>(j) * d, gr, d, lane, pol_stream);
+      if (FAM == FAM_H) R::store_hint(Gr.norm + static_cast<int64_t>(j) * d, gw, d, lane, pol_stream);
     } else {
       R::red_add(Gr.ent + static_cast<uint64_t>(ih) * d, gh, d, lane);
       R::red_add(Gr.ent + static_cast<uint64_t>(it) * d, gt, d, lane);
@@ -300,7 +303,8 @@ extern "C" int kgrec_corrupt_loss_fwd(const kgrec_tables* tables, int model, con
   if (rc) return rc;
   if (!pos_scores || !neg_scores || !loss || !workspace) { set_error("output / workspace pointer is NULL"); return KGREC_ERR_INVALID; }
   if (n_pos == 0) return KGREC_OK;
-  const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos}};
+  const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos},
+                    l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   float* group_loss = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CALL(FAMV, NCHV) k_group_fwd<FAMV, NCHV><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, group_loss, status);
@@ -327,7 +331,8 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
     return KGREC_ERR_INVALID;
   }
   if (n_pos == 0) return KGREC_OK;
-  const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos}};
+  const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos},
+                    l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CALL(FAMV, NCHV) k_group_bwd<FAMV, NCHV><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, grad_loss, grad_loss_dev, *grads);
   KGREC_GROUP_DISPATCH(CALL)

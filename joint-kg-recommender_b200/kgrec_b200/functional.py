@@ -122,7 +122,7 @@ def _finish_grads(model, weights, bufs, idx, mode, needs):
         buf = bufs[name]
         if name in _SLOT_TABLES[model] and mode != "dense":
             w = weights[name]
-            out[name] = torch.sparse_coo_tensor(idx[name].view(1, -1), buf, size=tuple(w.shape))
+            out[name] = torch.sparse_coo_tensor(idx[name].view(1, -1), buf, size=tuple(w.shape), check_invariants=False)
         else:
             out[name] = buf
     return out
@@ -313,7 +313,7 @@ class CorruptLossFunction(torch.autograd.Function):
                     idx = torch.cat([ph.long().view(-1, 1), pt.long().view(-1, 1), cid], dim=1).reshape(1, -1)
                 else:
                     idx = pr.long().view(1, -1)
-                out.append(torch.sparse_coo_tensor(idx, bufs[name], size=tuple(weights[name].shape)))
+                out.append(torch.sparse_coo_tensor(idx, bufs[name], size=tuple(weights[name].shape), check_invariants=False))
         return (None,) * 8 + tuple(out)
 
 
