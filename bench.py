@@ -76,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -211,13 +211,17 @@ def run_ours(args):
     dev_sets = [[x.to(dev) for x in hs] for hs in host_sets]
     loss_host = torch.empty(nb, dtype=torch.float32).pin_memory()
 
-    def step_device(s, ev=None, generic=False):
+    def step_device(s, ev=None, mode="step"):
         ix = dev_sets[s % n_sets]
         model.zero_grad(set_to_none=True)
         if ev: ev[0].record()
-        if generic:     # negatives as full (nh, nt, nr) triples, the reference drivers' format
+        if mode == "step":      # forward + margin loss + backward in one kernel, group-compact negatives
+            loss, _, _ = model.loss_step_corrupt(tuple(ix[:3]), ix[6], margin=1.0, batch_pos=BATCH)
+            if ev: ev[1].record(); ev[2].record()
+            return loss
+        if mode == "generic":   # negatives as full (nh, nt, nr) triples, the reference drivers' format
             loss, _, _ = model.rank_loss(tuple(ix[:3]), tuple(ix[3:6]), margin=1.0, batch_pos=BATCH)
-        else:           # negatives as one corrupted-entity id each (group-compact format)
+        else:                   # group-compact negatives, separate forward and autograd backward
             loss, _, _ = model.rank_loss_corrupt(tuple(ix[:3]), ix[6], margin=1.0, batch_pos=BATCH)
         if ev: ev[1].record()
         loss.sum().backward()
@@ -228,8 +232,7 @@ def run_ours(args):
         hs = host_sets[s % n_sets]
         ix = [hs[i].to(dev, non_blocking=True) for i in (0, 1, 2, 6)]
         model.zero_grad(set_to_none=True)
-        loss, _, _ = model.rank_loss_corrupt(tuple(ix[:3]), ix[3], margin=1.0, batch_pos=BATCH)
-        loss.sum().backward()
+        loss, _, _ = model.loss_step_corrupt(tuple(ix[:3]), ix[3], margin=1.0, batch_pos=BATCH)
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the caller reads the losses
         return loss_host
@@ -247,13 +250,13 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident timing ---------------------------------------------------------
-    for s in range(args.warmup):
-        step_device(s)
-    launches0 = model.kernel_launches
-    sampler = ClockSampler(local)
-    barrier()
+    sampler = ClockSampler(local)          # samples from the warm-up to the end of the e2e leg (all under load)
     if rank == 0:
         sampler.start()
+    for s in range(max(args.warmup, 50)):  # >= 50 ms of load so the clock record has samples
+        step_device(s)
+    launches0 = model.kernel_launches
+    barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_begin.record()
@@ -261,10 +264,8 @@ def run_ours(args):
         step_device(s, evs[s])
     t_end.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     total_ms = max_over_ranks(t_begin.elapsed_time(t_end))
-    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps     # fused forward + per-batch loss reduce
-    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps     # loss.sum() + backward kernel
+    step_kernel_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps   # k_group_step + k_batch_loss + glue
     launches = model.kernel_launches - launches0
     ms_per_step = total_ms / args.steps
     value = world * n_tri / (ms_per_step * 1e-3)
@@ -280,30 +281,36 @@ def run_ours(args):
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
     h2d = sum(host_sets[0][i].numel() * host_sets[0][i].element_size() for i in (0, 1, 2, 6))
     e2e = {"value": world * n_tri / (e2e_ms * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": nb * 4, "ms_per_step": e2e_ms}
 
-    # ---- the same step with negatives as full (nh, nt, nr) triples (reference drivers' format)
-    for s in range(2):
-        step_device(s, generic=True)
-    torch.cuda.synchronize()
-    gevs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    for s in range(args.steps):
-        step_device(s, gevs[s], generic=True)
-    torch.cuda.synchronize()
-    gen_fwd_ms = sum(e[0].elapsed_time(e[1]) for e in gevs) / args.steps
-    gen_bwd_ms = sum(e[1].elapsed_time(e[2]) for e in gevs) / args.steps
+    # ---- the same work as separate forward / autograd-backward kernels, in both negative formats
+    split = {}
+    for mode in ("split", "generic"):
+        for s in range(2):
+            step_device(s, mode=mode)
+        torch.cuda.synchronize()
+        gevs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        for s in range(args.steps):
+            step_device(s, gevs[s], mode=mode)
+        torch.cuda.synchronize()
+        split[mode] = (sum(e[0].elapsed_time(e[1]) for e in gevs) / args.steps,
+                       sum(e[1].elapsed_time(e[2]) for e in gevs) / args.steps)
+    fwd_ms, bwd_ms = split["split"]
+    gen_fwd_ms, gen_bwd_ms = split["generic"]
 
     # ---- single-batch latency (the reference's actual training shape) --------------------
     small = [x[:BATCH * (1 if i < 3 else K_NEG)].contiguous() for i, x in enumerate(dev_sets[0])]
     for _ in range(5):
-        model.rank_loss_corrupt(tuple(small[:3]), small[6], margin=1.0)
+        model.loss_step_corrupt(tuple(small[:3]), small[6], margin=1.0)
     torch.cuda.synchronize()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0.record()
     for _ in range(50):
-        model.rank_loss_corrupt(tuple(small[:3]), small[6], margin=1.0)
+        model.zero_grad(set_to_none=True)
+        model.loss_step_corrupt(tuple(small[:3]), small[6], margin=1.0)
     s1.record()
     torch.cuda.synchronize()
     single_us = s0.elapsed_time(s1) * 1e3 / 50
@@ -349,12 +356,13 @@ def run_ours(args):
     n_fwd, n_bwd = n_tri, n_tri
     fwd_gbs = n_fwd * FWD_GROUP_BYTES / (fwd_ms * 1e-3) / 1e9
     bwd_gbs = n_bwd * BWD_GROUP_BYTES / (bwd_ms * 1e-3) / 1e9
-    dom = "k_group_bwd" if bwd_ms >= fwd_ms else "k_group_fwd"
-    roof = {"bound": "hbm", "kernel": dom, "achieved": bwd_gbs if dom == "k_group_bwd" else fwd_gbs, "peak": peak,
-            "unit": "GB/s", "frac": (bwd_gbs if dom == "k_group_bwd" else fwd_gbs) / peak,
+    step_gbs = n_tri * BWD_GROUP_BYTES / (step_kernel_ms * 1e-3) / 1e9
+    dom = "k_group_step"
+    roof = {"bound": "hbm", "kernel": dom, "achieved": step_gbs, "peak": peak,
+            "unit": "GB/s", "frac": step_gbs / peak,
             "traffic": ncu_traffic(dom, nb),
             "peak_source": peak_src,
-            "bytes_per_triple": BWD_GROUP_BYTES if dom == "k_group_bwd" else FWD_GROUP_BYTES,
+            "bytes_per_triple": BWD_GROUP_BYTES,
             "note": "algorithmic bytes per scored triple in the fused pos + 10 neg group accounting of SURVEY 8d "
                     "((3+K) rows read [+ (3+K) gradient rows written] per 1+K triples); the event interval also "
                     "covers the torch glue around the launch; traffic: ncu capture under profiles/"}
@@ -363,8 +371,8 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "transe d=100 |E|=100k |R|=500, batch 1024 pos + 10 neg/pos (configs[1]); "
-                               "%d batches per step (one launch of each kernel), fused forward+margin loss then "
-                               "sparse-row-gradient backward; negatives in the group-compact corrupted-id format" % nb,
+                               "%d batches per step in one launch: forward + margin loss + sparse-row-gradient "
+                               "backward fused in k_group_step; negatives in the group-compact corrupted-id format" % nb,
                    "triples_per_step_per_gpu": n_tri, "index_dtype": "int32", "grad_mode": "sparse slots",
                    "parallelism": "replicas x%d (training path does not shard)" % world,
                    "l2": "inputs larger than L2: per step 14 MB of ids + 1.4 GB of gradient rows stream through the "
@@ -373,6 +381,9 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roof,
         "kernels": {
+            "k_group_step": {"ms": step_kernel_ms, "triples_per_s": n_tri / (step_kernel_ms * 1e-3),
+                             "algorithmic_GBps": step_gbs, "frac_of_peak": step_gbs / peak,
+                             "bytes_per_triple": BWD_GROUP_BYTES},
             "k_group_fwd": {"ms": fwd_ms, "triples_per_s": n_fwd / (fwd_ms * 1e-3), "algorithmic_GBps": fwd_gbs,
                             "frac_of_peak": fwd_gbs / peak, "bytes_per_triple": FWD_GROUP_BYTES},
             "k_group_bwd": {"ms": bwd_ms, "triples_per_s": n_bwd / (bwd_ms * 1e-3), "algorithmic_GBps": bwd_gbs,

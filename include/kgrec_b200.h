@@ -187,6 +187,19 @@ int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model,
                            const float* pos_scores, const float* neg_scores, float grad_loss,
                            const float* grad_loss_dev, const kgrec_grads* grads, kgrec_stream_t stream);
 
+/* Forward + loss + backward of the group-compact ranking loss in ONE pass: scores, per-batch
+ * losses and the row gradients of grad_loss * sum_b loss[b] (every reference driver calls
+ * backward() on the loss itself, knowledge_representation.py:207, so the upstream is a known
+ * scalar).  One gather of (3 + n_neg) rows and (3 + n_neg) gradient rows per group; outputs
+ * and slot layout as kgrec_corrupt_loss_fwd / _bwd. */
+int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model,
+                            const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
+                            const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
+                            int loss_kind, float margin_or_target, float grad_loss,
+                            float* pos_scores, float* neg_scores, float* loss,
+                            const kgrec_grads* grads, void* workspace, int32_t* status,
+                            kgrec_stream_t stream);
+
 /* ---- full-catalog evaluation path ---------------------------------------- */
 /* Common arguments of the three evaluation modes:
  *   model / side   which evaluate* method: KG sides score query (t,r) / (h,r) pairs against

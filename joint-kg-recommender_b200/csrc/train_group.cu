@@ -90,7 +90,7 @@ __device__ __forceinline__ uint32_t group_idx(const void* p, int j, int is64, in
   return static_cast<uint32_t>(v);
 }
 
-template <int FAM, int NCH>
+template <int FAM, int NCH, bool L1>
 __global__ void __launch_bounds__(kThreads)
 k_group_fwd(const GroupArgs G, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
             float* __restrict__ group_loss, int32_t* status) {
@@ -98,7 +98,8 @@ k_group_fwd(const GroupArgs G, float* __restrict__ pos_scores, float* __restrict
   constexpr int NE = NCH * 4;
   const kgrec_tables& T = G.T;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int K = G.L.n_neg, d = T.dim, l1 = T.l1;
+  const int K = G.L.n_neg, d = T.dim;
+  constexpr int l1 = L1 ? 1 : 0;
   const int n_pos = static_cast<int>(G.L.n_pos);
   const uint32_t n_ent = static_cast<uint32_t>(T.n_ent), ld = static_cast<uint32_t>(T.ld);
   const uint64_t pol_keep = policy_evict_last(G.keep);
@@ -146,7 +147,7 @@ k_group_fwd(const GroupArgs G, float* __restrict__ pos_scores, float* __restrict
 }
 
 // slots (mode 0): ent [n_pos * (2 + K), d] per group: h, t, c_1 .. c_K ; rel / norm [n_pos, d]
-template <int FAM, int NCH>
+template <int FAM, int NCH, bool L1>
 __global__ void __launch_bounds__(kThreads)
 k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float* __restrict__ neg_scores,
             const float grad_loss, const float* __restrict__ grad_loss_dev, const kgrec_grads Gr) {
@@ -155,7 +156,8 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
   const kgrec_tables& T = G.T;
   const LossCfg& L = G.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int K = L.n_neg, d = T.dim, l1 = T.l1;
+  const int K = L.n_neg, d = T.dim;
+  constexpr int l1 = L1 ? 1 : 0;
   const int n_pos = static_cast<int>(L.n_pos);
   const uint32_t n_ent = static_cast<uint32_t>(T.n_ent), ld = static_cast<uint32_t>(T.ld);
   const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
@@ -262,6 +264,135 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
   }
 }
 
+// ---- forward + loss + backward in one pass ------------------------------------------------
+// d(sum of the per-batch losses)/d(tables) together with the scores and the losses: every
+// reference driver calls backward() on the loss itself (knowledge_representation.py:207), so
+// the upstream of each loss term is known (`up`, times 1/(cnt K) for the BPR mean) while the
+// group is still in registers: one gather of (3 + K) rows, (3 + K) gradient rows written.
+template <int FAM, int NCH, bool L1>
+__global__ void __launch_bounds__(kThreads)
+k_group_step(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
+             float* __restrict__ group_loss, const kgrec_grads Gr, int32_t* status) {
+  using R = Row<NCH, true>;
+  constexpr int NE = NCH * 4;
+  constexpr int l1 = L1 ? 1 : 0;
+  const kgrec_tables& T = G.T;
+  const LossCfg& L = G.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K = L.n_neg, d = T.dim;
+  const int n_pos = static_cast<int>(L.n_pos);
+  const uint32_t n_ent = static_cast<uint32_t>(T.n_ent), ld = static_cast<uint32_t>(T.ld);
+  const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
+  const uint64_t pol_keep = policy_evict_last(G.keep), pol_stream = policy_evict_first();
+  for (int j = blockIdx.x * kWarpsPerCta + wid; j < n_pos; j += gridDim.x * kWarpsPerCta) {
+    const int32_t* cj = G.corrupt + static_cast<int64_t>(j) * K;
+    int32_t c = K > 0 ? __ldg(cj) : 0;
+    const uint32_t ih = group_idx(G.ph, j, G.is64, T.n_ent, status);
+    const uint32_t it = group_idx(G.pt, j, G.is64, T.n_ent, status);
+    const uint32_t ir = group_idx(G.pr, j, G.is64, T.n_rel, status);
+    GroupPos<FAM, NCH> P;
+    P.load(T, ih, it, ir, lane, pol_keep);
+    float up = up0;
+    if (L.kind == KGREC_LOSS_BPR) {
+      const int b = j / bp;
+      up /= static_cast<float>(min(bp, n_pos - b * bp)) * static_cast<float>(K);
+    }
+    const float sp = dist_sum(P.epos, l1);
+    float lsum = 0.f, cpos = 0.f;
+    float gh[NE], gt[NE], gr[NE], gw[NE];
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { gh[i] = 0.f; gt[i] = 0.f; gr[i] = 0.f; gw[i] = 0.f; }
+    const int64_t slot0 = static_cast<int64_t>(j) * (2 + K);
+    float x[NE], xn[NE];
+    bool head = c < 0;
+    uint32_t id = static_cast<uint32_t>(head ? ~c : c);
+    if (id >= n_ent) { if (status) *status = 1; id = 0; }
+    if (K > 0) R::load_hint(x, row_ptr(T.ent, id, ld), d, lane, pol_keep);
+    for (int k = 0; k < K; ++k) {
+      bool headn = false;
+      uint32_t idn = 0;
+      if (k + 1 < K) {
+        const int32_t cn = __ldg(cj + k + 1);
+        headn = cn < 0;
+        idn = static_cast<uint32_t>(headn ? ~cn : cn);
+        if (idn >= n_ent) { if (status) *status = 1; idn = 0; }
+        R::load_hint(xn, row_ptr(T.ent, idn, ld), d, lane, pol_keep);
+      }
+      float ax = 0.f;
+      if (FAM == FAM_H) ax = warp_sum(R::dot(x, P.w));
+      float e[NE];
+      P.residual(x, head, ax, e);
+      const float sn = dist_sum(e, l1);
+      if (lane == 0) neg_scores[static_cast<int64_t>(j) * K + k] = sn;
+      lsum += loss_term(L, sp, sn);
+      const float dp = loss_dpos(L, sp, sn);
+      cpos += dp;
+      const float ck = -dp * up;
+      float gc[NE];
+      if (ck != 0.f) {                     // warp-uniform: an inactive hinge has no gradient
+        float eps[NE];
+#pragma unroll
+        for (int i = 0; i < NE; ++i) eps[i] = ck * ddist_term(e[i], l1);
+        float ew = 0.f;
+        if (FAM == FAM_H) ew = warp_sum(R::dot(eps, P.w));
+        const float xw = head ? ax - P.b : P.a - ax;
+#pragma unroll
+        for (int i = 0; i < NE; ++i) {
+          const float gx = (FAM == FAM_H) ? eps[i] - ew * P.w[i] : eps[i];
+          gr[i] += eps[i];
+          if (head) { gc[i] = gx; gt[i] -= gx; }
+          else { gc[i] = -gx; gh[i] += gx; }
+          if (FAM == FAM_H) {
+            const float xd = head ? x[i] - P.t[i] : P.h[i] - x[i];
+            gw[i] -= ew * xd + xw * eps[i];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NE; ++i) gc[i] = 0.f;
+      }
+      if (Gr.mode == 0) R::store_hint(Gr.ent + (slot0 + 2 + k) * d, gc, d, lane, pol_stream);
+      else if (ck != 0.f) R::red_add(Gr.ent + static_cast<uint64_t>(id) * d, gc, d, lane);
+      head = headn;
+      id = idn;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) x[i] = xn[i];
+    }
+    {   // the positive's own contribution, with the coefficient summed over its negatives
+      const float cp = cpos * up;
+      float eps[NE];
+#pragma unroll
+      for (int i = 0; i < NE; ++i) eps[i] = cp * ddist_term(P.epos[i], l1);
+      float ew = 0.f;
+      if (FAM == FAM_H) ew = warp_sum(R::dot(eps, P.w));
+      const float xw = P.a - P.b;
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const float gx = (FAM == FAM_H) ? eps[i] - ew * P.w[i] : eps[i];
+        gh[i] += gx;
+        gt[i] -= gx;
+        gr[i] += eps[i];
+        if (FAM == FAM_H) gw[i] -= ew * (P.h[i] - P.t[i]) + xw * eps[i];
+      }
+    }
+    if (lane == 0) {
+      pos_scores[j] = sp;
+      group_loss[j] = lsum;
+    }
+    if (Gr.mode == 0) {
+      R::store_hint(Gr.ent + slot0 * d, gh, d, lane, pol_stream);
+      R::store_hint(Gr.ent + (slot0 + 1) * d, gt, d, lane, pol_stream);
+      R::store_hint(Gr.rel + static_cast<int64_t>(j) * d, gr, d, lane, pol_stream);
+      if (FAM == FAM_H) R::store_hint(Gr.norm + static_cast<int64_t>(j) * d, gw, d, lane, pol_stream);
+    } else {
+      R::red_add(Gr.ent + static_cast<uint64_t>(ih) * d, gh, d, lane);
+      R::red_add(Gr.ent + static_cast<uint64_t>(it) * d, gt, d, lane);
+      R::red_add(Gr.rel + static_cast<uint64_t>(ir) * d, gr, d, lane);
+      if (FAM == FAM_H) R::red_add(Gr.norm + static_cast<uint64_t>(ir) * d, gw, d, lane);
+    }
+  }
+}
+
 int make_plan(const kgrec_tables* T, int model, Plan* pl);
 
 static int group_check(const kgrec_tables* T, int model, Plan* pl, const void* ph, const void* pt, const void* pr,
@@ -307,7 +438,9 @@ extern "C" int kgrec_corrupt_loss_fwd(const kgrec_tables* tables, int model, con
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   float* group_loss = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL(FAMV, NCHV) k_group_fwd<FAMV, NCHV><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, group_loss, status);
+#define CALL(FAMV, NCHV)                                                                                                  \
+  if (tables->l1) k_group_fwd<FAMV, NCHV, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, group_loss, status); \
+  else k_group_fwd<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, group_loss, status);
   KGREC_GROUP_DISPATCH(CALL)
 #undef CALL
   KGREC_CUDA_OK(cudaGetLastError());
@@ -334,9 +467,42 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
   const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos},
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL(FAMV, NCHV) k_group_bwd<FAMV, NCHV><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, grad_loss, grad_loss_dev, *grads);
+#define CALL(FAMV, NCHV)                                                                                                  \
+  if (tables->l1) k_group_bwd<FAMV, NCHV, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, grad_loss, grad_loss_dev, *grads); \
+  else k_group_bwd<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, grad_loss, grad_loss_dev, *grads);
   KGREC_GROUP_DISPATCH(CALL)
 #undef CALL
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}
+
+extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, const void* ph, const void* pt,
+                                       const void* pr, int idx_bytes, int64_t n_pos, const int32_t* corrupt,
+                                       int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
+                                       float grad_loss, float* pos_scores, float* neg_scores, float* loss,
+                                       const kgrec_grads* grads, void* workspace, int32_t* status,
+                                       kgrec_stream_t stream) {
+  Plan pl;
+  int rc = group_check(tables, model, &pl, ph, pt, pr, idx_bytes, n_pos, corrupt, n_neg, batch_pos, loss_kind);
+  if (rc) return rc;
+  if (!pos_scores || !neg_scores || !loss || !workspace) { set_error("output / workspace pointer is NULL"); return KGREC_ERR_INVALID; }
+  if (!grads || (grads->mode != 0 && grads->mode != 1) || !grads->ent || !grads->rel || (pl.fam == FAM_H && !grads->norm)) {
+    set_error("bad grads descriptor");
+    return KGREC_ERR_INVALID;
+  }
+  if (n_pos == 0) return KGREC_OK;
+  const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos},
+                    l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
+  float* group_loss = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL(FAMV, NCHV)                                                                                        \
+  if (tables->l1) k_group_step<FAMV, NCHV, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status); \
+  else k_group_step<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status);
+  KGREC_GROUP_DISPATCH(CALL)
+#undef CALL
+  KGREC_CUDA_OK(cudaGetLastError());
+  const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
+  k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(group_loss, G.L, loss);
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;
 }

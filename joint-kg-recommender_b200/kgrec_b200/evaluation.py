@@ -76,6 +76,7 @@ def run(T, model, side, q, r, mode, catalog, id_base=0, k=10, filter_csr=None, g
                                          _ptr(catalog), cat_ld, n_cat, id_base,
                                          _ptr(cat_ids.to(torch.int32).contiguous() if cat_ids is not None else None),
                                          _ptr(gumbel_u), seed, _ptr(res), res.stride(0), stream))
+        KF.count_launches(1)
         return res
     if mode == "topk":
         keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
@@ -85,6 +86,7 @@ def run(T, model, side, q, r, mode, catalog, id_base=0, k=10, filter_csr=None, g
         _lib.check(lib.kgrec_eval_topk(C.byref(T), model, side, _ptr(q), _ptr(r), ib, _ptr(qvec), nq,
                                        _ptr(catalog), cat_ld, n_cat, id_base, k, _ptr(fptr), _ptr(fids),
                                        _ptr(gumbel_u), seed, _ptr(keys), _ptr(ws), ws.numel() * 8, stream))
+        KF.count_launches(2)          # scoring kernel + merge of the per-range lists
         return keys
     if mode == "rank":
         counts = torch.zeros(nq, dtype=torch.int32, device=dev) if out is None else out
@@ -92,6 +94,7 @@ def run(T, model, side, q, r, mode, catalog, id_base=0, k=10, filter_csr=None, g
                                              _ptr(catalog), cat_ld, n_cat, id_base,
                                              _ptr(gold_scores.contiguous().float()),
                                              _ptr(gold_ids.to(torch.int32).contiguous()), _ptr(counts), stream))
+        KF.count_launches(1)
         return counts
     raise ValueError("unknown eval mode %r" % (mode,))
 
@@ -103,6 +106,7 @@ def merge_topk(key_lists):
     out = torch.empty((nq, k), dtype=torch.int64, device=key_lists.device)
     _lib.check(lib.kgrec_merge_topk(_ptr(key_lists.contiguous()), n_lists, nq, k, _ptr(out),
                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    KF.count_launches(1)
     return out
 
 

@@ -30,6 +30,14 @@ _SLOT_TABLES = {
 }
 
 
+# kernels of this library enqueued so far (forward, backward and evaluation paths)
+LAUNCHES = [0]
+
+
+def count_launches(n):
+    LAUNCHES[0] += n
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -161,6 +169,7 @@ class ScoreFunction(torch.autograd.Function):
         lib = _lib.load()
         _lib.check(lib.kgrec_score_fwd(C.byref(T), cfg.model, _ptr(a), _ptr(b), _ptr(c), _idx_bytes(a, b, c), n,
                                        _ptr(gumbel_u), cfg.seed, _ptr(scores), _ptr(status), _stream()))
+        count_launches(1)
         ctx.cfg = cfg
         ctx.idx = (a, b, c, gumbel_u)
         ctx.save_for_backward(*tables)
@@ -181,6 +190,7 @@ class ScoreFunction(torch.autograd.Function):
         lib = _lib.load()
         _lib.check(lib.kgrec_score_bwd(C.byref(T), cfg.model, _ptr(a), _ptr(b), _ptr(c), _idx_bytes(a, b, c), n,
                                        _ptr(gumbel_u), cfg.seed, _ptr(gs), C.byref(G), _stream()))
+        count_launches(1)
         idx = _slot_indices(cfg.model, a, b, c, cfg.item2ent) if cfg.grad_mode != "dense" else {}
         out = _finish_grads(cfg.model, weights, bufs, idx, cfg.grad_mode, needs)
         return (None, None, None, None, None, None) + tuple(out[nm] for nm in names)
@@ -208,6 +218,7 @@ class RankLossFunction(torch.autograd.Function):
             C.byref(T), cfg.model, _ptr(pa), _ptr(pb), _ptr(pc), _ptr(na), _ptr(nb), _ptr(nc),
             _idx_bytes(pa, pb, pc, na, nb, nc), n_pos, n_neg, batch_pos, loss_kind, float(param),
             _ptr(gumbel_u), cfg.seed, _ptr(pos_s), _ptr(neg_s), _ptr(loss), _ptr(ws), _ptr(status), _stream()))
+        count_launches(2)
         ctx.cfg = cfg
         ctx.args = (pos, neg, n_neg, batch_pos, loss_kind, float(param), gumbel_u, pos_s, neg_s)
         ctx.save_for_backward(*tables)
@@ -234,6 +245,7 @@ class RankLossFunction(torch.autograd.Function):
             C.byref(T), cfg.model, _ptr(pa), _ptr(pb), _ptr(pc), _ptr(na), _ptr(nb), _ptr(nc),
             _idx_bytes(pa, pb, pc, na, nb, nc), n_pos, n_neg, batch_pos, loss_kind, param,
             _ptr(gumbel_u), cfg.seed, _ptr(pos_s), _ptr(neg_s), 1.0, _ptr(gl), C.byref(G), _stream()))
+        count_launches(1)
         idx = {}
         if cfg.grad_mode != "dense":
             pi = _slot_indices(cfg.model, pa, pb, pc, cfg.item2ent)
@@ -268,6 +280,7 @@ class CorruptLossFunction(torch.autograd.Function):
             C.byref(T), cfg.model, _ptr(ph), _ptr(pt), _ptr(pr), _idx_bytes(ph, pt, pr), n_pos, _ptr(corrupt),
             n_neg, batch_pos, loss_kind, float(param), _ptr(pos_s), _ptr(neg_s), _ptr(loss), _ptr(ws),
             _ptr(status), _stream()))
+        count_launches(2)
         ctx.cfg = cfg
         ctx.args = (pos, corrupt, n_neg, batch_pos, loss_kind, float(param), pos_s, neg_s)
         ctx.save_for_backward(*tables)
@@ -301,6 +314,7 @@ class CorruptLossFunction(torch.autograd.Function):
         _lib.check(lib.kgrec_corrupt_loss_bwd(
             C.byref(T), cfg.model, _ptr(ph), _ptr(pt), _ptr(pr), _idx_bytes(ph, pt, pr), n_pos, _ptr(corrupt),
             n_neg, batch_pos, loss_kind, param, _ptr(pos_s), _ptr(neg_s), 1.0, _ptr(gl), C.byref(g), _stream()))
+        count_launches(1)
         out = []
         for name in names:
             if not needs.get(name, False):
@@ -327,3 +341,45 @@ def encode_corrupt(pos, neg):
     head = nh.view(-1, k) != ph.view(-1, 1)
     c = torch.where(head, ~nh.view(-1, k).to(torch.int32), nt.view(-1, k).to(torch.int32))
     return c.contiguous().view(-1)
+
+
+def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, param, status, grad_loss=1.0):
+    """Scores, per-batch losses and gradients of grad_loss * sum(loss) in one kernel
+    (kgrec_corrupt_loss_step).  Returns (loss, pos_scores, neg_scores, {table: grad})."""
+    names = MODEL_TABLES[cfg.model]
+    T = make_tables(weights, cfg.dim, cfg.l1, cfg.use_gumbel, cfg.item2ent)
+    ph, pt, pr = pos
+    n_pos = ph.numel()
+    dev = ph.device
+    pos_s = torch.empty(n_pos, dtype=torch.float32, device=dev)
+    neg_s = torch.empty(n_pos * n_neg, dtype=torch.float32, device=dev)
+    loss = torch.empty((n_pos + batch_pos - 1) // batch_pos, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(1, n_pos), dtype=torch.float32, device=dev)
+    g = Grads()
+    dense = cfg.grad_mode == "dense"
+    g.mode = 1 if dense else 0
+    shapes = {"ent": n_pos * (2 + n_neg), "rel": n_pos, "norm": n_pos}
+    bufs = {}
+    for name in names:
+        bufs[name] = torch.zeros_like(weights[name]) if dense else \
+            torch.empty((shapes[name], cfg.dim), dtype=torch.float32, device=dev)
+        setattr(g, name, bufs[name].data_ptr())
+    lib = _lib.load()
+    _lib.check(lib.kgrec_corrupt_loss_step(
+        C.byref(T), cfg.model, _ptr(ph), _ptr(pt), _ptr(pr), _idx_bytes(ph, pt, pr), n_pos, _ptr(corrupt), n_neg,
+        batch_pos, loss_kind, float(param), float(grad_loss), _ptr(pos_s), _ptr(neg_s), _ptr(loss), C.byref(g),
+        _ptr(ws), _ptr(status), _stream()))
+    count_launches(2)
+    grads = {}
+    for name in names:
+        if dense:
+            grads[name] = bufs[name]
+        else:
+            if name == "ent":
+                cid = torch.where(corrupt < 0, ~corrupt, corrupt).view(n_pos, n_neg).long()
+                idx = torch.cat([ph.long().view(-1, 1), pt.long().view(-1, 1), cid], dim=1).reshape(1, -1)
+            else:
+                idx = pr.long().view(1, -1)
+            grads[name] = torch.sparse_coo_tensor(idx, bufs[name], size=tuple(weights[name].shape),
+                                                  check_invariants=False)
+    return loss, pos_s, neg_s, grads

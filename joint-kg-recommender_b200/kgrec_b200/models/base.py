@@ -53,7 +53,11 @@ class KGRecModule(nn.Module):
         self._seed_counter = 0
         self._status = None
         self._item2ent = None
-        self.kernel_launches = 0        # kernels of this library enqueued through the module
+
+    @property
+    def kernel_launches(self):
+        """Kernels of the CUDA library enqueued so far by this process (all modules)."""
+        return KF.LAUNCHES[0]
 
     # -- reference API --------------------------------------------------------
     def disable_grad(self):
@@ -115,7 +119,6 @@ class KGRecModule(nn.Module):
         if gumbel_u is not None:
             gumbel_u = gumbel_u.to(dev, torch.float32).contiguous()
         seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
-        self.kernel_launches += 1
         return KF.ScoreFunction.apply(self._cfg(model, seed), a, b, c, gumbel_u, self._status_buf(dev),
                                       *self._tables_for(model))
 
@@ -131,7 +134,6 @@ class KGRecModule(nn.Module):
         if gumbel_u is not None:
             gumbel_u = gumbel_u.to(dev, torch.float32).contiguous()
         seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
-        self.kernel_launches += 2
         return KF.RankLossFunction.apply(self._cfg(model, seed), pos, neg, n_neg, batch_pos or n_pos, kind, param,
                                          gumbel_u, self._status_buf(dev), *self._tables_for(model))
 
@@ -143,10 +145,28 @@ class KGRecModule(nn.Module):
         if n_pos == 0 or corrupt.numel() % n_pos:
             raise ValueError("corrupt ids must be a whole multiple of the positives")
         kind = {"margin": _lib.LOSS_MARGIN, "bpr": _lib.LOSS_BPR}[loss]
-        self.kernel_launches += 2
         return KF.CorruptLossFunction.apply(self._cfg(model, 0), pos, corrupt, corrupt.numel() // n_pos,
                                             batch_pos or n_pos, kind, param, self._status_buf(dev),
                                             *self._tables_for(model))
+
+    def _loss_step_corrupt(self, model, pos, corrupt, loss, param, batch_pos=None, grad_loss=1.0):
+        dev = self._require_cuda()
+        pos = tuple(KF.as_index(x, dev) for x in pos)
+        corrupt = corrupt.to(dev, torch.int32, non_blocking=True).contiguous().view(-1)
+        n_pos = pos[0].numel()
+        if n_pos == 0 or corrupt.numel() % n_pos:
+            raise ValueError("corrupt ids must be a whole multiple of the positives")
+        kind = {"margin": _lib.LOSS_MARGIN, "bpr": _lib.LOSS_BPR}[loss]
+        names = KF.MODEL_TABLES[model]
+        w = self._weights()
+        out, ps, ns, grads = KF.corrupt_loss_step(self._cfg(model, 0), {k: w[k] for k in names}, pos, corrupt,
+                                                  corrupt.numel() // n_pos, batch_pos or n_pos, kind, param,
+                                                  self._status_buf(dev), grad_loss)
+        for k in names:          # what loss.sum().backward() would have left in .grad
+            p = w[k]
+            if p.requires_grad:
+                p.grad = grads[k] if p.grad is None else p.grad + grads[k]
+        return out, ps, ns
 
     # -- evaluation helpers ------------------------------------------------------
     def _eval(self, model, side, q, r, mode, **kw):
@@ -154,5 +174,4 @@ class KGRecModule(nn.Module):
         q = KF.as_index(q, dev) if q is not None else None
         r = KF.as_index(r, dev) if r is not None else None
         T = KF.make_tables(self._weights(), self.embedding_size, self.L1_flag, self.use_st_gumbel, self._item2ent)
-        self.kernel_launches += 1
         return KE.run(T, model, side, q, r, mode, **kw)

@@ -103,7 +103,7 @@ class jTransUPModel(RecModelBase):
         lib = _lib.load()
         _lib.check(lib.kgrec_ktup_item_table(C.byref(T), 0, self.item_total, C.c_void_p(out.data_ptr()),
                                              out.stride(0), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        self.kernel_launches += 1
+        KF.count_launches(1)
         return out
 
     def evaluateRec(self, u_ids, all_i_ids=None, gumbel_u=None):

@@ -17,8 +17,7 @@ if what in ("train", "all"):
     ix = [x.to(dev) for x in bench.make_indices(torch, gen, 256)]
     for _ in range(2):
         m.zero_grad(set_to_none=True)
-        loss, _, _ = m.rank_loss_corrupt(tuple(ix[:3]), ix[6], margin=1.0, batch_pos=bench.BATCH)
-        loss.sum().backward()
+        m.loss_step_corrupt(tuple(ix[:3]), ix[6], margin=1.0, batch_pos=bench.BATCH)
     torch.cuda.synchronize()
 if what in ("eval", "all"):
     q = torch.randint(0, bench.N_ENT, (4096,), generator=gen).to(dev)

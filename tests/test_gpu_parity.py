@@ -494,3 +494,38 @@ def test_corrupt_format_matches_expanded_triples(cls_name, l1, loss, param, d):
         close(fl, cl.detach().cpu().numpy(), rtol=1e-5)
         close(fn, cn.detach().cpu().numpy(), rtol=1e-5)
     m.check_indices()
+
+
+@pytest.mark.parametrize("cls_name", ["TransEModel", "TransHModel"])
+@pytest.mark.parametrize("l1", [False, True])
+@pytest.mark.parametrize("loss,param", [("margin", 1.0), ("bpr", -1.0)])
+def test_single_pass_step_equals_forward_plus_backward(cls_name, l1, loss, param):
+    """kgrec_corrupt_loss_step == kgrec_corrupt_loss_fwd + autograd backward of loss.sum()."""
+    import kgrec_b200 as K
+    torch.manual_seed(9)
+    d, E, R, B, KN = 100, 5000, 11, 300, 10
+    m = getattr(K, cls_name)(l1, d, E, R)
+    g = torch.Generator().manual_seed(5)
+    pos = tuple(torch.randint(0, n, (B,), generator=g).cuda() for n in (E, E, R))
+    cid = torch.randint(0, E, (B * KN,), generator=g, dtype=torch.int32)
+    corrupt = torch.where(torch.rand(B * KN, generator=g) < 0.5, ~cid, cid).cuda()
+    for gm in ("dense", "sparse"):
+        m.grad_mode = gm
+        m.zero_grad(set_to_none=True)
+        l1_, p1, n1 = m.rank_loss_corrupt(pos, corrupt, margin=param, loss=loss, batch_pos=128)
+        (2.0 * l1_.sum()).backward()
+        want = {k: v.clone() for k, v in grads_by_name(m).items()}
+        m.zero_grad(set_to_none=True)
+        l2_, p2, n2 = m.loss_step_corrupt(pos, corrupt, margin=param, loss=loss, batch_pos=128, grad_loss=2.0)
+        close(p2, p1.cpu().numpy(), rtol=2e-6, atol=0)      # same arithmetic, different kernels: <= a few ulp
+        close(n2, n1.cpu().numpy(), rtol=2e-6, atol=0)
+        close(l2_, l1_.detach().cpu().numpy(), rtol=1e-5)
+        got = grads_by_name(m)
+        assert set(got) == set(want)
+        for k in want:
+            close(got[k], want[k].cpu().numpy(), rtol=1e-4, atol=2e-5)
+        # accumulates like autograd
+        m.loss_step_corrupt(pos, corrupt, margin=param, loss=loss, batch_pos=128, grad_loss=2.0)
+        for k in want:
+            close(grads_by_name(m)[k], 2 * want[k].cpu().numpy(), rtol=1e-4, atol=4e-5)
+    m.check_indices()
