@@ -270,7 +270,7 @@ k_group_bwd(const GroupArgs G, const float* __restrict__ pos_scores, const float
 // the upstream of each loss term is known (`up`, times 1/(cnt K) for the BPR mean) while the
 // group is still in registers: one gather of (3 + K) rows, (3 + K) gradient rows written.
 template <int FAM, int NCH, bool L1>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (NCH == 1 && FAM == FAM_E) ? 4 : 1)
 k_group_step(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
              float* __restrict__ group_loss, const kgrec_grads Gr, int32_t* status) {
   using R = Row<NCH, true>;

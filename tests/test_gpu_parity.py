@@ -529,3 +529,92 @@ def test_single_pass_step_equals_forward_plus_backward(cls_name, l1, loss, param
         for k in want:
             close(grads_by_name(m)[k], 2 * want[k].cpu().numpy(), rtol=1e-4, atol=4e-5)
     m.check_indices()
+
+
+def _big_table(rows, d, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    w = torch.randn(rows, d, device="cuda", generator=g)
+    return torch.nn.Parameter(torch.nn.functional.normalize(w, dim=1))
+
+
+def test_full_scale_configs():
+    """BASELINE.json configs[3] / configs[4] sizes: 500k-entity training tables, 5M-entity d=128
+    catalog, 1M x 1M rec tables.  Checked through size-independent properties against plain
+    torch arithmetic on a few rows (the oracle cannot run at these sizes)."""
+    import kgrec_b200 as K
+    from kgrec_b200 import evaluation as KE
+    torch.manual_seed(0)
+    # ---- configs[4]: d=128, 5M entities, top-10 + rank counts, catalog in 3 shards
+    d, E, R, Q = 128, 5_000_000, 50, 300
+    m = K.TransHModel(False, d, 8, R)
+    m.ent_embeddings.weight = _big_table(E, d, 1)
+    m.ent_total = E
+    g = torch.Generator().manual_seed(3)
+    h = torch.randint(0, E, (Q,), generator=g).cuda()
+    r = torch.randint(0, R, (Q,), generator=g).cuda()
+    keys = m.topk("tail", h, r, k=10)
+    ids, sc = KE.keys_to_ids_scores(keys)
+    ent, rel, nrm = m.ent_embeddings.weight.detach(), m.rel_embeddings.weight.detach(), m.norm_embeddings.weight.detach()
+    for b in range(0, Q, 97):
+        w = nrm[r[b]]
+        c = ent[h[b]] - (ent[h[b]] @ w) * w + rel[r[b]]
+        pe = ent - (ent @ w)[:, None] * w
+        ref = ((c - pe) ** 2).sum(1)
+        top = torch.topk(ref, 10, largest=False)
+        assert set(ids[b].tolist()) == set(top.indices.tolist())
+        close(sc[b], top.values.sort().values.cpu().numpy(), rtol=1e-4)
+    parts = []
+    for s in range(3):
+        lo, hi = KE.shard_bounds(E, 3, s)
+        parts.append(m.topk("tail", h, r, k=10, catalog=ent[lo:hi], id_base=lo))
+    assert torch.equal(KE.merge_topk(torch.stack(parts)), keys)
+    gold = ids[:, 3].contiguous()                                  # the 4th best of each query ...
+    assert m.rank_counts("tail", h, r, gold).tolist() == [3] * Q   # ... has exactly 3 entities before it
+    del m, ent, parts
+    torch.cuda.empty_cache()
+    # ---- configs[3]: 500k entities d=100, fused single-pass step, dense == sparse gradients
+    d, E, R, B, KN = 100, 500_000, 30, 8192, 10
+    m = K.TransHModel(True, d, 8, R)
+    m.ent_embeddings.weight = _big_table(E + 1, d, 2)
+    m.ent_total = E + 1
+    pos = tuple(torch.randint(0, n, (B,), generator=g).cuda() for n in (E, E, R))
+    cid = torch.randint(0, E, (B * KN,), generator=g, dtype=torch.int32)
+    corrupt = torch.where(torch.rand(B * KN, generator=g) < 0.5, ~cid, cid).cuda()
+    out = {}
+    for gm in ("dense", "sparse"):
+        m.grad_mode = gm
+        m.zero_grad(set_to_none=True)
+        loss, ps, ns = m.loss_step_corrupt(pos, corrupt, margin=1.0, batch_pos=1024)
+        out[gm] = (loss.clone(), {k: v.clone() for k, v in grads_by_name(m).items()})
+    assert torch.equal(out["dense"][0], out["sparse"][0]) and out["dense"][0].numel() == 8
+    for k in out["dense"][1]:
+        assert torch.allclose(out["dense"][1][k], out["sparse"][1][k], rtol=1e-4, atol=1e-5)
+    # loss of batch 0 against plain torch arithmetic
+    ent, rel, nrm = m.ent_embeddings.weight.detach(), m.rel_embeddings.weight.detach(), m.norm_embeddings.weight.detach()
+    hb, tb, rb = (x[:1024] for x in pos)
+    c0 = corrupt[:10240].view(1024, 10)
+    nh = torch.where(c0 < 0, (~c0).long(), hb[:, None].expand(-1, 10))
+    nt = torch.where(c0 < 0, tb[:, None].expand(-1, 10), c0.long())
+
+    def score(hh, tt, rr):
+        w = nrm[rr]
+        ph = ent[hh] - (ent[hh] * w).sum(-1, keepdim=True) * w
+        pt = ent[tt] - (ent[tt] * w).sum(-1, keepdim=True) * w
+        return (ph + rel[rr] - pt).abs().sum(-1)
+    sp = score(hb, tb, rb)
+    sn = score(nh, nt, rb[:, None].expand(-1, 10))
+    close(loss[0], torch.clamp(sp[:, None] - sn + 1.0, min=0).sum().item(), rtol=1e-4)
+    m.check_indices()
+    del m
+    torch.cuda.empty_cache()
+    # ---- rec side at 1M x 1M, d=128, P=20, Gumbel: top-10 items of a few users is reproducible
+    mu = K.TransUPModel(False, 128, 8, 8, 20, False)
+    mu.user_embeddings.weight = _big_table(1_000_000, 128, 4)
+    mu.item_embeddings.weight = _big_table(1_000_000, 128, 5)
+    mu.user_total = mu.item_total = 1_000_000
+    u = torch.arange(0, 64, device="cuda") * 15_000
+    k1 = mu.topk_items(u, k=10)
+    ids1, sc1 = KE.keys_to_ids_scores(k1)
+    for b in (0, 63):
+        close(mu(u[b].expand(10), ids1[b]), sc1[b].cpu().numpy(), rtol=2e-4)      # eval score == forward score
+    assert (sc1[:, 1:] >= sc1[:, :-1]).all()
