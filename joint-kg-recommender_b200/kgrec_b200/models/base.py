@@ -116,6 +116,8 @@ class KGRecModule(nn.Module):
         dev = self._require_cuda()
         a, b = KF.as_index(a, dev), KF.as_index(b, dev)
         c = KF.as_index(c, dev) if c is not None else None
+        if a.numel() == 0:                       # empty batch: the reference returns an empty score vector
+            return torch.zeros(0, dtype=torch.float32, device=dev) + 0 * sum(w.sum() for w in self._tables_for(model))
         if gumbel_u is not None:
             gumbel_u = gumbel_u.to(dev, torch.float32).contiguous()
         seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
@@ -173,5 +175,12 @@ class KGRecModule(nn.Module):
         dev = self._require_cuda()
         q = KF.as_index(q, dev) if q is not None else None
         r = KF.as_index(r, dev) if r is not None else None
+        nq = q.numel() if q is not None else kw["qvec"].shape[0]
+        if nq == 0:                              # no queries: empty results of the right shape
+            if mode == "scores":
+                return torch.zeros((0, kw["catalog"].shape[0]), dtype=torch.float32, device=dev)
+            if mode == "topk":
+                return torch.zeros((0, kw.get("k", 10)), dtype=torch.int64, device=dev)
+            return torch.zeros(0, dtype=torch.int32, device=dev)
         T = KF.make_tables(self._weights(), self.embedding_size, self.L1_flag, self.use_st_gumbel, self._item2ent)
         return KE.run(T, model, side, q, r, mode, **kw)

@@ -618,3 +618,44 @@ def test_full_scale_configs():
     for b in (0, 63):
         close(mu(u[b].expand(10), ids1[b]), sc1[b].cpu().numpy(), rtol=2e-4)      # eval score == forward score
     assert (sc1[:, 1:] >= sc1[:, :-1]).all()
+
+
+def test_edge_cases():
+    """Empty and single-element inputs, K larger than the catalog, everything filtered, duplicate
+    rows in one batch (gradient accumulation), ragged last loss batch."""
+    import kgrec_b200 as K
+    from kgrec_b200 import evaluation as KE
+    torch.manual_seed(0)
+    m = K.TransEModel(False, 100, 50, 3)
+    W = np_tables(m)
+    empty = lt([])
+    assert m(empty, empty, empty).shape == (0,)
+    assert m.evaluateTail(empty, empty).shape == (0, 50)
+    assert m.topk("tail", empty, empty, k=5).shape == (0, 5)
+    one = m(lt([7]), lt([8]), lt([2]))
+    close(one, O.transe_score(W["ent"], W["rel"], np.array([7]), np.array([8]), np.array([2]), False))
+    # K > catalog: the tail of the list is empty (id -1, score +inf)
+    keys = m.topk("tail", lt([1, 2]), lt([0, 1]), k=64)
+    ids, sc = KE.keys_to_ids_scores(keys)
+    assert (ids[:, :50] >= 0).all() and (ids[:, 50:] == -1).all() and torch.isinf(sc[:, 50:]).all()
+    assert sorted(ids[0, :50].tolist()) == list(range(50))
+    # everything filtered for query 0, nothing for query 1
+    csr = KE.build_filter_csr([0, 1], [{0: set(range(50))}], dev())
+    ids, _ = KE.keys_to_ids_scores(m.topk("tail", lt([1, 2]), lt([0, 1]), k=5, filter_csr=csr))
+    assert (ids[0] == -1).all() and (ids[1] >= 0).all()
+    # the same row many times in one batch: dense accumulation == oracle scatter-add
+    m.grad_mode = "dense"
+    h, t, r = np.array([4] * 40), np.array([5] * 40), np.array([1] * 40)
+    m.zero_grad()
+    m(lt(h), lt(t), lt(r)).sum().backward()
+    want = O.transe_grads(W["ent"], W["rel"], h, t, r, False, np.ones(40, np.float32))
+    close(m.ent_embeddings.weight.grad, want["ent"], rtol=1e-4, atol=1e-5)
+    # one positive, one negative, loss batches of 1; ragged: 5 positives in batches of 2
+    l, p, n = m.rank_loss_corrupt((lt([1]), lt([2]), lt([0])), torch.tensor([~3], dtype=torch.int32).cuda(), margin=1.0)
+    close(n, O.transe_score(W["ent"], W["rel"], np.array([3]), np.array([2]), np.array([0]), False))
+    l5, _, _ = m.rank_loss_corrupt((lt([1, 2, 3, 4, 5]), lt([6, 7, 8, 9, 10]), lt([0, 1, 2, 0, 1])),
+                                   torch.arange(20, 30, dtype=torch.int32).cuda(), margin=1.0, batch_pos=2)
+    assert l5.shape == (3,)
+    with pytest.raises(ValueError):
+        m.rank_loss_corrupt((lt([1, 2]), lt([2, 3]), lt([0, 0])), torch.tensor([1, 2, 3], dtype=torch.int32).cuda())
+    m.check_indices()
