@@ -271,20 +271,47 @@ def run_ours(args):
     value = world * n_tri / (ms_per_step * 1e-3)
 
     # ---- end-to-end through the module API with host buffers ----------------------------
-    for s in range(args.warmup):
-        step_e2e(s)
+    # ids start in pinned host memory; the package's DevicePrefetcher copies step i+1 on a side
+    # stream while step i runs; every step's per-batch losses are copied back to the host and the
+    # loop ends with a stream sync, so all H2D / D2H traffic is inside the timed region.
+    from kgrec_b200.data import DevicePrefetcher
+
+    def host_batches(n):
+        for s in range(n):
+            hs = host_sets[s % n_sets]
+            yield [hs[0], hs[1], hs[2], hs[6]]
+
+    def run_e2e(n):
+        for ix in DevicePrefetcher(host_batches(n), dev):
+            model.zero_grad(set_to_none=True)
+            loss, _, _ = model.loss_step_corrupt(tuple(ix[:3]), ix[3], margin=1.0, batch_pos=BATCH)
+            loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()       # the caller reads the losses
+    run_e2e(args.warmup)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for s in range(args.steps):
-        step_e2e(s)
+    run_e2e(args.steps)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    # the same without overlap (copy, compute, read back, one step at a time)
+    for s in range(2):
+        step_e2e(s)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for s in range(args.steps):
+        step_e2e(s)
+    f1.record()
+    barrier()
+    e2e_sync_ms = max_over_ranks(f0.elapsed_time(f1)) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(host_sets[0][i].numel() * host_sets[0][i].element_size() for i in (0, 1, 2, 6))
     e2e = {"value": world * n_tri / (e2e_ms * 1e-3), "unit": "triples/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": nb * 4, "ms_per_step": e2e_ms}
+           "d2h_bytes_per_step": nb * 4, "ms_per_step": e2e_ms,
+           "pipeline": "DevicePrefetcher: H2D of step i+1 overlaps step i; losses read back every step",
+           "unpipelined_value": world * n_tri / (e2e_sync_ms * 1e-3)}
 
     # ---- the same work as separate forward / autograd-backward kernels, in both negative formats
     split = {}
