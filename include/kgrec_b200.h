@@ -200,6 +200,26 @@ int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model,
                             const kgrec_grads* grads, void* workspace, int32_t* status,
                             kgrec_stream_t stream);
 
+/* ---- sparse-row optimizer -----------------------------------------
+ * Replaces the reference's dense optimizer step and clip_grad_norm (utils/trainer.py:63-81,
+ * knowledge_representation.py:213) at a cost proportional to the rows the batch touched.
+ * acc: persistent dense accumulator [rows, dim] the backward kernels wrote with grads->mode 1
+ * (all-zero outside a step); idx: the ids of the batch (duplicates allowed); flags: int32
+ * [rows] scratch, all-zero outside a step. */
+/* adds to *sqnorm the squared L2 norm of the accumulated gradient rows of idx (each once) */
+int kgrec_rows_sqnorm(const float* acc, int32_t* flags, const void* idx, int idx_bytes, int64_t n,
+                      int64_t rows, int32_t dim, float* sqnorm, kgrec_stream_t stream);
+/* one optimizer update of every distinct row of idx, then acc rows and flags are cleared.
+ * kind 0 SGD, 1 Adagrad (state1 = sum), 2 Adam on the touched rows (state1 = m, state2 = v,
+ * step = 1-based count).  sqnorm (optional, device): gradients are scaled by
+ * min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) as clip_grad_norm does; norm_claimed = 1 when
+ * kgrec_rows_sqnorm ran on the same idx in this step. */
+int kgrec_rows_step(float* table, float* acc, float* state1, float* state2, int32_t* flags,
+                    const void* idx, int idx_bytes, int64_t n, int64_t rows, int32_t dim,
+                    int kind, float lr, float eps, float beta1, float beta2, int64_t step,
+                    float weight_decay, const float* sqnorm, float max_norm, int norm_claimed,
+                    kgrec_stream_t stream);
+
 /* ---- full-catalog evaluation path ---------------------------------------- */
 /* Common arguments of the three evaluation modes:
  *   model / side   which evaluate* method: KG sides score query (t,r) / (h,r) pairs against

@@ -64,6 +64,11 @@ _SIGNATURES = {
                                           C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_float, C.c_float,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "kgrec_rows_sqnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int32,
+                                    C.c_void_p, C.c_void_p]),
+    "kgrec_rows_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int64, C.c_int64, C.c_int32, C.c_int, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_int64, C.c_float, C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
     "kgrec_eval_scores": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]),
