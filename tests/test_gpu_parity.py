@@ -696,3 +696,61 @@ def test_sparse_row_optimizer_matches_torch(cls_name, opt_name, steps, clip):
         close(p1, p2.detach().cpu().numpy(), rtol=2e-4, atol=5e-5)   # atomic accumulation order differs between the runs
     for k in opt.acc:                                  # accumulators and flags are clean again
         assert not opt.acc[k].any() and not opt.flags[k].any()
+
+
+@pytest.mark.parametrize("cls_name", ["TransEModel", "TransHModel", "jTransUPModel"])
+def test_driver_level_eval_matches_ranking_walk(cls_name):
+    """metrics from on-chip top-K / rank counts == the reference's argsort walk
+    (oracle restatement) over the full score matrix, with filters and multi-gold queries."""
+    import kgrec_b200 as K
+    from kgrec_b200 import metrics as KM
+    torch.manual_seed(12)
+    rng = np.random.RandomState(12)
+    d, E, R, U, I, topn = 100, 2500, 6, 300, 900, 10
+    if cls_name == "jTransUPModel":
+        i_map = {i: i for i in range(I)}
+        new_map = {i: ((int(rng.randint(0, E)) if rng.rand() < 0.7 else -1), i) for i in range(I)}
+        m = K.jTransUPModel(False, d, U, I, E, R, i_map, new_map, False, False)
+        n_ent = E + 1
+    else:
+        m = getattr(K, cls_name)(True, d, E, R)
+        n_ent = E
+    # ---- KG side
+    def rand_dict(n_keys, key_hi, lo, hi):
+        out = {}
+        while len(out) < n_keys:
+            key = (int(rng.randint(0, key_hi)), int(rng.randint(0, R)))
+            out[key] = set(int(x) for x in rng.choice(E, rng.randint(lo, hi), replace=False))
+        return out
+    head_eval, tail_eval = rand_dict(90, E, 1, 4), rand_dict(110, E, 1, 4)
+    head_all = [{k: set(int(x) for x in rng.choice(E, 15, replace=False)) for k in list(head_eval)[::2]}]
+    tail_all = [{k: set(int(x) for x in rng.choice(E, 25, replace=False)) for k in list(tail_eval)[::3]}, {}]
+    got = KM.evaluate_kg(m, head_eval, tail_eval, head_all, tail_all, topn=topn, batch=64)
+    want = {}
+    for side, ev, alld in (("head", head_eval, head_all), ("tail", tail_eval, tail_all)):
+        keys = list(ev)
+        q, r = lt([k[0] for k in keys]), lt([k[1] for k in keys])
+        full = (m.evaluateHead(q, r) if side == "head" else m.evaluateTail(q, r)).cpu().numpy()
+        assert full.shape[1] == n_ent
+        res = []
+        for b, key in enumerate(keys):
+            filt = set()
+            for dct in alld:
+                if key in dct:
+                    filt.update(dct[key])
+            res.extend(O.kg_ranks(full[b], ev[key], filt, topn).values())
+        want[side] = np.asarray(res, dtype=np.float64)
+    for side, g_ in (("head", got[2]), ("tail", got[3])):
+        np.testing.assert_allclose(g_, want[side].mean(axis=0), rtol=1e-12)
+    tot = len(want["head"]) + len(want["tail"])
+    np.testing.assert_allclose(got[0], (want["head"][:, 0].sum() + want["tail"][:, 0].sum()) / tot, rtol=1e-12)
+    np.testing.assert_allclose(got[1], (want["head"][:, 1].sum() + want["tail"][:, 1].sum()) / tot, rtol=1e-12)
+    # ---- rec side
+    if cls_name == "jTransUPModel":
+        eval_dict = {int(u): set(int(x) for x in rng.choice(I, rng.randint(0, 5), replace=False)) for u in rng.choice(U, 120, replace=False)}
+        train = {u: set(int(x) for x in rng.choice(I, 40, replace=False)) - eval_dict[u] for u in eval_dict}
+        got_r = KM.evaluate_rec(m, eval_dict, [train], topn=topn, batch=50)
+        users = [u for u in eval_dict if eval_dict[u]]
+        full = m.evaluateRec(lt(users)).cpu().numpy()
+        rows = [O.rec_metrics(O.rec_topk(full[b], train[u], topn), eval_dict[u]) for b, u in enumerate(users)]
+        np.testing.assert_allclose(got_r, np.asarray(rows, dtype=np.float64).mean(axis=0), rtol=1e-12)
