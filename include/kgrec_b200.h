@@ -200,6 +200,28 @@ int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model,
                             const kgrec_grads* grads, void* workspace, int32_t* status,
                             kgrec_stream_t stream);
 
+/* ---- device-side negative sampling --------------------------------
+ * The reference draws negatives with per-triple Python rejection loops (utils/data.py:12-85).
+ * Known triples / ratings are 64-bit keys in an open-addressing hash set in HBM:
+ *   triple key  = (h * n_rel + r) * n_ent + t        rating key = u * n_item + i
+ * Draws are Philox4x32-10 keyed by (seed, negative index, attempt): reproducible per seed. */
+int64_t kgrec_hashset_capacity(int64_t n_keys);        /* power of two >= 2 n_keys */
+int kgrec_hashset_build(const uint64_t* keys, int64_t n, uint64_t* table, int64_t capacity,
+                        kgrec_stream_t stream);
+/* getTrainTripleBatch + corrupt_head/tail_filter (data.py:12-56): n_neg negatives per positive,
+ * head or tail with probability 1/2, uniform entity, redrawn while equal to the original or a
+ * known triple (table == NULL: unfiltered).  Output: the group-compact int32 format of
+ * kgrec_corrupt_loss_* (>= 0 tail replaced, < 0 head replaced by ~value). */
+int kgrec_sample_corrupt(const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
+                         int32_t n_neg, int64_t n_ent, int64_t n_rel,
+                         const uint64_t* table, int64_t capacity, uint64_t seed,
+                         int32_t* corrupt, kgrec_stream_t stream);
+/* getNegRatings (data.py:64-85): n_neg negative items per (user, positive item), uniform,
+ * redrawn while equal to the positive or a known item of the user. */
+int kgrec_sample_neg_items(const void* u, const void* pi, int idx_bytes, int64_t n, int32_t n_neg,
+                           int64_t n_item, const uint64_t* table, int64_t capacity, uint64_t seed,
+                           int32_t* neg_items, kgrec_stream_t stream);
+
 /* ---- sparse-row optimizer -----------------------------------------
  * Replaces the reference's dense optimizer step and clip_grad_norm (utils/trainer.py:63-81,
  * knowledge_representation.py:213) at a cost proportional to the rows the batch touched.

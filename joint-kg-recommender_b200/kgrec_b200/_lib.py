@@ -64,6 +64,12 @@ _SIGNATURES = {
                                           C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_float, C.c_float,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "kgrec_hashset_capacity": (C.c_int64, [C.c_int64]),
+    "kgrec_hashset_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "kgrec_sample_corrupt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64,
+                                       C.c_int64, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "kgrec_sample_neg_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64,
+                                         C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "kgrec_rows_sqnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int32,
                                     C.c_void_p, C.c_void_p]),
     "kgrec_rows_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

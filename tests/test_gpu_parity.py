@@ -754,3 +754,52 @@ def test_driver_level_eval_matches_ranking_walk(cls_name):
         full = m.evaluateRec(lt(users)).cpu().numpy()
         rows = [O.rec_metrics(O.rec_topk(full[b], train[u], topn), eval_dict[u]) for b, u in enumerate(users)]
         np.testing.assert_allclose(got_r, np.asarray(rows, dtype=np.float64).mean(axis=0), rtol=1e-12)
+
+
+def test_device_negative_sampling():
+    """the device samplers honour the reference's rules (utils/data.py:12-85):
+    a negative never equals its positive's original id, never is a known triple / rating, the
+    head/tail coin is fair, entities are uniform, and a seed reproduces the batch."""
+    from kgrec_b200.sampling import TripleNegativeSampler, RatingNegativeSampler
+    rng = np.random.RandomState(3)
+    E, R, B, KN = 500, 4, 4000, 8
+    # a dense known set so that rejection actually happens: ~30 % of all (h, r, *) tails are known
+    known = np.stack([rng.randint(0, 40, 60000), rng.randint(0, E, 60000), rng.randint(0, R, 60000)], axis=1)
+    known = np.unique(known, axis=0)
+    kset = set(map(tuple, known.tolist()))
+    s = TripleNegativeSampler(E, R, torch.from_numpy(known))
+    pos = known[rng.choice(len(known), B, replace=False)]
+    h, t, r = (lt(pos[:, i]) for i in range(3))
+    c = s.sample((h, t, r), KN, seed=11)
+    assert torch.equal(c, s.sample((h, t, r), KN, seed=11))
+    assert not torch.equal(c, s.sample((h, t, r), KN, seed=12))
+    cn = c.cpu().numpy().reshape(B, KN)
+    head = cn < 0
+    ent = np.where(head, ~cn, cn)
+    assert ent.min() >= 0 and ent.max() < E
+    nh = np.where(head, ent, pos[:, :1])
+    nt = np.where(head, pos[:, 1:2], ent)
+    assert not (head & (ent == pos[:, :1])).any() and not (~head & (ent == pos[:, 1:2])).any()
+    bad = sum((int(a), int(b), int(pos[j, 2])) in kset for j in range(B) for a, b in zip(nh[j], nt[j]))
+    assert bad == 0
+    assert abs(head.mean() - 0.5) < 0.02                                   # fair coin (32k draws)
+    # tails of h < 40 are filtered heavily; unfiltered draws are uniform over the entities
+    free = TripleNegativeSampler(E, R, None).sample((h, t, r), KN, seed=5).cpu().numpy()
+    e2 = np.where(free < 0, ~free, free)
+    cnt = np.bincount(e2, minlength=E)
+    assert cnt.min() > 0 and abs(cnt.std() / cnt.mean() - 1 / np.sqrt(cnt.mean())) < 0.05   # Poisson-like spread
+    # ratings
+    U, I = 50, 300
+    kr = np.unique(np.stack([rng.randint(0, U, 6000), rng.randint(0, I, 6000)], axis=1), axis=0)
+    rs = RatingNegativeSampler(I, torch.from_numpy(kr))
+    pr = kr[rng.choice(len(kr), 2000, replace=False)]
+    ni = rs.sample(lt(pr[:, 0]), lt(pr[:, 1]), 3, seed=4).cpu().numpy().reshape(-1, 3)
+    rset = set(map(tuple, kr.tolist()))
+    assert ni.min() >= 0 and ni.max() < I
+    assert not any((int(pr[j, 0]), int(x)) in rset for j in range(len(pr)) for x in ni[j])
+    # the sampler's output drives the fused step directly
+    import kgrec_b200 as K
+    m = K.TransEModel(False, 100, E, R)
+    loss, _, _ = m.loss_step_corrupt((h, t, r), c, margin=1.0, batch_pos=1000)
+    assert loss.shape == (4,) and torch.isfinite(loss).all()
+    m.check_indices()
