@@ -301,6 +301,18 @@ int kgrec_eval_rank_count(const kgrec_tables* tables, int model, int side,
                           const float* gold_scores, const int32_t* gold_ids,
                           int32_t* counts, kgrec_stream_t stream);
 
+/* Soft-preference rec-side evaluation (use_st_gumbel = 0) on augmented rows: with raw logits as
+ * mixing weights (transUP.py:108-113) r and w are linear in the logits, so each table row is
+ * augmented ONCE into [x | x +/- XA | -/+ XB | x . XB] (leading dimension kgrec_pref_aug_ld(d))
+ * and the pair score needs two cross dots and one distance pass.  Build the query rows
+ * (is_query = 1; ids gathers user rows) and the catalog rows (is_query = 0; rows = the item
+ * table, or the kgrec_ktup_item_table output), then call kgrec_eval_scores / kgrec_eval_topk
+ * with side = KGREC_SIDE_REC, qvec = the augmented query rows and cat = the augmented catalog. */
+int32_t kgrec_pref_aug_ld(int32_t dim);
+int kgrec_pref_aug_rows(const kgrec_tables* tables, int model, int is_query,
+                        const void* ids, int idx_bytes, const float* rows, int64_t row_ld, int64_t n,
+                        float* out, int64_t ld_out, kgrec_stream_t stream);
+
 /* KTUP rec-side catalog: out[i] = Item[item_begin + i] + Ent[item2ent[item_begin + i]]
  * (jTransUP.py:177-181), n_items rows with leading dimension ld_out. */
 int kgrec_ktup_item_table(const kgrec_tables* tables, int64_t item_begin, int64_t n_items,

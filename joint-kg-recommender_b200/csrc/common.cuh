@@ -265,4 +265,12 @@ __device__ __forceinline__ float gumbel_from_uniform(float u) {
   return -logf(-logf(u + eps) + eps);
 }
 
+// In-kernel draws (no caller-supplied uniforms to reproduce): u in (0,1) strictly, so the two
+// eps terms of the reference formula are not needed and the logs can be the 2-instruction
+// lg2.approx form.  Same distribution; used only when the noise is generated on the device.
+__device__ __forceinline__ float gumbel_fast(uint32_t bits) {
+  const float u = (static_cast<float>(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+  return -__logf(-__logf(u));
+}
+
 }  // namespace kgrec

@@ -103,14 +103,14 @@ __device__ __forceinline__ bool filtered(const int32_t* __restrict__ flt, int64_
 }
 
 // cheap counter hash for the eval-time Gumbel draw (one 32-bit word per (query, row, k))
-__device__ __forceinline__ float hash_uniform(uint64_t seed, uint32_t q, uint32_t n, uint32_t k) {
+__device__ __forceinline__ uint32_t hash_bits(uint64_t seed, uint32_t q, uint32_t n, uint32_t k) {
   uint32_t x = static_cast<uint32_t>(seed) ^ (q * 0x9E3779B1u);
   x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15;
   x ^= n * 0x85EBCA77u + static_cast<uint32_t>(seed >> 32);
   x *= 0x735a2d97u; x ^= x >> 15;
   x ^= k * 0xC2B2AE3Du;
   x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
-  return static_cast<float>(x >> 8) * (1.0f / 16777216.0f);
+  return x;
 }
 
 struct EvalArgs {
@@ -429,10 +429,10 @@ k_eval(const EvalArgs A) {
             int bk = 0x7fffffff;
             const uint32_t gn = static_cast<uint32_t>(A.id_base + row0 + rr);
             for (int k = myj; k < P; k += 4) {
-              float uu;
-              if (A.gumbel_u) uu = q_valid ? __ldg(A.gumbel_u + (my_query * A.n_cat + (row0 + rr)) * P + k) : 0.5f;
-              else uu = hash_uniform(A.seed, static_cast<uint32_t>(my_query), gn, static_cast<uint32_t>(k));
-              const float v = UPw[myq * ppad + k] + IP[rr * ppad + k] + gumbel_from_uniform(uu);
+              float gn_k;
+              if (A.gumbel_u) gn_k = gumbel_from_uniform(q_valid ? __ldg(A.gumbel_u + (my_query * A.n_cat + (row0 + rr)) * P + k) : 0.5f);
+              else gn_k = gumbel_fast(hash_bits(A.seed, static_cast<uint32_t>(my_query), gn, static_cast<uint32_t>(k)));
+              const float v = UPw[myq * ppad + k] + IP[rr * ppad + k] + gn_k;
               if (v > best) { best = v; bk = k; }
             }
 #pragma unroll
@@ -894,6 +894,263 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
   end_qtile();
 }
 
+// =============================================================================================
+// Soft-preference (no Gumbel) rec-side evaluation on the register-tiled structure.
+//
+// With raw logits as mixing weights (transUP.py:108-113) everything is linear in the logits:
+//   z = (u + i) P'^T / 2 = zu + zi,  r = hf z P' = UA_q + IA_n,  w = hf z N' = UB_q + IB_n
+// so with augmented rows built once per table by k_pref_aug
+//   query   [ U = u | A = u + UA | -UB | c = u . UB ]      catalog [ I = i | B = i - IA | IB | dn = i . IB ]
+// the pair score is  L( (A - s UB) - (B + s IB) ),  s = (u - i).(UB + IB) = c - dn + sum(U IB - I UB):
+// two cross dots and one fused distance pass -- 6 FP32 lane-ops per (pair, dim), no per-pair
+// mixing.  Rows are lda = 3 d + pad floats (pad makes lda / 4 odd: conflict-free 128-bit loads).
+// =============================================================================================
+__host__ __device__ inline int pref_aug_ld(int d) { return 3 * d + ((((3 * d) / 4) & 1) ? 8 : 4); }
+
+// one warp per row: out[row] = augmented row (see above).  x rows come from `rows` (+ ids gather).
+__global__ void __launch_bounds__(kThreads)
+k_pref_aug(const kgrec_tables T, const int ktup, const int is_query, const void* ids, const int is64,
+           const float* __restrict__ rows, const int64_t row_ld, const int64_t n, float* __restrict__ out, const int64_t lda) {
+  using R = Row<2, true>;
+  constexpr int NE = 8;
+  extern __shared__ __align__(16) float aug_smem[];
+  const int d = T.dim, P = T.n_pref, stride = (d + 3) & ~3;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* sP = aug_smem;
+  float* sN = sP + P * stride;
+  float* scr = sN + P * stride + wid * kMaxPref;
+  for (int idx = threadIdx.x; idx < P * stride; idx += blockDim.x) {
+    const int k = idx / stride, j = idx - k * stride;
+    float a = 0.f, b = 0.f;
+    if (j < d) {
+      a = __ldg(T.pref + static_cast<int64_t>(k) * T.ld + j);
+      b = __ldg(T.pref_norm + static_cast<int64_t>(k) * T.ld + j);
+      if (ktup) { a += __ldg(T.rel + static_cast<int64_t>(k) * T.ld + j); b += __ldg(T.norm + static_cast<int64_t>(k) * T.ld + j); }
+    }
+    sP[idx] = a;
+    sN[idx] = b;
+  }
+  __syncthreads();
+  const float hf = ktup ? 0.5f : 1.f;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + wid; row < n; row += static_cast<int64_t>(gridDim.x) * kWarpsPerCta) {
+    const int64_t src = ids ? load_idx(ids, row, is64) : row;
+    float x[NE];
+    R::load(x, rows + src * row_ld, d, lane);
+    __syncwarp();
+    for (int g = 0; g < P; g += 8) {               // XP_k = x . P'_k / 2
+      float vals[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        vals[kk] = 0.f;
+        if (g + kk < P) {
+          float pr[NE];
+          R::load_s(pr, sP + (g + kk) * stride, d, lane);
+          vals[kk] = R::dot(pr, x);
+        }
+      }
+      const float v = warp_reduce_scatter8(vals, lane);
+      const int k = g + (lane >> 2);
+      if ((lane & 3) == 0 && k < P) scr[k] = 0.5f * v;
+    }
+    __syncwarp();
+    float xa[NE], xb[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) { xa[e] = 0.f; xb[e] = 0.f; }
+    for (int k = 0; k < P; ++k) {
+      const float z = hf * scr[k];
+      float pr[NE];
+      R::load_s(pr, sP + k * stride, d, lane);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) xa[e] = fmaf(z, pr[e], xa[e]);
+      R::load_s(pr, sN + k * stride, d, lane);
+#pragma unroll
+      for (int e = 0; e < NE; ++e) xb[e] = fmaf(z, pr[e], xb[e]);
+    }
+    const float sc = warp_sum(R::dot(x, xb));
+    float seg1[NE], seg2[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      seg1[e] = is_query ? x[e] + xa[e] : x[e] - xa[e];
+      seg2[e] = is_query ? -xb[e] : xb[e];
+    }
+    float* o = out + row * lda;
+    R::store(o, x, d, lane);
+    R::store(o + d, seg1, d, lane);
+    R::store(o + 2 * d, seg2, d, lane);
+    for (int j = 3 * d + lane; j < lda; j += 32) o[j] = (j == 3 * d) ? sc : 0.f;
+  }
+}
+
+struct SoftSmem { size_t bars, q, tiles, lists, total; };
+__host__ __device__ inline SoftSmem soft_smem_layout(int mode, int lda, int stages, int k, int warps) {
+  SoftSmem s{};
+  size_t off = 0;
+  s.bars = off; off += 2 * 8 * sizeof(uint64_t);
+  off = (off + 127) & ~static_cast<size_t>(127);
+  s.q = off; off += static_cast<size_t>(RQ) * warps * lda * sizeof(float);
+  off = (off + 127) & ~static_cast<size_t>(127);
+  s.tiles = off; off += static_cast<size_t>(stages) * 32 * lda * sizeof(float);
+  if (mode == MODE_TOPK) { s.lists = off; off += static_cast<size_t>(RQ) * warps * k * sizeof(uint64_t); }
+  s.total = off;
+  return s;
+}
+
+template <int MODE, bool L1, int W>
+__global__ void __launch_bounds__(W * 32, 1)
+k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int TN = 32;
+  constexpr int TQT = RQ * W;
+  const int d = A.T.dim;
+  const int lda = static_cast<int>(A.cat_ld);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const SoftSmem L = soft_smem_layout(MODE, lda, stages, A.k, W);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
+  uint64_t* empty = full + 8;
+  float* sQ = reinterpret_cast<float*>(smem_raw + L.q);
+  float* tiles = reinterpret_cast<float*>(smem_raw + L.tiles);
+
+  const int64_t n_tiles = (A.n_cat + TN - 1) / TN;
+  const int64_t n_qtiles = (A.nq + TQT - 1) / TQT;
+  const int64_t total_units = n_tiles * n_qtiles;
+  const int64_t u_begin = min(total_units, static_cast<int64_t>(blockIdx.x) * units_per_cta);
+  const int64_t u_end = min(total_units, u_begin + units_per_cta);
+  const int64_t my_units = u_end - u_begin;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, W); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (my_units <= 0) return;
+  auto issue_tile = [&](int64_t g) {          // lane 0 of warp 0
+    const int s = static_cast<int>(g % stages);
+    const int64_t row0 = ((u_begin + g) % n_tiles) * TN;
+    const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
+    if (g >= stages) mbar_wait(empty + s, static_cast<uint32_t>(((g / stages) - 1) & 1));
+    const uint32_t bytes = static_cast<uint32_t>(rows) * lda * sizeof(float);
+    mbar_arrive_expect_tx(full + s, bytes);
+    bulk_g2s(tiles + static_cast<size_t>(s) * TN * lda, A.cat + row0 * lda, bytes, full + s);
+  };
+  const int prefetch = stages - 1;
+  if (threadIdx.x == 0)
+    for (int64_t g = 0; g < prefetch && g < my_units; ++g) issue_tile(g);
+
+  [[maybe_unused]] uint32_t thr_hi[RQ];
+  [[maybe_unused]] uint64_t* lists = nullptr;
+  if constexpr (MODE == MODE_TOPK)
+    lists = reinterpret_cast<uint64_t*>(smem_raw + L.lists) + static_cast<size_t>(wid) * RQ * A.k;
+  const float* cq = sQ + wid * RQ * lda;
+  const int nk4 = d >> 2;
+  int64_t cur_qt = -1, q0 = 0;
+  auto begin_qtile = [&](int64_t qt) {
+    cur_qt = qt;
+    q0 = qt * TQT + wid * RQ;
+    __syncwarp();
+    for (int qi = 0; qi < RQ; ++qi) {
+      const int64_t q = q0 + qi;
+      float4* dst = reinterpret_cast<float4*>(sQ + (wid * RQ + qi) * lda);
+      const float4* src = reinterpret_cast<const float4*>(A.qvec + q * lda);
+      for (int c = lane; c < lda / 4; c += 32) dst[c] = (q < A.nq) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi) thr_hi[qi] = 0xffffffffu;
+    if constexpr (MODE == MODE_TOPK)
+      for (int i = lane; i < RQ * A.k; i += 32) lists[i] = KEY_INF;
+    __syncwarp();
+  };
+  auto end_qtile = [&]() {
+    if constexpr (MODE == MODE_TOPK) {
+      __syncwarp();
+      const int64_t first_cta = (cur_qt * n_tiles) / units_per_cta;
+      const int64_t piece = static_cast<int64_t>(blockIdx.x) - first_cta;
+      for (int i = lane; i < RQ * A.k; i += 32) {
+        const int64_t q = q0 + i / A.k;
+        if (q < A.nq) A.part_keys[(piece * A.nq + q) * A.k + (i % A.k)] = lists[i];
+      }
+    }
+  };
+
+  for (int64_t g = 0; g < my_units; ++g) {
+    const int64_t u = u_begin + g;
+    const int64_t qt = u / n_tiles, ti = u - qt * n_tiles;
+    if (qt != cur_qt) {
+      if (cur_qt >= 0) end_qtile();
+      begin_qtile(qt);
+    }
+    const int s = static_cast<int>(g % stages);
+    if (threadIdx.x == 0 && g + prefetch < my_units) issue_tile(g + prefetch);
+    __syncwarp();
+    const float* xr = tiles + static_cast<size_t>(s) * TN * lda + lane * lda;   // this lane's catalog row
+    const int64_t row0 = ti * TN;
+    const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
+    mbar_wait(full + s, static_cast<uint32_t>((g / stages) & 1));
+
+    // pass 1: cross dots  sum_j ( U_q IB_n + I_n (-UB_q) )
+    f32x2 sd2[RQ];
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi) sd2[qi] = 0ull;
+#pragma unroll 1
+    for (int k4 = 0; k4 < nk4; ++k4) {
+      const ulonglong2 xi = *reinterpret_cast<const ulonglong2*>(xr + 4 * k4);
+      const ulonglong2 xw = *reinterpret_cast<const ulonglong2*>(xr + 2 * d + 4 * k4);
+#pragma unroll
+      for (int qi = 0; qi < RQ; ++qi) {
+        const ulonglong2 qu = *reinterpret_cast<const ulonglong2*>(cq + qi * lda + 4 * k4);
+        const ulonglong2 qn = *reinterpret_cast<const ulonglong2*>(cq + qi * lda + 2 * d + 4 * k4);
+        sd2[qi] = fma2(qu.x, xw.x, fma2(qu.y, xw.y, fma2(xi.x, qn.x, fma2(xi.y, qn.y, sd2[qi]))));
+      }
+    }
+    const float dn = xr[3 * d];
+    float sv[RQ];
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi) sv[qi] = sum2(sd2[qi]) + cq[qi * lda + 3 * d] - dn;
+    // pass 2: L( (A_q - s UB_q) - (B_n + s IB_n) )
+    f32x2 acc2[RQ];
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi) acc2[qi] = 0ull;
+#pragma unroll 1
+    for (int k4 = 0; k4 < nk4; ++k4) {
+      const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(xr + d + 4 * k4);
+      const ulonglong2 xw = *reinterpret_cast<const ulonglong2*>(xr + 2 * d + 4 * k4);
+#pragma unroll
+      for (int qi = 0; qi < RQ; ++qi) {
+        const ulonglong2 qa = *reinterpret_cast<const ulonglong2*>(cq + qi * lda + d + 4 * k4);
+        const ulonglong2 qn = *reinterpret_cast<const ulonglong2*>(cq + qi * lda + 2 * d + 4 * k4);
+        const f32x2 s2 = splat2(sv[qi]);
+        const f32x2 e01 = sub2(fma2(s2, qn.x, qa.x), fma2(s2, xw.x, xb.x));
+        const f32x2 e23 = sub2(fma2(s2, qn.y, qa.y), fma2(s2, xw.y, xb.y));
+        if (L1) {
+          const float t = abssum2(e01) + abssum2(e23);
+          acc2[qi] = static_cast<f32x2>(__float_as_uint(__uint_as_float(static_cast<uint32_t>(acc2[qi])) + t));
+        } else {
+          acc2[qi] = fma2(e01, e01, fma2(e23, e23, acc2[qi]));
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+
+    const bool valid = lane < rows;
+    const int64_t n_local = row0 + lane;
+#pragma unroll
+    for (int qi = 0; qi < RQ; ++qi) {
+      const int64_t q = q0 + qi;
+      if (q >= A.nq) continue;
+      const float sc = sum2(acc2[qi]);
+      if constexpr (MODE == MODE_FULL) {
+        if (valid) __stcs(A.out + q * A.ld_out + n_local, sc);
+      } else {
+        const uint32_t sb = __float_as_uint(sc);
+        const unsigned mask = __ballot_sync(FULL, valid && sb <= thr_hi[qi]);
+        if (mask)
+          thr_hi[qi] = topk_insert_candidates(mask, sb, static_cast<uint32_t>(A.id_base + row0), lists + qi * A.k, A.k,
+                                              A.filter_ptr, A.filter_ids, q, lane);
+      }
+    }
+  }
+  end_qtile();
+}
+
 // K-way merge: in [n_lists][nq][k] ascending lists -> out [nq][k].  One warp per query.
 __global__ void __launch_bounds__(256)
 k_merge_topk(const uint64_t* __restrict__ in, int n_lists, int64_t nq, int k, uint64_t* __restrict__ out) {
@@ -939,6 +1196,7 @@ struct EvalPlan {
   int64_t n_qtiles;
   size_t smem;
   bool tiled;       // register-tiled kernel (KG kinds)
+  bool soft_aug;    // rec side, soft preferences, augmented rows (k_eval_soft)
   int rn, stages, grid, warps;
   int64_t units_per_cta;
 };
@@ -967,6 +1225,33 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
   }
   const bool rec = side == KGREC_SIDE_REC;
   if (rec != (pl->kind >= KIND_PREF_HARD)) { set_error("side %d does not fit model %d", side, model); return KGREC_ERR_INVALID; }
+  pl->soft_aug = false;
+  if (rec && have_qvec) {
+    // augmented-row evaluation of the soft preference model (rows built by kgrec_pref_aug_rows)
+    if (pl->kind != KIND_PREF_SOFT) { set_error("augmented rec rows are for use_st_gumbel = 0"); return KGREC_ERR_INVALID; }
+    if (cat_ld != pref_aug_ld(d)) { set_error("augmented catalog must have leading dimension %d", pref_aug_ld(d)); return KGREC_ERR_INVALID; }
+    if (mode == MODE_RANK) { set_error("rank counts are built for the KG sides"); return KGREC_ERR_UNSUPPORTED; }
+    if (mode == MODE_TOPK && (k <= 0 || k > 128)) { set_error("topn %d outside [1, 128]", k); return KGREC_ERR_UNSUPPORTED; }
+    pl->soft_aug = true;
+    pl->tiled = false;
+    pl->warps = 8;
+    int stages = 3;
+    while (stages > 2 && soft_smem_layout(mode, static_cast<int>(cat_ld), stages, k, 8).total > 215 * 1024) --stages;
+    pl->stages = stages;
+    pl->smem = soft_smem_layout(mode, static_cast<int>(cat_ld), stages, k, 8).total;
+    if (pl->smem > 225 * 1024) { set_error("eval: shared-memory budget exceeded (%zu bytes)", pl->smem); return KGREC_ERR_UNSUPPORTED; }
+    const int64_t n_tiles_t = (n_cat + 31) / 32;
+    pl->n_qtiles = (nq + RQ * 8 - 1) / (RQ * 8);
+    const int64_t total_units = n_tiles_t * pl->n_qtiles;
+    int64_t ctas = sm_count();
+    if (ctas > total_units) ctas = total_units;
+    pl->units_per_cta = (total_units + ctas - 1) / ctas;
+    pl->grid = static_cast<int>((total_units + pl->units_per_cta - 1) / pl->units_per_cta);
+    pl->n_splits = static_cast<int>((n_tiles_t + pl->units_per_cta - 1) / pl->units_per_cta + 1);
+    A->T = *T; A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
+    A->n_splits = pl->n_splits; A->tn = 32; A->k = k;
+    return KGREC_OK;
+  }
   bool al = true;
   auto chk = [&](const void* p) { if (!p || !aligned16(p)) al = false; };
   if (rec) { chk(T->user); chk(T->pref); chk(T->pref_norm); if (A->ktup) { chk(T->rel); chk(T->norm); } }
@@ -1032,6 +1317,18 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
 template <int MODE>
 static int launch_eval(const EvalArgs& A, const EvalPlan& pl, cudaStream_t st) {
   const dim3 grid(static_cast<unsigned>(pl.n_qtiles), static_cast<unsigned>(pl.n_splits));
+  if (pl.soft_aug) {
+    if constexpr (MODE == MODE_RANK) {
+      set_error("rank counts are built for the KG sides");
+      return KGREC_ERR_UNSUPPORTED;
+    } else {
+      auto kern = A.T.l1 ? k_eval_soft<MODE, true, 8> : k_eval_soft<MODE, false, 8>;
+      KGREC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(pl.smem)));
+      kern<<<pl.grid, 8 * 32, pl.smem, st>>>(A, pl.stages, pl.units_per_cta);
+      KGREC_CUDA_OK(cudaGetLastError());
+      return KGREC_OK;
+    }
+  }
   if (pl.tiled) {
 #define KGREC_TILED_CASE(KINDV, RNV, WV)                                                                      \
   {                                                                                                           \
@@ -1109,7 +1406,7 @@ extern "C" int kgrec_eval_topk(const kgrec_tables* tables, int model, int side, 
   A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
   A.gumbel_u = gumbel_u; A.seed = seed; A.id_base = id_base;
   A.filter_ptr = filter_ptr; A.filter_ids = filter_ids;
-  if (pl.n_splits == 1 && !pl.tiled) {
+  if (pl.n_splits == 1 && !pl.tiled && !pl.soft_aug) {
     A.part_keys = out_keys;
     return launch_eval<MODE_TOPK>(A, pl, st);
   }
@@ -1118,7 +1415,7 @@ extern "C" int kgrec_eval_topk(const kgrec_tables* tables, int model, int side, 
     return KGREC_ERR_INVALID;
   }
   A.part_keys = static_cast<uint64_t*>(workspace);
-  if (pl.tiled) KGREC_CUDA_OK(cudaMemsetAsync(workspace, 0xff, static_cast<size_t>(need), st));   // unused pieces = empty lists
+  if (pl.tiled || pl.soft_aug) KGREC_CUDA_OK(cudaMemsetAsync(workspace, 0xff, static_cast<size_t>(need), st));   // unused pieces = empty lists
   if ((rc = launch_eval<MODE_TOPK>(A, pl, st))) return rc;
   return kgrec_merge_topk(A.part_keys, pl.n_splits, nq, k, out_keys, stream);
 }
@@ -1159,6 +1456,34 @@ extern "C" int kgrec_ktup_item_table(const kgrec_tables* tables, int64_t item_be
   const int64_t total = n_items * tables->dim;
   const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
   k_ktup_items<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*tables, item_begin, n_items, out, ld_out);
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}
+
+extern "C" int32_t kgrec_pref_aug_ld(int32_t dim) { return pref_aug_ld(dim); }
+
+extern "C" int kgrec_pref_aug_rows(const kgrec_tables* tables, int model, int is_query, const void* ids, int idx_bytes,
+                                   const float* rows, int64_t row_ld, int64_t n, float* out, int64_t ld_out,
+                                   kgrec_stream_t stream) {
+  if (!tables || !rows || !out || n < 0 || (model != KGREC_TUP && model != KGREC_KTUP)) { set_error("pref_aug_rows: bad arguments"); return KGREC_ERR_INVALID; }
+  const int d = tables->dim;
+  if (d <= 0 || d > 256 || d % 4 || row_ld % 4 || tables->ld % 4 || ld_out != pref_aug_ld(d)) {
+    set_error("pref_aug_rows: embedding_size must be a multiple of 4 (<= 256) and ld_out = %d", pref_aug_ld(d > 0 ? d : 4));
+    return KGREC_ERR_UNSUPPORTED;
+  }
+  const bool ktup = model == KGREC_KTUP;
+  if (!tables->pref || !tables->pref_norm || (ktup && (!tables->rel || !tables->norm)) || tables->n_pref <= 0 || tables->n_pref > kMaxPref ||
+      !aligned16(rows) || !aligned16(out) || !aligned16(tables->pref) || !aligned16(tables->pref_norm)) {
+    set_error("pref_aug_rows: preference tables missing / misaligned");
+    return KGREC_ERR_INVALID;
+  }
+  if (ids && idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 4 or 8"); return KGREC_ERR_INVALID; }
+  if (n == 0) return KGREC_OK;
+  const size_t smem = (static_cast<size_t>(2) * tables->n_pref * ((d + 3) & ~3) + kWarpsPerCta * kMaxPref) * sizeof(float);
+  KGREC_CUDA_OK(cudaFuncSetAttribute(k_pref_aug, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta, cap = static_cast<int64_t>(sm_count()) * 4;
+  k_pref_aug<<<static_cast<int>(ctas < cap ? ctas : cap), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      *tables, ktup ? 1 : 0, is_query ? 1 : 0, ids, idx_bytes == 8, rows, row_ld, n, out, ld_out);
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;
 }

@@ -269,8 +269,8 @@ struct RecPair {
       float best = -INFINITY;
       int bk = 0x7fffffff;
       for (int k = lane; k < P; k += 32) {
-        const float uu = gu_row ? __ldg(gu_row + k) : philox_uniform(seed, pair_id, static_cast<uint32_t>(k));
-        const float v = scr[k] + gumbel_from_uniform(uu);
+        const float v = scr[k] + (gu_row ? gumbel_from_uniform(__ldg(gu_row + k))
+                                         : gumbel_fast(philox_uniform_bits(seed, pair_id, static_cast<uint32_t>(k))));
         scr[kMaxPref + k] = v;
         if (v > best) { best = v; bk = k; }
       }

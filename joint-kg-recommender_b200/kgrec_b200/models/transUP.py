@@ -20,17 +20,50 @@ class RecModelBase(KGRecModule):
     def _rec_catalog(self):
         return self.item_embeddings.weight.detach()
 
-    def _rec_scores(self, u_ids, gumbel_u=None):
-        seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
-        return self._eval(self.MODEL, _lib.SIDE_REC, u_ids, None, "scores", catalog=self._rec_catalog(),
-                          gumbel_u=gumbel_u, seed=seed)
+    def _aug_rows(self, rows, is_query, ids=None):
+        """Augmented rows of the soft-preference evaluation (kgrec_pref_aug_rows)."""
+        import ctypes as C
+        dev = self._require_cuda()
+        lib = _lib.load()
+        T = KF.make_tables(self._weights(), self.embedding_size, self.L1_flag, self.use_st_gumbel, self._item2ent)
+        n = ids.numel() if ids is not None else rows.shape[0]
+        lda = int(lib.kgrec_pref_aug_ld(self.embedding_size))
+        out = torch.empty((n, lda), dtype=torch.float32, device=dev)
+        _lib.check(lib.kgrec_pref_aug_rows(C.byref(T), self.MODEL, 1 if is_query else 0,
+                                           KF._ptr(ids), ids.element_size() if ids is not None else 8,
+                                           KF._ptr(rows), rows.stride(0), n, KF._ptr(out), lda, KF._stream()))
+        KF.count_launches(1)
+        return out
 
-    def topk_items(self, u_ids, k=10, filter_csr=None, catalog=None, id_base=0, gumbel_u=None):
-        """K best items per user as uint64 keys (int64 storage): score bits << 32 | item id."""
+    def soft_catalog(self, catalog=None):
+        """Augmented item catalog for repeated soft-mode evaluation calls (build once per table
+        state: it depends on the item and preference tables)."""
+        cat = self._rec_catalog() if catalog is None else catalog
+        return self._aug_rows(cat.contiguous(), False)
+
+    def _rec_call(self, mode, u_ids, gumbel_u, catalog, soft_catalog, **kw):
+        dev = self._require_cuda()
+        use_aug = (not self.use_st_gumbel) and self.embedding_size % 4 == 0 and self.embedding_size <= 256
+        if use_aug:
+            u = KF.as_index(u_ids, dev)
+            if u.numel() == 0:
+                return self._eval(self.MODEL, _lib.SIDE_REC, u, None, mode, catalog=self._rec_catalog(), **kw)
+            aug_cat = soft_catalog if soft_catalog is not None else self.soft_catalog(catalog)
+            qrows = self._aug_rows(self.user_embeddings.weight.detach(), True, ids=u)
+            return self._eval(self.MODEL, _lib.SIDE_REC, None, None, mode, catalog=aug_cat, qvec=qrows, **kw)
         seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
         cat = self._rec_catalog() if catalog is None else catalog
-        return self._eval(self.MODEL, _lib.SIDE_REC, u_ids, None, "topk", catalog=cat, id_base=id_base, k=k,
-                          filter_csr=filter_csr, gumbel_u=gumbel_u, seed=seed)
+        return self._eval(self.MODEL, _lib.SIDE_REC, u_ids, None, mode, catalog=cat, gumbel_u=gumbel_u, seed=seed, **kw)
+
+    def _rec_scores(self, u_ids, gumbel_u=None):
+        return self._rec_call("scores", u_ids, gumbel_u, None, None)
+
+    def topk_items(self, u_ids, k=10, filter_csr=None, catalog=None, id_base=0, gumbel_u=None, soft_catalog=None):
+        """K best items per user as uint64 keys (int64 storage): score bits << 32 | item id.
+        catalog: a row shard of the item table (KTUP: of _rec_catalog()); soft_catalog: its
+        augmented form from soft_catalog(), reusable across calls while the tables are unchanged."""
+        return self._rec_call("topk", u_ids, gumbel_u, catalog, soft_catalog, id_base=id_base, k=k,
+                              filter_csr=filter_csr)
 
     def rank_loss(self, pos, neg, target=-1.0, loss="bpr", batch_pos=None, gumbel_u=None):
         """Fused pos + K negatives + ranking loss: pos = (u, i), neg = (u repeated, ni)."""
