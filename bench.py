@@ -410,6 +410,28 @@ def run_ours(args):
               "fp32_bound_pairs_per_s": 148 * 128 * 1.965e9 / (2 * D) * world,
               "frac_of_fp32_bound": nq * n_cat / (ems * 1e-3) / (148 * 128 * 1.965e9 / (2 * D) * world)}
 
+    # ---- rec-side evaluation (BASELINE configs[2] shape): TUP d=100, P=20, 50k users x 50k items,
+    # soft preferences (the shipped transup.sh setting), top-10 per user, on this rank only
+    ev_rec = None
+    if not args.no_eval and rank == 0:
+        torch.manual_seed(11)
+        rmodel = K.TransUPModel(False, D, 50_000, 50_000, 20, False)
+        qu = torch.arange(0, args.eval_queries, device=dev) % 50_000
+        soft_cat = rmodel.soft_catalog()
+        for _ in range(2):
+            rmodel.topk_items(qu, k=10, soft_catalog=soft_cat)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(3):
+            rmodel.topk_items(qu, k=10, soft_catalog=soft_cat)
+        r1.record()
+        torch.cuda.synchronize()
+        rms = r0.elapsed_time(r1) / 3
+        ev_rec = {"metric": "scored (user,item) pairs/s, TUP soft d=100 P=20 full-catalog top-10", "value": args.eval_queries * 50_000 / (rms * 1e-3),
+                  "unit": "pairs/s", "ms": rms, "users": args.eval_queries, "items": 50_000, "n_gpus": 1,
+                  "note": "augmented item rows built once (soft_catalog), user rows per call"}
+        del rmodel, soft_cat
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -464,6 +486,7 @@ def run_ours(args):
                             "with_device_negative_sampling_ms": loop_ms,
                             "with_device_negative_sampling_triples_per_s": n_tri / (loop_ms * 1e-3)},
         "eval": ev,
+        "eval_rec": ev_rec,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg(torch)

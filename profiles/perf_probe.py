@@ -31,7 +31,7 @@ n_tri = ix[0].numel() * 11
 for name, cls in (("transe", K.TransEModel), ("transh", K.TransHModel)):
     m = cls(False, 100, 100_000, 500)
     m.grad_mode = "sparse"
-    pos, neg = tuple(ix[:3]), tuple(ix[3:])
+    pos, neg = tuple(ix[:3]), tuple(ix[3:6])
     f = timeit(lambda: m.rank_loss(pos, neg, margin=1.0, batch_pos=1024))
 
     def fb():

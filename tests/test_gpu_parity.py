@@ -803,3 +803,55 @@ def test_device_negative_sampling():
     loss, _, _ = m.loss_step_corrupt((h, t, r), c, margin=1.0, batch_pos=1000)
     assert loss.shape == (4,) and torch.isfinite(loss).all()
     m.check_indices()
+
+
+@pytest.mark.parametrize("with_norm", [False, True])
+def test_unchanged_driver_call_pattern_trajectory(with_norm):
+    """The reference's KG train_loop body (knowledge_representation.py:179-216) written against
+    the drop-in module, step for step: LongTensor ids, pos/neg forward calls, marginLoss, the
+    regulariser gathers through model.ent_embeddings / rel_embeddings / norm_embeddings
+    (loss.py:18-23), backward with dense grads, clip_grad_norm, Adam with weight decay.  Five
+    steps must follow the same trajectory as the reference's op sequence on the CPU
+    (oracle/torch_port.py, itself pinned to the golden vectors)."""
+    import kgrec_b200 as K
+    from oracle import torch_port as TP
+    torch.manual_seed(31)
+    d, E, R, B = 100, 400, 6, 128
+    gpu = (K.TransHModel if with_norm else K.TransEModel)(False, d, E, R)      # L2: smooth gradients
+    cpu = TP.TransPort(False, d, E, R, with_norm)
+    cpu.load_state_dict({k: v.detach().cpu().clone() for k, v in gpu.state_dict().items()})
+
+    def norm_loss(emb):
+        return torch.clamp((emb ** 2).sum(1) - 1.0, min=0).sum()
+
+    def orth_loss(rel, nrm):
+        return (((nrm * rel).sum(1) ** 2) / (rel ** 2).sum(1)).sum()
+
+    opts = [torch.optim.Adam([p for _, p in m.named_parameters()], lr=0.01, weight_decay=1e-5) for m in (gpu, cpu)]
+    g = torch.Generator().manual_seed(7)
+    for step in range(5):
+        ids = [torch.randint(0, n, (B,), generator=g) for n in (E, E, R, E, E)]
+        losses = []
+        for m, opt, dev_ in ((gpu, opts[0], "cuda"), (cpu, opts[1], "cpu")):
+            ph, pt, pr, nh, nt = (x.to(dev_) for x in ids)
+            nr = pr
+            opt.zero_grad()
+            pos = m(ph, pt, pr)
+            neg = m(nh, nt, nr)
+            loss = torch.sum(torch.max(pos - neg + 1.0, torch.zeros_like(pos)))            # marginLoss
+            ent = m.ent_embeddings(torch.cat([ph, pt, nh, nt]))
+            rel = m.rel_embeddings(torch.cat([pr, nr]))
+            if with_norm:
+                loss = loss + orth_loss(rel, m.norm_embeddings(torch.cat([pr, nr])))
+            loss = loss + norm_loss(ent) + norm_loss(rel)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_([p for _, p in m.named_parameters()], 5.0)
+            opt.step()
+            losses.append(float(loss))
+        assert abs(losses[0] - losses[1]) <= 2e-4 * abs(losses[1]), (step, losses)
+    for (n1, p1), (n2, p2) in zip(gpu.named_parameters(), cpu.named_parameters()):
+        assert n1 == n2
+        close(p1, p2.detach().numpy(), rtol=1e-3, atol=2e-4)
+    # and the evaluation the driver runs afterwards: scores.data.cpu().numpy() per batch
+    q, r = torch.randint(0, E, (16,), generator=g), torch.randint(0, R, (16,), generator=g)
+    close(gpu.evaluateTail(q.cuda(), r.cuda()).data.cpu().numpy(), cpu.evaluate_side(q, r, False).detach().numpy(), rtol=1e-3, atol=1e-4)

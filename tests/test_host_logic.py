@@ -185,3 +185,47 @@ def test_sharded_topk_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_dataio_round_trip(tmp_path):
+    """the reference's TSV layouts parse to the same lists / dicts its loaders
+    build (load_triple_data.py:5-30, load_rating_data.py:19-38), cache round-trips, CSR filter
+    lists match the dict walk, and checkpoints keep the reference's layout."""
+    from kgrec_b200 import dataio, evaluation as KE
+    import kgrec_b200 as K
+    rng = np.random.RandomState(0)
+    trip = np.stack([rng.randint(0, 50, 400), rng.randint(0, 50, 400), rng.randint(0, 5, 400)], axis=1)
+    kg = tmp_path / "train.dat"
+    kg.write_text("".join("%d\t%d\t%d\n" % tuple(r) for r in trip) + "malformed line\n\n7\t8\n")
+    f = dataio.TripleFile(str(kg))
+    assert f.total == 400 and f.as_list() == [tuple(int(v) for v in r) for r in trip]
+    hd, td = f.head_dict(), f.tail_dict()
+    for h, t, r in trip.tolist():
+        assert h in hd[(t, r)] and t in td[(h, r)]
+    assert sum(len(v) for v in hd.values()) == len({tuple(r) for r in trip.tolist()})
+    assert os.path.exists(str(kg) + ".kgrec.npz")
+    assert np.array_equal(dataio.TripleFile(str(kg)).rows, f.rows)           # from the cache
+    rat = tmp_path / "ratings.dat"
+    rat.write_text("".join("%d\t%d\t%d\n" % (u, i, 5) for u, i in zip(rng.randint(0, 9, 100), rng.randint(0, 30, 100))))
+    rf = dataio.RatingFile(str(rat), use_cache=False)
+    rd = rf.rating_dict()
+    assert rf.total == 100 and all(i in rd[u] for u, i in rf.as_list())
+    keys = list(td)[:20]
+    p1, i1 = dataio.csr_from_dicts(keys, [td, {keys[0]: {1, 2, 3}}])
+    p2, i2 = KE.build_filter_csr(keys, [td, {keys[0]: {1, 2, 3}}], torch.device("cpu"))
+    assert torch.equal(p1, p2) and torch.equal(i1, i2)
+    m = K.TransHModel(False, 8, 50, 5)
+    opt = torch.optim.Adagrad(m.parameters(), lr=0.1)
+    ck = tmp_path / "exp.ckpt"
+    dataio.save_checkpoint(str(ck), m, opt, step=12, best_step=10, best_dev_performance=0.5)
+    raw = torch.load(str(ck), map_location="cpu")
+    assert set(raw) == {"step", "best_step", "best_dev_performance", "model_state_dict", "optimizer_state_dict"}
+    assert set(raw["model_state_dict"]) == {"ent_embeddings.weight", "rel_embeddings.weight", "norm_embeddings.weight"}
+    m2 = K.TransHModel(False, 8, 50, 5)
+    assert dataio.load_checkpoint(str(ck), m2) == (12, 10, 0.5)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    # a TransE checkpoint warm-starts a TransH model (strict=False), as trainer.loadEmbedding-style reuse does
+    e = K.TransEModel(False, 8, 50, 5)
+    dataio.save_checkpoint(str(ck), e)
+    dataio.load_checkpoint(str(ck), m2)
+    assert torch.equal(m2.ent_embeddings.weight, e.ent_embeddings.weight)
