@@ -587,8 +587,8 @@ def test_full_scale_configs():
         loss, ps, ns = m.loss_step_corrupt(pos, corrupt, margin=1.0, batch_pos=1024)
         out[gm] = (loss.clone(), {k: v.clone() for k, v in grads_by_name(m).items()})
     assert torch.equal(out["dense"][0], out["sparse"][0]) and out["dense"][0].numel() == 8
-    for k in out["dense"][1]:
-        assert torch.allclose(out["dense"][1][k], out["sparse"][1][k], rtol=1e-4, atol=1e-5)
+    for k in out["dense"][1]:     # dense mode accumulates with atomics: summation order varies run to run
+        assert torch.allclose(out["dense"][1][k], out["sparse"][1][k], rtol=1e-3, atol=1e-4)
     # loss of batch 0 against plain torch arithmetic
     ent, rel, nrm = m.ent_embeddings.weight.detach(), m.rel_embeddings.weight.detach(), m.norm_embeddings.weight.detach()
     hb, tb, rb = (x[:1024] for x in pos)
@@ -818,6 +818,12 @@ def test_unchanged_driver_call_pattern_trajectory(with_norm):
     torch.manual_seed(31)
     d, E, R, B = 100, 400, 6, 128
     gpu = (K.TransHModel if with_norm else K.TransEModel)(False, d, E, R)      # L2: smooth gradients
+    with torch.no_grad():
+        # rows start exactly L2-normalised, i.e. ON the kink of the reference's normLoss
+        # (max(|x|^2 - 1, 0), loss.py:21-23) where CPU and GPU rounding decide differently;
+        # move them off it so the trajectory is well defined
+        gpu.ent_embeddings.weight.mul_(1.04)
+        gpu.rel_embeddings.weight.mul_(0.95)
     cpu = TP.TransPort(False, d, E, R, with_norm)
     cpu.load_state_dict({k: v.detach().cpu().clone() for k, v in gpu.state_dict().items()})
 
