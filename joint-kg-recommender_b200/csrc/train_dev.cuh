@@ -714,10 +714,24 @@ int set_smem(K kernel, size_t bytes) {
   else if (pl.nch == 2) { constexpr int NCH = 2; constexpr bool VEC = true;  __VA_ARGS__ } \
   else                  { constexpr int NCH = 4; constexpr bool VEC = true;  __VA_ARGS__ }
 
+// TUP / KTUP pairs in large flat batches go through the tile engine (train_rec_tile.cu); these
+// return -1 when the shape is outside what it is built for (small n, d > 128, P > 32, unaligned)
+// and the one-warp-per-pair kernels below take the call.
+int rec_tile_score_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n, const float* gumbel_u,
+                       uint64_t seed, float* scores, int32_t* status, cudaStream_t st);
+int rec_tile_rank_loss_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, const LossCfg& L,
+                           const float* gumbel_u, uint64_t seed, float* pos_scores, float* neg_scores,
+                           float* group_loss, int32_t* status, cudaStream_t st);
+int rec_tile_score_bwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n, const LossCfg& L,
+                       const float* gumbel_u, uint64_t seed, const BwdArgs& B, const kgrec_grads& G, cudaStream_t st);
+
 template <int FAM>
 int launch_score_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n, const float* gumbel_u,
                      uint64_t seed, float* scores, int32_t* status, cudaStream_t st) {
   int rc = KGREC_OK;
+  if constexpr (FAM == FAM_REC) {
+    if ((rc = rec_tile_score_fwd(T, pl, I, n, gumbel_u, seed, scores, status, st)) >= 0) return rc;
+  }
   KGREC_DISPATCH_ROW({
     auto kern = k_score_fwd<FAM, NCH, VEC>;
     if ((rc = set_smem(kern, pl.smem_fwd))) return rc;
@@ -732,6 +746,10 @@ int launch_rank_loss_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I
                          const float* gumbel_u, uint64_t seed, float* pos_scores, float* neg_scores,
                          float* group_loss, int32_t* status, cudaStream_t st) {
   int rc = KGREC_OK;
+  if constexpr (FAM == FAM_REC) {
+    if ((rc = rec_tile_rank_loss_fwd(T, pl, I, L, gumbel_u, seed, pos_scores, neg_scores, group_loss, status, st)) >= 0)
+      return rc;
+  }
   KGREC_DISPATCH_ROW({
     auto kern = k_rank_loss_fwd<FAM, NCH, VEC>;
     if ((rc = set_smem(kern, pl.smem_fwd))) return rc;
@@ -747,6 +765,7 @@ int launch_score_bwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, in
                      const float* gumbel_u, uint64_t seed, const BwdArgs& B, const kgrec_grads& G, cudaStream_t st) {
   int rc = KGREC_OK;
   if constexpr (FAM == FAM_REC) {
+    if ((rc = rec_tile_score_bwd(T, pl, I, n, L, gumbel_u, seed, B, G, st)) >= 0) return rc;
 #define KGREC_BWD_REC(PRV)                                                                                  \
   {                                                                                                         \
     auto kern = k_score_bwd<FAM_REC, NCH, VEC, PRV>;                                                        \

@@ -36,6 +36,17 @@ def dense(gr):
     return gr.to_dense() if gr.is_sparse else gr
 
 
+@pytest.fixture(params=["auto", "force"])
+def rec_engine(request, monkeypatch):
+    """TUP / KTUP training calls run twice: size-based engine choice (small batches -> one warp
+    per pair) and every call forced through the tile engine (csrc/train_rec_tile.cu)."""
+    if request.param == "force":
+        monkeypatch.setenv("KGREC_REC_TILE", "force")
+    else:
+        monkeypatch.delenv("KGREC_REC_TILE", raising=False)
+    return request.param
+
+
 def grads_by_name(model):
     return {n.replace(".weight", ""): dense(p.grad) for n, p in model.named_parameters() if p.grad is not None}
 
@@ -81,7 +92,7 @@ def test_golden_kg(golden, name, tag, grad_mode):
 @pytest.mark.parametrize("tag", ["l2", "l1"])
 @pytest.mark.parametrize("mode", ["soft", "gumbel"])
 @pytest.mark.parametrize("grad_mode", ["dense", "sparse"])
-def test_golden_transup(golden, tag, mode, grad_mode):
+def test_golden_transup(golden, tag, mode, grad_mode, rec_engine):
     import kgrec_b200 as K
     g = golden(f"transup_{tag}_{mode}")
     U, D = g["w_user_embeddings"].shape
@@ -115,7 +126,7 @@ def test_golden_transup(golden, tag, mode, grad_mode):
 
 @pytest.mark.parametrize("tag", ["l2", "l1"])
 @pytest.mark.parametrize("mode", ["soft", "gumbel"])
-def test_golden_jtransup(golden, tag, mode):
+def test_golden_jtransup(golden, tag, mode, rec_engine):
     import kgrec_b200 as K
     g = golden(f"jtransup_{tag}_{mode}")
     U, D = g["w_user_embeddings"].shape
@@ -231,7 +242,7 @@ def test_oracle_transr(l1):
 @pytest.mark.parametrize("d,P", [(100, 20), (64, 13), (128, 50), (52, 4)])
 @pytest.mark.parametrize("l1", [False, True])
 @pytest.mark.parametrize("gumbel", [False, True])
-def test_oracle_tup(d, P, l1, gumbel):
+def test_oracle_tup(d, P, l1, gumbel, rec_engine):
     import kgrec_b200 as K
     torch.manual_seed(P)
     rng = np.random.RandomState(P)
@@ -268,7 +279,7 @@ def test_oracle_tup(d, P, l1, gumbel):
         assert torch.equal(a, b)
 
 
-def test_oracle_ktup_gumbel_l1():
+def test_oracle_ktup_gumbel_l1(rec_engine):
     import kgrec_b200 as K
     torch.manual_seed(11)
     rng = np.random.RandomState(11)
@@ -297,6 +308,81 @@ def test_oracle_ktup_gumbel_l1():
     qu = rng.randint(0, U, 4)
     nev = rng.rand(4, I, R).astype(np.float32)
     close(m.evaluateRec(lt(qu), gumbel_u=torch.from_numpy(nev)), O.ktup_rec_eval(*T, qu, True, nev), rtol=5e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("d,P,gumbel,l1,ktup", [(100, 20, False, False, False), (100, 20, True, True, False),
+                                                 (100, 20, False, False, True), (64, 13, False, True, True),
+                                                 (128, 32, True, False, True), (16, 8, False, False, False)])
+def test_rec_tile_engine_large(d, P, gumbel, l1, ktup):
+    """Batches large enough for the tile engine's own size rule (ragged last tile, several tiles
+    per CTA): flat forward / backward and the fused ranking loss against the oracle."""
+    import kgrec_b200 as K
+    torch.manual_seed(d + P)
+    rng = np.random.RandomState(d * P)
+    U, I, E = 3000, 2500, 4000
+    if ktup:
+        aligned = rng.rand(I) < 0.7
+        ents = rng.permutation(E)[:I]
+        i_map = {i: i for i in range(I)}
+        new_map = {i: ((int(ents[i]) if aligned[i] else -1), i) for i in range(I)}
+        m = K.jTransUPModel(l1, d, U, I, E, P, i_map, new_map, False, gumbel)
+        W = np_tables(m)
+        T = (W["user"], W["item"], W["ent"], W["rel"], W["norm"], W["pref"], W["pref_norm"],
+             m.item2ent.cpu().numpy().astype(np.int64))
+        fscore, fgrads = O.ktup_rec_score, O.ktup_rec_grads
+        call = lambda u, i, nz: m((lt(u), lt(i)), None, is_rec=True, gumbel_u=nz)
+    else:
+        m = K.TransUPModel(l1, d, U, I, P, gumbel)
+        W = np_tables(m)
+        T = (W["user"], W["item"], W["pref"], W["pref_norm"])
+        fscore, fgrads = O.tup_score, O.tup_grads
+        call = lambda u, i, nz: m(lt(u), lt(i), gumbel_u=nz)
+
+    def check_grads(want, scale):
+        got = grads_by_name(m)
+        for k in want:
+            w = np.asarray(want[k], np.float64)
+            close(got[k + "_embeddings"], w, rtol=2e-3, atol=2e-4 * max(1.0, scale * float(np.abs(w).max())))
+
+    # flat calls (the unchanged drivers' shape, one big batch)
+    B = 21013
+    u, i = rng.randint(0, U, B), rng.randint(0, I, B)
+    noise = rng.rand(B, P).astype(np.float32) if gumbel else None
+    tn = torch.from_numpy(noise) if gumbel else None
+    close(call(u, i, tn), fscore(*T, u, i, l1, noise), rtol=2e-4)
+    gup = (rng.randn(B) / 8).astype(np.float32)
+    want = fgrads(*T, u, i, l1, gup, noise)
+    for gm in ("dense", "sparse"):
+        m.grad_mode = gm
+        m.zero_grad()
+        call(u, i, tn).backward(torch.from_numpy(gup).cuda())
+        check_grads(want, 1.0)
+
+    # fused ranking loss: n_pos positives x K negatives, BPR mean per batch of 1024
+    n_pos, Kn, target, bp = 7001, 2, -1.0, 1024
+    u, pi = rng.randint(0, U, n_pos), rng.randint(0, I, n_pos)
+    un, ni = np.repeat(u, Kn), rng.randint(0, I, n_pos * Kn)
+    noise = rng.rand(n_pos * (1 + Kn), P).astype(np.float32) if gumbel else None
+    tn = torch.from_numpy(noise) if gumbel else None
+    sp = fscore(*T, u, pi, l1, None if noise is None else noise[:n_pos])
+    sn = fscore(*T, un, ni, l1, None if noise is None else noise[n_pos:])
+    m.grad_mode = "sparse"
+    m.zero_grad()
+    fl, fp, fn = m.rank_loss((lt(u), lt(pi)), (lt(un), lt(ni)), target=target, batch_pos=bp, gumbel_u=tn)
+    close(fp, sp, rtol=2e-4)
+    close(fn, sn, rtol=2e-4)
+    spr = np.repeat(sp, Kn)
+    nb = (n_pos + bp - 1) // bp
+    want_l = [O.bpr_loss(spr[b * bp * Kn:(b + 1) * bp * Kn], sn[b * bp * Kn:(b + 1) * bp * Kn], target) for b in range(nb)]
+    close(fl, np.asarray(want_l), rtol=2e-4)
+    fl.sum().backward()
+    gp_all, gn_all = np.zeros(n_pos * Kn, np.float32), np.zeros(n_pos * Kn, np.float32)
+    for b in range(nb):
+        sl = slice(b * bp * Kn, (b + 1) * bp * Kn)
+        gp_all[sl], gn_all[sl] = O.bpr_loss_grads(spr[sl], sn[sl], target)
+    g_all = np.concatenate([gp_all.reshape(n_pos, Kn).sum(1), gn_all]).astype(np.float32)
+    want = fgrads(*T, np.concatenate([u, un]), np.concatenate([pi, ni]), l1, g_all, noise)
+    check_grads(want, 1.0)
 
 
 # ------------------------------------------------------------------------------------------
