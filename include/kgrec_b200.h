@@ -165,6 +165,23 @@ int kgrec_rank_loss_bwd(const kgrec_tables* tables, int model,
                         const float* pos_scores, const float* neg_scores, float grad_loss,
                         const float* grad_loss_dev, const kgrec_grads* grads, kgrec_stream_t stream);
 
+/* kgrec_rank_loss_fwd + kgrec_rank_loss_bwd(grad_loss) as ONE call: scores, per-batch losses
+ * and the row gradients of grad_loss * sum_b loss[b] -- what a training step of
+ * item_recommendation.py:165-181 / knowledgable_recommendation.py needs from the model.
+ * TUP / KTUP pairs are scored, differentiated and reduced in a single kernel pass when a
+ * positive and its negatives fit one warp's rows (n_neg <= 15, embedding_size <= 128,
+ * preference_total <= 32); other shapes and models run the two kernels back to back.
+ * Gradient slots as in kgrec_rank_loss_bwd. */
+int kgrec_rank_loss_step(const kgrec_tables* tables, int model,
+                         const void* pa, const void* pb, const void* pc,
+                         const void* na, const void* nb, const void* nc,
+                         int idx_bytes, int64_t n_pos, int32_t n_neg, int64_t batch_pos,
+                         int loss_kind, float margin_or_target, float grad_loss,
+                         const float* gumbel_u, uint64_t seed,
+                         float* pos_scores, float* neg_scores, float* loss,
+                         const kgrec_grads* grads, void* workspace, int32_t* status,
+                         kgrec_stream_t stream);
+
 /* The same fused ranking loss in the group-compact negative format (TransE / TransH and the
  * KTUP KG branch).  The reference draws a negative by corrupting the head OR the tail of its
  * positive (utils/data.py:12-56), so negative k of positive j is one int32:

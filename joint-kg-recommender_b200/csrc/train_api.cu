@@ -182,3 +182,41 @@ extern "C" int kgrec_rank_loss_bwd(const kgrec_tables* tables, int model, const 
   return KGREC_BY_FAMILY(pl.fam, launch_score_bwd)(*tables, pl, I, n_pos * (1 + static_cast<int64_t>(n_neg)), L,
                                                    gumbel_u, seed, B, *grads, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int kgrec_rank_loss_step(const kgrec_tables* tables, int model, const void* pa, const void* pb,
+                                    const void* pc, const void* na, const void* nb, const void* nc, int idx_bytes,
+                                    int64_t n_pos, int32_t n_neg, int64_t batch_pos, int loss_kind,
+                                    float margin_or_target, float grad_loss, const float* gumbel_u, uint64_t seed,
+                                    float* pos_scores, float* neg_scores, float* loss, const kgrec_grads* grads,
+                                    void* workspace, int32_t* status, kgrec_stream_t stream) {
+  Plan pl;
+  int rc = make_plan(tables, model, &pl);
+  if (rc) return rc;
+  if ((rc = check_bwd_plan(tables, pl)) || (rc = check_idx(pa, pb, pc, pl.fam, idx_bytes)) ||
+      (rc = check_idx(na, nb, nc, pl.fam, idx_bytes)) || (rc = check_grads(pl, grads)))
+    return rc;
+  if ((rc = check_loss(loss_kind, n_pos, n_neg, batch_pos))) return rc;
+  if (!pos_scores || !neg_scores || !loss || !workspace) { set_error("output / workspace pointer is NULL"); return KGREC_ERR_INVALID; }
+  if (n_pos == 0) return KGREC_OK;
+  const IdxArgs I{pa, pb, pc, na, nb, nc, idx_bytes == 8};
+  const LossCfg L{loss_kind, margin_or_target, n_neg, n_pos, batch_pos};
+  float* group_loss = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
+  rc = -1;
+  if (pl.fam == FAM_REC)
+    rc = rec_tile_loss_step(*tables, pl, I, L, grad_loss, gumbel_u, seed, pos_scores, neg_scores, group_loss, *grads, status, st);
+  if (rc > 0) return rc;
+  if (rc < 0) {   // shapes the single-pass kernel is not built for: forward, then backward from the saved scores
+    rc = KGREC_BY_FAMILY(pl.fam, launch_rank_loss_fwd)(*tables, pl, I, L, gumbel_u, seed, pos_scores, neg_scores,
+                                                       group_loss, status, st);
+    if (rc) return rc;
+    const BwdArgs B{nullptr, pos_scores, neg_scores, grad_loss, nullptr};
+    rc = KGREC_BY_FAMILY(pl.fam, launch_score_bwd)(*tables, pl, I, n_pos * (1 + static_cast<int64_t>(n_neg)), L,
+                                                   gumbel_u, seed, B, *grads, st);
+    if (rc) return rc;
+  }
+  k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(group_loss, L, loss);
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}

@@ -724,6 +724,9 @@ int rec_tile_rank_loss_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs&
                            float* group_loss, int32_t* status, cudaStream_t st);
 int rec_tile_score_bwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n, const LossCfg& L,
                        const float* gumbel_u, uint64_t seed, const BwdArgs& B, const kgrec_grads& G, cudaStream_t st);
+int rec_tile_loss_step(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, const LossCfg& L, float grad_loss,
+                       const float* gumbel_u, uint64_t seed, float* pos_scores, float* neg_scores, float* group_loss,
+                       const kgrec_grads& G, int32_t* status, cudaStream_t st);
 
 template <int FAM>
 int launch_score_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n, const float* gumbel_u,

@@ -42,7 +42,13 @@ struct TileArgs {
   kgrec_grads G;
   int lda;                       // shared row stride in floats, lda / 4 odd
   int n_tiles;
+  // single-pass step: a warp's 16 rows hold gw whole groups of gsz = 1 + n_neg pairs (the positive,
+  // then its negatives), so the ranking loss and its gradient are formed between two passes
+  int gsz, gw;
+  float* group_loss;
 };
+
+enum { MODE_FWD = 0, MODE_BWD = 1, MODE_STEP = 2 };
 
 __device__ __forceinline__ float qsum(float v) {   // all-reduce over the 4 slices of a pair
   v += __shfl_xor_sync(FULL, v, 8);
@@ -95,9 +101,11 @@ __device__ __forceinline__ float upstream_one(const BwdArgs& B, const LossCfg& L
 
 template <int PT> struct KSplit { static constexpr int KH = (PT == 20) ? 10 : 8; };   // preferences per pass-F thread
 
-template <int PT, bool GUMBEL, bool BWD>
+template <int PT, bool GUMBEL, int MODE>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A) {
   extern __shared__ __align__(16) float smem[];
+  constexpr bool BWD = MODE != MODE_FWD;
+  constexpr bool STEP = MODE == MODE_STEP;
   constexpr int KH = KSplit<PT>::KH;
   constexpr int KSPLIT = PT / KH;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -152,9 +160,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
 
   // ids of a tile's rows, one per lane: lanes 0-15 hold the user id of row wid*16 + lane, lanes
   // 16-31 the item id of row wid*16 + lane - 16; -1 past the end.  Fetched one tile ahead.
+  // flat pair index (positives first, then negatives) of the warp's local row rl of tile t; -1 = none
+  auto pair_of = [&](int t, int rl) -> int64_t {
+    if (t >= A.n_tiles) return -1;
+    if constexpr (STEP) {
+      const int gl = rl / A.gsz, tt = rl - gl * A.gsz;
+      const int64_t j = (static_cast<int64_t>(t) * nw + wid) * A.gw + gl;
+      if (gl >= A.gw || j >= A.n_pos) return -1;
+      return tt == 0 ? j : A.n_pos + j * (A.gsz - 1) + (tt - 1);
+    } else {
+      const int64_t i = static_cast<int64_t>(t) * M + wid * kPairsPerWarp + rl;
+      return i < A.n ? i : -1;
+    }
+  };
   auto fetch_ids = [&](int t) -> int64_t {
-    const int64_t i = static_cast<int64_t>(t) * M + wid * kPairsPerWarp + (lane & 15);
-    if (t >= A.n_tiles || i >= A.n) return -1;
+    const int64_t i = pair_of(t, lane & 15);
+    if (i < 0) return -1;
     const bool neg = i >= A.n_pos;
     const int64_t li = neg ? i - A.n_pos : i;
     return load_idx(lane < 16 ? (neg ? A.na : A.a) : (neg ? A.nb : A.b), li, A.is64);
@@ -165,15 +186,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
   // Rows wid*16 .. wid*16+15 of the tile belong to this warp from the gather to the flush; only
   // pass F reads other warps' rows (two CTA barriers per tile in the backward, none in the forward).
   for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-    const int64_t base = static_cast<int64_t>(tile) * M;
-    const int valid = static_cast<int>(min(static_cast<int64_t>(M), A.n - base));
+    const int64_t pidx[kMP] = {pair_of(tile, slot), pair_of(tile, 8 + slot)};
 
     // ---- gather: raw rows by cp.async (u -> E, item -> W, aligned entity -> S), all 16 rows of
     // the warp in flight at once, then S = u + i', X = u - i'  (i' = item + entity for KTUP,
     // jTransUP.py:133)
     {
       int64_t id = idv;
-      if constexpr (!BWD) {
+      if constexpr (MODE != MODE_BWD) {
         if (id >= 0) id = checked(id, lane < 16 ? T.n_user : T.n_item, A.status);
       }
       int64_t ia = 0;
@@ -181,8 +201,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
       const int rl = wid * kPairsPerWarp + (lane & 15);
       if (lane < 16) sid[rl] = static_cast<int>(id);
       else { sid[M + rl] = static_cast<int>(id); sid[2 * M + rl] = static_cast<int>(ia); }
-      if constexpr (BWD) {
-        if (lane < 16) sg[rl] = id >= 0 ? upstream_one(A.B, A.L, base + rl) : 0.f;
+      if constexpr (MODE == MODE_BWD) {
+        if (lane < 16) sg[rl] = id >= 0 ? upstream_one(A.B, A.L, pair_of(tile, lane)) : 0.f;
       }
 #pragma unroll 4
       for (int j = 0; j < kPairsPerWarp; ++j) {
@@ -243,13 +263,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
     if constexpr (GUMBEL) {
 #pragma unroll
       for (int a = 0; a < kMP; ++a) {
-        const int64_t pid = base + mloc[a];
+        const int64_t pid = pidx[a];
         float nz[PT / 4];
 #pragma unroll
         for (int j = 0; j < PT / 4; ++j) {
           const int k = 4 * j + q;
           nz[j] = 0.f;
-          if (k < P && pid < A.n)
+          if (k < P && pid >= 0)
             nz[j] = A.gumbel_u ? gumbel_from_uniform(__ldg(A.gumbel_u + pid * P + k))
                                : gumbel_fast(philox_uniform_bits(A.seed, static_cast<uint64_t>(pid), static_cast<uint32_t>(k)));
         }
@@ -307,36 +327,69 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
     for (int a = 0; a < kMP; ++a) xw[a] = qsum(xw[a]);
 
     // ---- pass C: e = (x + r) - xw w; score = L(e); eps = g dL/de   (own chunks only: no sync)
-    float ew[kMP] = {0.f, 0.f}, sc[kMP] = {0.f, 0.f}, g[kMP] = {0.f, 0.f};
-    if constexpr (BWD) {
+    float ew[kMP] = {0.f, 0.f}, g[kMP] = {0.f, 0.f};
+    if constexpr (MODE != MODE_BWD) {
+      float sc[kMP] = {0.f, 0.f};
+      for (int c = q; c < NC; c += 4) {
+#pragma unroll
+        for (int a = 0; a < kMP; ++a) {
+          const float4 xr = E[mloc[a] * lda4 + c], w4 = W[mloc[a] * lda4 + c];
+          sc[a] += dist_term(fmaf(-xw[a], w4.x, xr.x), l1) + dist_term(fmaf(-xw[a], w4.y, xr.y), l1) +
+                   dist_term(fmaf(-xw[a], w4.z, xr.z), l1) + dist_term(fmaf(-xw[a], w4.w, xr.w), l1);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < kMP; ++a) {
+        sc[a] = qsum(sc[a]);
+        const int64_t i = pidx[a];
+        if (q == 0 && i >= 0) {
+          if (i < A.n_pos) A.scores_a[i] = sc[a];
+          else A.scores_b[i - A.n_pos] = sc[a];
+        }
+        if constexpr (STEP) {
+          if (q == 0) sg[mloc[a]] = sc[a];
+        }
+      }
+      if constexpr (STEP) {
+        // ranking loss of the group and its derivative (utils/loss.py:8-16,29-31), scores in sg
+        __syncwarp();
+        const int K = A.gsz - 1;
+#pragma unroll
+        for (int a = 0; a < kMP; ++a) {
+          const int rl = mloc[a] - wid * kPairsPerWarp, gl = rl / A.gsz, tt = rl - gl * A.gsz;
+          const int64_t i = pidx[a];
+          if (i >= 0) {
+            const int64_t j = i < A.n_pos ? i : (i - A.n_pos) / K;
+            const float* gs = sg + wid * kPairsPerWarp + gl * A.gsz;    // [pos, neg_1 .. neg_K]
+            const float up = A.B.grad_loss * loss_batch_scale(A.L, j);
+            if (tt == 0) {
+              float c = 0.f, lsum = 0.f;
+              for (int k = 1; k <= K; ++k) { c += loss_dpos(A.L, gs[0], gs[k]); lsum += loss_term(A.L, gs[0], gs[k]); }
+              g[a] = c * up;
+              if (q == 0) A.group_loss[j] = lsum;
+            } else {
+              g[a] = -loss_dpos(A.L, gs[0], gs[tt]) * up;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    if constexpr (MODE == MODE_BWD) {
 #pragma unroll
       for (int a = 0; a < kMP; ++a) g[a] = sg[mloc[a]];
     }
-    for (int c = q; c < NC; c += 4) {
+    if constexpr (BWD) {
+      for (int c = q; c < NC; c += 4) {
 #pragma unroll
-      for (int a = 0; a < kMP; ++a) {
-        const float4 xr = E[mloc[a] * lda4 + c], w4 = W[mloc[a] * lda4 + c];
-        const float4 e = make_float4(fmaf(-xw[a], w4.x, xr.x), fmaf(-xw[a], w4.y, xr.y), fmaf(-xw[a], w4.z, xr.z), fmaf(-xw[a], w4.w, xr.w));
-        if constexpr (BWD) {
+        for (int a = 0; a < kMP; ++a) {
+          const float4 xr = E[mloc[a] * lda4 + c], w4 = W[mloc[a] * lda4 + c];
+          const float4 e = make_float4(fmaf(-xw[a], w4.x, xr.x), fmaf(-xw[a], w4.y, xr.y), fmaf(-xw[a], w4.z, xr.z), fmaf(-xw[a], w4.w, xr.w));
           const float4 eps = make_float4(g[a] * ddist_term(e.x, l1), g[a] * ddist_term(e.y, l1), g[a] * ddist_term(e.z, l1), g[a] * ddist_term(e.w, l1));
           ew[a] = dot4acc(eps, w4, ew[a]);
           E[mloc[a] * lda4 + c] = eps;
-        } else {
-          sc[a] += dist_term(e.x, l1) + dist_term(e.y, l1) + dist_term(e.z, l1) + dist_term(e.w, l1);
         }
       }
-    }
-    if constexpr (!BWD) {
-#pragma unroll
-      for (int a = 0; a < kMP; ++a) {
-        const float s = qsum(sc[a]);
-        const int64_t i = base + mloc[a];
-        if (q == 0 && i < A.n) {
-          if (i < A.n_pos) A.scores_a[i] = s;
-          else A.scores_b[i - A.n_pos] = s;
-        }
-      }
-    } else {
 #pragma unroll
       for (int a = 0; a < kMP; ++a) ew[a] = qsum(ew[a]);
 
@@ -408,7 +461,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
       // ---- pass F: g_pref[k] += cA[k] eps + cB[k] s ; g_pref_norm[k] += cA[k] gw  over the tile's pairs
       if (grp < ngrp) {
 #pragma unroll 2
-        for (int m = grp; m < valid; m += ngrp) {
+        for (int m = grp; m < M; m += ngrp) {   // rows without a pair hold zeros
           const float4 e4 = E[m * lda4 + jc], s4 = S[m * lda4 + jc], g4 = W[m * lda4 + jc];
           const float2* ca = reinterpret_cast<const float2*>(coef + m * 2 * PT + kh * KH);
           const float2* cb = reinterpret_cast<const float2*>(coef + m * 2 * PT + PT + kh * KH);
@@ -457,10 +510,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
       // ---- flush the row gradients: whole rows, the warp's own 16
       for (int j = 0; j < kPairsPerWarp; ++j) {
         const int r = wid * kPairsPerWarp + j;
-        if (r >= valid || lane >= NC) continue;
+        const int64_t i = pair_of(tile, j);
+        if (i < 0 || lane >= NC) continue;
         const float4 gu = S[r * lda4 + lane];
         float4 gi = E[r * lda4 + lane];
-        const int64_t i = base + r;
         const int ia = sid[2 * M + r];
         const bool pad = A.ktup && ia == T.n_ent - 1;     // padding row: no gradient (jTransUP.py:96)
         if (A.G.mode == 0) {
@@ -520,7 +573,8 @@ struct TilePlan {
 // KGREC_REC_TILE=0 keeps every call on the one-warp-per-pair kernels, =force sends every
 // supported shape through the tiles whatever n is (the parity tests run both engines on the
 // reference's golden vectors); default: by size.
-bool plan_tiles(const kgrec_tables& T, const Plan& pl, int64_t n, TilePlan* tp) {
+// n work units (pairs, or whole groups in step mode), upw of them per warp
+bool plan_tiles(const kgrec_tables& T, const Plan& pl, int64_t n, int upw, TilePlan* tp) {
   const int d = T.dim, P = T.n_pref;
   if (!pl.vec || d > 128 || P > 32 || n < 1) return false;
   const char* env = getenv("KGREC_REC_TILE");
@@ -537,9 +591,9 @@ bool plan_tiles(const kgrec_tables& T, const Plan& pl, int64_t n, TilePlan* tp) 
   const int nw_min = (nc * ksplit + 31) / 32 > 2 ? (nc * ksplit + 31) / 32 : 2;
   const int sms = sm_count();
   // smaller tiles while they still give every SM one; below that the one-warp-per-pair kernels win
-  while (nw > nw_min && (n + nw * kPairsPerWarp - 1) / (nw * kPairsPerWarp) < sms) --nw;
+  while (nw > nw_min && (n + nw * upw - 1) / (nw * upw) < sms) --nw;
   if (nw < nw_min) return false;
-  const int64_t tiles = (n + nw * kPairsPerWarp - 1) / (nw * kPairsPerWarp);
+  const int64_t tiles = (n + nw * upw - 1) / (nw * upw);
   if ((tiles < sms && !force) || tiles > 0x7fffffff) return false;
   tp->nw = nw;
   tp->n_tiles = static_cast<int>(tiles);
@@ -548,12 +602,12 @@ bool plan_tiles(const kgrec_tables& T, const Plan& pl, int64_t n, TilePlan* tp) 
   return true;
 }
 
-template <bool BWD>
+template <int MODE>
 int launch_tiles(const TileArgs& A, const TilePlan& tp, cudaStream_t st) {
   int rc = KGREC_OK;
 #define KGREC_TILE(PTV, GUM)                                                             \
   {                                                                                      \
-    auto kern = k_rec_tile<PTV, GUM, BWD>;                                               \
+    auto kern = k_rec_tile<PTV, GUM, MODE>;                                              \
     if ((rc = set_smem(kern, tp.smem))) return rc;                                       \
     kern<<<tp.grid, tp.nw * 32, tp.smem, st>>>(A);                                       \
   }
@@ -572,12 +626,12 @@ int launch_tiles(const TileArgs& A, const TilePlan& tp, cudaStream_t st) {
 int rec_tile_score_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n, const float* gumbel_u,
                        uint64_t seed, float* scores, int32_t* status, cudaStream_t st) {
   TilePlan tp;
-  if (!plan_tiles(T, pl, n, &tp)) return -1;
+  if (!plan_tiles(T, pl, n, kPairsPerWarp, &tp)) return -1;
   TileArgs A{};
   A.T = T; A.ktup = pl.ktup; A.a = I.a; A.b = I.b; A.na = nullptr; A.nb = nullptr; A.is64 = I.is64;
   A.n = n; A.n_pos = n; A.gumbel_u = gumbel_u; A.seed = seed; A.scores_a = scores; A.scores_b = nullptr;
   A.status = status; A.lda = tp.lda; A.n_tiles = tp.n_tiles;
-  return launch_tiles<false>(A, tp, st);
+  return launch_tiles<MODE_FWD>(A, tp, st);
 }
 
 int rec_tile_rank_loss_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, const LossCfg& L,
@@ -585,12 +639,12 @@ int rec_tile_rank_loss_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs&
                            float* group_loss, int32_t* status, cudaStream_t st) {
   TilePlan tp;
   const int64_t n = L.n_pos * (1 + static_cast<int64_t>(L.n_neg));
-  if (!plan_tiles(T, pl, n, &tp)) return -1;
+  if (!plan_tiles(T, pl, n, kPairsPerWarp, &tp)) return -1;
   TileArgs A{};
   A.T = T; A.ktup = pl.ktup; A.a = I.a; A.b = I.b; A.na = I.na; A.nb = I.nb; A.is64 = I.is64;
   A.n = n; A.n_pos = L.n_pos; A.gumbel_u = gumbel_u; A.seed = seed; A.scores_a = pos_scores; A.scores_b = neg_scores;
   A.status = status; A.lda = tp.lda; A.n_tiles = tp.n_tiles;
-  const int rc = launch_tiles<false>(A, tp, st);
+  const int rc = launch_tiles<MODE_FWD>(A, tp, st);
   if (rc) return rc;
   k_group_loss<<<static_cast<unsigned>((L.n_pos + 255) / 256), 256, 0, st>>>(pos_scores, neg_scores, L, group_loss);
   KGREC_CUDA_OK(cudaGetLastError());
@@ -600,13 +654,30 @@ int rec_tile_rank_loss_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs&
 int rec_tile_score_bwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n, const LossCfg& L,
                        const float* gumbel_u, uint64_t seed, const BwdArgs& B, const kgrec_grads& G, cudaStream_t st) {
   TilePlan tp;
-  if (!plan_tiles(T, pl, n, &tp)) return -1;
+  if (!plan_tiles(T, pl, n, kPairsPerWarp, &tp)) return -1;
   const bool fused = B.pos_scores != nullptr;
   TileArgs A{};
   A.T = T; A.ktup = pl.ktup; A.a = I.a; A.b = I.b; A.na = I.na; A.nb = I.nb; A.is64 = I.is64;
   A.n = n; A.n_pos = fused ? L.n_pos : n; A.gumbel_u = gumbel_u; A.seed = seed;
   A.L = L; A.B = B; A.G = G; A.lda = tp.lda; A.n_tiles = tp.n_tiles;
-  return launch_tiles<true>(A, tp, st);
+  return launch_tiles<MODE_BWD>(A, tp, st);
+}
+
+// forward + ranking loss + backward in one pass over groups of (positive, its negatives)
+int rec_tile_loss_step(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, const LossCfg& L, float grad_loss,
+                       const float* gumbel_u, uint64_t seed, float* pos_scores, float* neg_scores, float* group_loss,
+                       const kgrec_grads& G, int32_t* status, cudaStream_t st) {
+  if (L.n_neg > kPairsPerWarp - 1) return -1;
+  const int gsz = 1 + L.n_neg, gw = kPairsPerWarp / gsz;
+  TilePlan tp;
+  if (!plan_tiles(T, pl, L.n_pos, gw, &tp)) return -1;
+  TileArgs A{};
+  A.T = T; A.ktup = pl.ktup; A.a = I.a; A.b = I.b; A.na = I.na; A.nb = I.nb; A.is64 = I.is64;
+  A.n = L.n_pos * static_cast<int64_t>(gsz); A.n_pos = L.n_pos; A.gumbel_u = gumbel_u; A.seed = seed;
+  A.scores_a = pos_scores; A.scores_b = neg_scores; A.status = status;
+  A.L = L; A.B = BwdArgs{nullptr, nullptr, nullptr, grad_loss, nullptr}; A.G = G;
+  A.lda = tp.lda; A.n_tiles = tp.n_tiles; A.gsz = gsz; A.gw = gw; A.group_loss = group_loss;
+  return launch_tiles<MODE_STEP>(A, tp, st);
 }
 
 }  // namespace kgrec

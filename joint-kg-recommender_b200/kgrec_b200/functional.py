@@ -383,3 +383,38 @@ def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, p
             grads[name] = torch.sparse_coo_tensor(idx, bufs[name], size=tuple(weights[name].shape),
                                                   check_invariants=False)
     return loss, pos_s, neg_s, grads
+
+
+def rank_loss_step(cfg, weights, pos, neg, n_neg, batch_pos, loss_kind, param, gumbel_u, status, grad_loss=1.0):
+    """kgrec_rank_loss_step: scores, per-batch losses and the gradients of grad_loss * sum(loss) of the
+    fused positive + K-negative ranking loss in one call (one kernel pass for TUP / KTUP pairs).
+    Returns (loss, pos_scores, neg_scores, {table: grad})."""
+    names = MODEL_TABLES[cfg.model]
+    T = make_tables(weights, cfg.dim, cfg.l1, cfg.use_gumbel, cfg.item2ent)
+    pa, pb, pc = pos
+    na, nb, nc = neg
+    n_pos = pa.numel()
+    n = n_pos * (1 + n_neg)
+    dev = pa.device
+    pos_s = torch.empty(n_pos, dtype=torch.float32, device=dev)
+    neg_s = torch.empty(n_pos * n_neg, dtype=torch.float32, device=dev)
+    loss = torch.empty((n_pos + batch_pos - 1) // batch_pos, dtype=torch.float32, device=dev)
+    ws = torch.empty(max(1, n_pos), dtype=torch.float32, device=dev)
+    G, bufs = _alloc_grads(cfg.model, weights, n, cfg.grad_mode, cfg.dim)
+    lib = _lib.load()
+    _lib.check(lib.kgrec_rank_loss_step(
+        C.byref(T), cfg.model, _ptr(pa), _ptr(pb), _ptr(pc), _ptr(na), _ptr(nb), _ptr(nc),
+        _idx_bytes(pa, pb, pc, na, nb, nc), n_pos, n_neg, batch_pos, loss_kind, float(param), float(grad_loss),
+        _ptr(gumbel_u), cfg.seed, _ptr(pos_s), _ptr(neg_s), _ptr(loss), C.byref(G), _ptr(ws), _ptr(status), _stream()))
+    count_launches(2)
+    idx = {}
+    if cfg.grad_mode != "dense":
+        pi = _slot_indices(cfg.model, pa, pb, pc, cfg.item2ent)
+        ni = _slot_indices(cfg.model, na, nb, nc, cfg.item2ent)
+        for k in pi:
+            if k == "ent" and cfg.model != _lib.KTUP:
+                idx[k] = torch.cat([pa, na, pb, nb]).long()
+            else:
+                idx[k] = torch.cat([pi[k], ni[k]])
+    grads = _finish_grads(cfg.model, weights, bufs, idx, cfg.grad_mode, {k: True for k in names})
+    return loss, pos_s, neg_s, grads

@@ -170,6 +170,30 @@ class KGRecModule(nn.Module):
                 p.grad = grads[k] if p.grad is None else p.grad + grads[k]
         return out, ps, ns
 
+    def _loss_step(self, model, pos, neg, loss, param, batch_pos=None, gumbel_u=None, grad_loss=1.0):
+        """Forward + ranking loss + backward in one call; leaves the gradients in .grad."""
+        dev = self._require_cuda()
+        pos = tuple(KF.as_index(x, dev) if x is not None else None for x in pos)
+        neg = tuple(KF.as_index(x, dev) if x is not None else None for x in neg)
+        n_pos = pos[0].numel()
+        if n_pos == 0 or neg[0].numel() % n_pos:
+            raise ValueError("negatives must be a whole multiple of the positives")
+        kind = {"margin": _lib.LOSS_MARGIN, "bpr": _lib.LOSS_BPR}[loss]
+        if gumbel_u is not None:
+            gumbel_u = gumbel_u.to(dev, torch.float32).contiguous()
+        seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
+        names = KF.MODEL_TABLES[model]
+        w = self._weights()
+        out, ps, ns, grads = KF.rank_loss_step(self._cfg(model, seed), {k: w[k] for k in names}, pos, neg,
+                                               neg[0].numel() // n_pos, batch_pos or n_pos, kind, param, gumbel_u,
+                                               self._status_buf(dev), grad_loss)
+        for k in names:
+            p = w[k]
+            if p.requires_grad and grads[k] is not None:
+                g = grads[k].clone() if (model == _lib.KTUP and k in ("rel", "norm")) else grads[k]   # shared buffer
+                p.grad = g if p.grad is None else p.grad + g
+        return out, ps, ns
+
     # -- evaluation helpers ------------------------------------------------------
     def _eval(self, model, side, q, r, mode, **kw):
         dev = self._require_cuda()

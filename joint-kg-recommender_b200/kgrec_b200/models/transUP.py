@@ -71,6 +71,12 @@ class RecModelBase(KGRecModule):
         neg = (neg[0], neg[1], None)
         return self._rank_loss(self.MODEL, pos, neg, loss, target, batch_pos, gumbel_u)
 
+    def loss_step(self, pos, neg, target=-1.0, loss="bpr", batch_pos=None, gumbel_u=None):
+        """rank_loss(...) followed by loss.sum().backward(), as one kernel pass: returns
+        (loss[batches], pos_scores, neg_scores) and leaves the gradients in .grad."""
+        return self._loss_step(self.MODEL, (pos[0], pos[1], None), (neg[0], neg[1], None), loss, target, batch_pos,
+                               gumbel_u)
+
     def _mix_tables(self):
         """(P, N, half): the preference tables the mixing uses."""
         return self.pref_embeddings.weight, self.pref_norm_embeddings.weight, 1.0

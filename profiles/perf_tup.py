@@ -25,13 +25,16 @@ for name in ("tup_soft", "tup_gumbel", "ktup_soft", "ktup_gumbel"):
         m = K.jTransUPModel(False, 100, 50_000, I, E, 20, {i: i for i in range(I)}, new_map, False, gum)
     m.grad_mode = "sparse"
     u, i, ni = (torch.randint(0, 50_000, (n_pos,), generator=g, dtype=torch.int32).to(dev) for _ in range(3))
-    for eng in ("tile", "warp"):
+    for eng in ("step", "tile", "warp"):
         if eng == "warp":
             os.environ["KGREC_REC_TILE"] = "0"
         else:
             os.environ.pop("KGREC_REC_TILE", None)
         def step():
             m.zero_grad(set_to_none=True)
+            if eng == "step":
+                m.loss_step((u, i), (u, ni), target=-1.0, batch_pos=1024)
+                return
             l, _, _ = m.rank_loss((u, i), (u, ni), target=-1.0, batch_pos=1024)
             l.sum().backward()
         for _ in range(3):

@@ -384,6 +384,57 @@ def test_rec_tile_engine_large(d, P, gumbel, l1, ktup):
     want = fgrads(*T, np.concatenate([u, un]), np.concatenate([pi, ni]), l1, g_all, noise)
     check_grads(want, 1.0)
 
+    # the same step as ONE kernel pass (kgrec_rank_loss_step): forward + loss + backward
+    two_pass = {k: v.clone() for k, v in grads_by_name(m).items()}
+    for gm in ("sparse", "dense"):
+        m.grad_mode = gm
+        m.zero_grad()
+        sl, sp1, sn1 = m.loss_step((lt(u), lt(pi)), (lt(un), lt(ni)), target=target, batch_pos=bp, gumbel_u=tn)
+        assert torch.allclose(sp1, fp, rtol=1e-6, atol=1e-6) and torch.allclose(sn1, fn, rtol=1e-6, atol=1e-6)
+        assert torch.allclose(sl, fl, rtol=1e-5, atol=1e-6)
+        check_grads(want, 1.0)
+        got = grads_by_name(m)
+        for k in two_pass:
+            assert torch.allclose(got[k], two_pass[k], rtol=2e-3, atol=1e-4 * max(1.0, float(two_pass[k].abs().max())))
+
+
+def test_rank_loss_step_other_shapes():
+    """kgrec_rank_loss_step outside the single-pass kernel's shapes (KG model; many negatives) falls
+    back to forward + backward kernels behind the same call."""
+    import kgrec_b200 as K
+    from kgrec_b200 import functional as KF, _lib
+    torch.manual_seed(5)
+    rng = np.random.RandomState(5)
+    m = K.TransUPModel(False, 64, 500, 400, 11, False)
+    m.grad_mode = "sparse"
+    n_pos, Kn = 5003, 17          # 17 negatives per positive do not fit one warp's rows
+    u, pi = rng.randint(0, 500, n_pos), rng.randint(0, 400, n_pos)
+    un, ni = np.repeat(u, Kn), rng.randint(0, 400, n_pos * Kn)
+    fl, fp, fn = m.rank_loss((lt(u), lt(pi)), (lt(un), lt(ni)), target=-1.0, batch_pos=1000)
+    fl.sum().backward()
+    ref = {k: v.clone() for k, v in grads_by_name(m).items()}
+    m.zero_grad()
+    sl, sp, sn = m.loss_step((lt(u), lt(pi)), (lt(un), lt(ni)), target=-1.0, batch_pos=1000)
+    assert torch.equal(sp, fp) and torch.equal(sn, fn) and torch.allclose(sl, fl)
+    got = grads_by_name(m)
+    for k in ref:
+        assert torch.allclose(got[k], ref[k], rtol=1e-3, atol=1e-5)
+    # KG model through the same C entry point
+    e = K.TransEModel(True, 100, 2000, 13)
+    e.grad_mode = "sparse"
+    B, Kn = 999, 3
+    h, t, r = rng.randint(0, 2000, B), rng.randint(0, 2000, B), rng.randint(0, 13, B)
+    nh, nt, nr = rng.randint(0, 2000, B * Kn), np.repeat(t, Kn), np.repeat(r, Kn)
+    fl, fp, fn = e.rank_loss((lt(h), lt(t), lt(r)), (lt(nh), lt(nt), lt(nr)), margin=1.0, batch_pos=100)
+    fl.sum().backward()
+    ref = {k: v.clone() for k, v in grads_by_name(e).items()}
+    e.zero_grad()
+    sl, sp, sn = e._loss_step(_lib.TRANSE, (lt(h), lt(t), lt(r)), (lt(nh), lt(nt), lt(nr)), "margin", 1.0, 100)
+    assert torch.equal(sp, fp) and torch.equal(sn, fn) and torch.allclose(sl, fl)
+    got = grads_by_name(e)
+    for k in ref:
+        assert torch.allclose(got[k], ref[k], rtol=1e-4, atol=1e-6)
+
 
 # ------------------------------------------------------------------------------------------
 # evaluation: full matrix vs oracle, top-K / rank vs the oracle's ranking walk
