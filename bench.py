@@ -432,6 +432,43 @@ def run_ours(args):
                   "unit": "pairs/s", "ms": rms, "users": args.eval_queries, "items": 50_000, "n_gpus": 1,
                   "note": "augmented item rows built once (soft_catalog), user rows per call"}
         del rmodel, soft_cat
+    # ---- rec-side training step (BASELINE configs[2] / [3] shapes): 256 batches x (1024 positives + 1 negative
+    # each), forward + BPR loss + backward in one pass of the tile kernel (kgrec_rank_loss_step), this rank only
+    tr_rec = None
+    if not args.no_eval and rank == 0:
+        import numpy as np
+        tr_rec = {}
+        n_pos = 256 * BATCH
+        fp32_fma_per_s = 148 * 128 * 1.965e9
+        for name, gum, fma in (("tup_st_gumbel", True, 14000), ("ktup_soft", False, 18000)):
+            torch.manual_seed(13)
+            if name.startswith("tup"):
+                tm = K.TransUPModel(False, D, 50_000, 50_000, 20, gum)
+            else:
+                n_item, n_ent = 50_000, 500_000
+                ents = np.random.RandomState(0).permutation(n_ent)[:n_item]
+                new_map = {i: (int(ents[i]) if i % 10 < 7 else -1, i) for i in range(n_item)}
+                tm = K.jTransUPModel(False, D, 50_000, n_item, n_ent, 20, {i: i for i in range(n_item)}, new_map, False, gum)
+            tm.grad_mode = "sparse"
+            tg = torch.Generator().manual_seed(5)
+            tu, ti, tn = (torch.randint(0, 50_000, (n_pos,), generator=tg, dtype=torch.int32).to(dev) for _ in range(3))
+            for _ in range(3):
+                tm.zero_grad(set_to_none=True)
+                tm.loss_step((tu, ti), (tu, tn), target=-1.0, batch_pos=BATCH)
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(5):
+                tm.zero_grad(set_to_none=True)
+                tm.loss_step((tu, ti), (tu, tn), target=-1.0, batch_pos=BATCH)
+            t1.record()
+            torch.cuda.synchronize()
+            tms = t0.elapsed_time(t1) / 5
+            pps = 2 * n_pos / (tms * 1e-3)
+            tr_rec[name] = {"metric": "scored (user,item) pairs/s, forward + BPR loss + backward, d=100 P=20", "value": pps,
+                            "unit": "pairs/s", "ms": tms, "pairs_per_step": 2 * n_pos, "bound": "fp32 pipe",
+                            "fma_per_pair": fma, "frac_of_fp32_bound": pps * fma / fp32_fma_per_s}
+            del tm
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -487,6 +524,7 @@ def run_ours(args):
                             "with_device_negative_sampling_triples_per_s": n_tri / (loop_ms * 1e-3)},
         "eval": ev,
         "eval_rec": ev_rec,
+        "train_rec": tr_rec,
     }
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg(torch)

@@ -13,6 +13,7 @@
 //
 // Reference arithmetic: transE.py:51-63, transH.py:58-71 (+ utils/misc.py:18-19),
 // utils/loss.py:8-16, 29-31; CPU restatement: oracle/kg_oracle.py.
+#include <cstdlib>
 #include "train_dev.cuh"
 
 namespace kgrec {
@@ -393,6 +394,168 @@ k_group_step(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
   }
 }
 
+// --- TransE, d <= 128: the step kernel again, written for issue slots --------------------------
+// k_group_step above is bound by instruction issue (ncu: 77 % issue-active, 159 warp-instructions per
+// scored triple of which ~30 are the arithmetic).  This version removes the rest:
+//   * the residual is kept as e' = B - x with B = h + r (tail replaced) or t - r (head replaced):
+//     |e'| = |e|, the corrupted row's gradient is -eps' in both cases, and the shared rows collect
+//     eps' in two accumulators (accT / accH) picked by one warp-uniform branch, so no per-element
+//     head/tail select is left:  g_h = accT + eps_p, g_t = accH - eps_p, g_r = accT - accH + eps_p;
+//   * loss kind, gradient layout and norm are template parameters (no constant-bank reloads and
+//     branches on them inside the loop), the tail predicate lane*4 < d is hoisted, row / slot
+//     addresses advance by one IMAD.WIDE each;
+//   * the negative loop is unrolled by two with ping-pong row buffers (no register rotation), and
+//     the ids of the next group are fetched while this one computes.
+template <bool L1, bool DENSE, bool MARGIN, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
+               float* __restrict__ group_loss, const kgrec_grads Gr, int32_t* status) {
+  const kgrec_tables& T = G.T;
+  const LossCfg& L = G.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K = L.n_neg;
+  const int n_pos = static_cast<int>(L.n_pos);
+  const uint32_t n_ent = static_cast<uint32_t>(T.n_ent);
+  const uint32_t ld4 = static_cast<uint32_t>(T.ld) * 4u, d4 = static_cast<uint32_t>(T.dim) * 4u;   // row pitches in bytes
+  const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
+  const uint64_t pol_keep = policy_evict_last(G.keep), pol_stream = policy_evict_first();
+  const bool act = lane * 4 < T.dim;
+  const char* ent_b = reinterpret_cast<const char*>(T.ent) + lane * 16;
+  const char* rel_b = reinterpret_cast<const char*>(T.rel) + lane * 16;
+  char* gent_b = reinterpret_cast<char*>(Gr.ent) + lane * 16;
+  char* grel_b = reinterpret_cast<char*>(Gr.rel) + lane * 16;
+  const float prm = L.param;
+  const int stride = gridDim.x * kWarpsPerCta;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto row = [&](const char* base, uint32_t id) { return reinterpret_cast<const float4*>(base + static_cast<uint64_t>(id) * ld4); };
+  bool bad = false;
+  auto ent_id = [&](int32_t c, bool& head) {        // corrupted-entity id of one int32 of the compact format
+    head = c < 0;
+    uint32_t id = static_cast<uint32_t>(head ? ~c : c);
+    if (id >= n_ent) { bad = true; id = 0; }
+    return id;
+  };
+
+  int j = blockIdx.x * kWarpsPerCta + wid;
+  uint32_t ih = 0, it = 0, ir = 0;
+  int32_t c0 = 0;
+  if (j < n_pos) {
+    ih = group_idx(G.ph, j, G.is64, T.n_ent, status);
+    it = group_idx(G.pt, j, G.is64, T.n_ent, status);
+    ir = group_idx(G.pr, j, G.is64, T.n_rel, status);
+    c0 = __ldg(G.corrupt + static_cast<uint32_t>(j) * K);
+  }
+  for (; j < n_pos; j += stride) {
+    float4 h = z4, t = z4, r = z4, xa = z4, xb = z4;
+    bool heada, headb = false;
+    uint32_t ida = ent_id(c0, heada), idb = 0;
+    if (act) {
+      h = ldg_f4_hint(row(ent_b, ih), pol_keep);
+      t = ldg_f4_hint(row(ent_b, it), pol_keep);
+      r = ldg_f4_hint(row(rel_b, ir), pol_keep);
+      xa = ldg_f4_hint(row(ent_b, ida), pol_keep);
+    }
+    [[maybe_unused]] const uint32_t ih0 = ih, it0 = it, ir0 = ir;
+    const int jn = j + stride;
+    if (jn < n_pos) {   // the next group's ids travel while this group computes
+      ih = group_idx(G.ph, jn, G.is64, T.n_ent, status);
+      it = group_idx(G.pt, jn, G.is64, T.n_ent, status);
+      ir = group_idx(G.pr, jn, G.is64, T.n_rel, status);
+      c0 = __ldg(G.corrupt + static_cast<uint32_t>(jn) * K);
+    }
+    const int32_t* cj = G.corrupt + static_cast<uint32_t>(j) * K;
+    float up = up0;
+    if (!MARGIN) {
+      const int b = j / bp;
+      up /= static_cast<float>(min(bp, n_pos - b * bp)) * static_cast<float>(K);
+    }
+    const float4 bh = make_float4(h.x + r.x, h.y + r.y, h.z + r.z, h.w + r.w);        // h + r
+    const float4 bt = make_float4(t.x - r.x, t.y - r.y, t.z - r.z, t.w - r.w);        // t - r
+    const float4 ep = make_float4(bh.x - t.x, bh.y - t.y, bh.z - t.z, bh.w - t.w);    // (h + r) - t
+    const float sp = warp_sum(dist_term(ep.x, L1) + dist_term(ep.y, L1) + dist_term(ep.z, L1) + dist_term(ep.w, L1));
+    float lsum = 0.f, cpos = 0.f, mys = 0.f;
+    float4 accT = z4, accH = z4;
+    uint32_t goff = (static_cast<uint32_t>(j) * (2 + K) + 2) * d4;      // byte offset of the first corrupted-row slot
+
+    auto negative = [&](const float4& x, const bool head, const uint32_t id, const int k) {
+      const float4 B = head ? bt : bh;
+      const float4 e = make_float4(B.x - x.x, B.y - x.y, B.z - x.z, B.w - x.w);
+      const float sn = warp_sum(dist_term(e.x, L1) + dist_term(e.y, L1) + dist_term(e.z, L1) + dist_term(e.w, L1));
+      if (lane == k) mys = sn;
+      float coef;      // -(dLoss/dsn): the corrupted row's gradient is coef * dL(e')/de'
+      if (MARGIN) {
+        const float tt = sp - sn + prm;
+        lsum += fmaxf(tt, 0.f);
+        coef = tt > 0.f ? up : 0.f;
+        cpos += tt > 0.f ? 1.f : 0.f;
+      } else {
+        const float xx = prm * (sp - sn);
+        lsum += fmaxf(-xx, 0.f) + log1pf(expf(-fabsf(xx)));
+        const float dp = -prm / (1.f + expf(xx));
+        cpos += dp;
+        coef = dp * up;
+      }
+      if (coef != 0.f) {                    // warp-uniform: an inactive hinge has no gradient
+        float4 gc;                          // = -eps'
+        if (L1) {
+          gc = make_float4(coef * ddist_term(e.x, 1), coef * ddist_term(e.y, 1), coef * ddist_term(e.z, 1), coef * ddist_term(e.w, 1));
+        } else {
+          const float c2 = 2.f * coef;
+          gc = make_float4(c2 * e.x, c2 * e.y, c2 * e.z, c2 * e.w);
+        }
+        if (head) { accH.x -= gc.x; accH.y -= gc.y; accH.z -= gc.z; accH.w -= gc.w; }
+        else { accT.x -= gc.x; accT.y -= gc.y; accT.z -= gc.z; accT.w -= gc.w; }
+        if (act) {
+          if (DENSE) red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(id) * d4), gc.x, gc.y, gc.z, gc.w);
+          else stg_f4_hint(reinterpret_cast<float4*>(gent_b + goff), gc.x, gc.y, gc.z, gc.w, pol_stream);
+        }
+      } else if (!DENSE) {
+        if (act) stg_f4_hint(reinterpret_cast<float4*>(gent_b + goff), 0.f, 0.f, 0.f, 0.f, pol_stream);
+      }
+      goff += d4;
+    };
+
+    for (int k = 0; k < K; k += 2) {
+      if (k + 1 < K) {
+        idb = ent_id(__ldg(cj + k + 1), headb);
+        if (act) xb = ldg_f4_hint(row(ent_b, idb), pol_keep);
+      }
+      negative(xa, heada, ida, k);
+      if (k + 1 < K) {
+        if (k + 2 < K) {
+          ida = ent_id(__ldg(cj + k + 2), heada);
+          if (act) xa = ldg_f4_hint(row(ent_b, ida), pol_keep);
+        }
+        negative(xb, headb, idb, k + 1);
+      }
+    }
+    // the positive's own contribution, with the coefficient summed over its negatives
+    const float cp = cpos * up;
+    const float4 eps = make_float4(cp * ddist_term(ep.x, L1), cp * ddist_term(ep.y, L1), cp * ddist_term(ep.z, L1), cp * ddist_term(ep.w, L1));
+    const float4 gh = make_float4(accT.x + eps.x, accT.y + eps.y, accT.z + eps.z, accT.w + eps.w);
+    const float4 gt = make_float4(accH.x - eps.x, accH.y - eps.y, accH.z - eps.z, accH.w - eps.w);
+    const float4 gr = make_float4(accT.x - accH.x + eps.x, accT.y - accH.y + eps.y, accT.z - accH.z + eps.z, accT.w - accH.w + eps.w);
+    if (lane == 0) {
+      pos_scores[j] = sp;
+      group_loss[j] = lsum;
+    }
+    if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
+    if (act) {
+      if (DENSE) {
+        red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(ih0) * d4), gh.x, gh.y, gh.z, gh.w);
+        red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(it0) * d4), gt.x, gt.y, gt.z, gt.w);
+        red_add_f4(reinterpret_cast<float*>(grel_b + static_cast<uint64_t>(ir0) * d4), gr.x, gr.y, gr.z, gr.w);
+      } else {
+        const uint32_t g0 = static_cast<uint32_t>(j) * (2 + K) * d4;
+        stg_f4_hint(reinterpret_cast<float4*>(gent_b + g0), gh.x, gh.y, gh.z, gh.w, pol_stream);
+        stg_f4_hint(reinterpret_cast<float4*>(gent_b + g0 + d4), gt.x, gt.y, gt.z, gt.w, pol_stream);
+        stg_f4_hint(reinterpret_cast<float4*>(grel_b + static_cast<uint32_t>(j) * d4), gr.x, gr.y, gr.z, gr.w, pol_stream);
+      }
+    }
+  }
+  if (bad && status) *status = 1;
+}
+
 int make_plan(const kgrec_tables* T, int model, Plan* pl);
 
 static int group_check(const kgrec_tables* T, int model, Plan* pl, const void* ph, const void* pt, const void* pr,
@@ -495,11 +658,29 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   float* group_loss = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // KGREC_GROUP_STEP=0: the general kernel for every shape (A/B runs, tests); =3: three CTAs per SM
+  const char* env = getenv("KGREC_GROUP_STEP");
+  const bool small32 = n_neg <= 32 && static_cast<double>(n_pos) * (2 + n_neg) * tables->dim * 4 < 4.0e9 &&
+                       static_cast<double>(n_pos) * n_neg < 2.0e9;          // 32-bit slot offsets, scores kept in lanes
+  if (pl.fam == FAM_E && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
+#define CALL_E(L1V, DV, MV)                                                                                      \
+  {                                                                                                              \
+    if (env && env[0] == '3')                                                                                    \
+      k_group_step_e<L1V, DV, MV, 3><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status); \
+    else                                                                                                         \
+      k_group_step_e<L1V, DV, MV, 4><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status); \
+  }
+    const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
+    if (tables->l1) { if (dn) { if (mg) CALL_E(true, true, true) else CALL_E(true, true, false) } else { if (mg) CALL_E(true, false, true) else CALL_E(true, false, false) } }
+    else { if (dn) { if (mg) CALL_E(false, true, true) else CALL_E(false, true, false) } else { if (mg) CALL_E(false, false, true) else CALL_E(false, false, false) } }
+#undef CALL_E
+  } else {
 #define CALL(FAMV, NCHV)                                                                                        \
   if (tables->l1) k_group_step<FAMV, NCHV, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status); \
   else k_group_step<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status);
   KGREC_GROUP_DISPATCH(CALL)
 #undef CALL
+  }
   KGREC_CUDA_OK(cudaGetLastError());
   const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
   k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(group_loss, G.L, loss);

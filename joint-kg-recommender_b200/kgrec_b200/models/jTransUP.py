@@ -93,6 +93,10 @@ class jTransUPModel(RecModelBase):
     def kg_rank_loss_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None):
         return self._rank_loss_corrupt(_lib.TRANSH, pos, corrupt, loss, margin, batch_pos)
 
+    def kg_loss_step_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None, grad_loss=1.0):
+        """KG branch forward + loss + backward in one kernel (the TransH group kernel on ent / rel / norm)."""
+        return self._loss_step_corrupt(_lib.TRANSH, pos, corrupt, loss, margin, batch_pos, grad_loss)
+
     # -- evaluation ----------------------------------------------------------------------------
     def _rec_catalog(self):
         """ie = Item + Ent[item2ent] for every item (jTransUP.py:177-181), built on the device."""

@@ -13,10 +13,12 @@ for r in rows:
     if r[0] == "File Path":
         cur_file = os.path.basename(r[1]); continue
     if r[0] == "Line No":
-        h = r; sm, ei, wv = h.index("# Samples"), h.index("Instructions Executed"), h.index("L1 Wavefronts Shared"); continue
+        h = r; sm, ei = h.index("# Samples"), h.index("Instructions Executed")
+        wv = h.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in h else None
+        continue
     if h and r[0].isdigit():
         try:
-            items.append((cur_file, int(r[0]), r[1].strip()[:100], int(r[sm] or 0), int(r[ei] or 0), int(r[wv] or 0)))
+            items.append((cur_file, int(r[0]), r[1].strip()[:100], int(r[sm] or 0), int(r[ei] or 0), int(r[wv] or 0) if wv is not None else 0))
         except ValueError:
             pass
 ts, tn, tw = (sum(x[i] for x in items) or 1 for i in (3, 4, 5))
