@@ -208,14 +208,18 @@ int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model,
  * losses and the row gradients of grad_loss * sum_b loss[b] (every reference driver calls
  * backward() on the loss itself, knowledge_representation.py:207, so the upstream is a known
  * scalar).  One gather of (3 + n_neg) rows and (3 + n_neg) gradient rows per group; outputs
- * and slot layout as kgrec_corrupt_loss_fwd / _bwd. */
+ * and slot layout as kgrec_corrupt_loss_fwd / _bwd.
+ * slot_ent_ids [n_pos * (2 + n_neg)] / slot_rel_ids [n_pos] (optional, int64): the table row of every
+ * gradient slot, i.e. the index array of the sparse COO gradient whose values the slots are
+ * (torch.sparse_coo_tensor(ids, slots)); written by the same pass so that no host-side index
+ * building is left in a training step. */
 int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model,
                             const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
                             const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
                             int loss_kind, float margin_or_target, float grad_loss,
                             float* pos_scores, float* neg_scores, float* loss,
-                            const kgrec_grads* grads, void* workspace, int32_t* status,
-                            kgrec_stream_t stream);
+                            const kgrec_grads* grads, int64_t* slot_ent_ids, int64_t* slot_rel_ids,
+                            void* workspace, int32_t* status, kgrec_stream_t stream);
 
 /* ---- device-side negative sampling --------------------------------
  * The reference draws negatives with per-triple Python rejection loops (utils/data.py:12-85).

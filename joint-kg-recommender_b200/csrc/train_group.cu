@@ -404,12 +404,17 @@ k_group_step(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
 //   * loss kind, gradient layout and norm are template parameters (no constant-bank reloads and
 //     branches on them inside the loop), the tail predicate lane*4 < d is hoisted, row / slot
 //     addresses advance by one IMAD.WIDE each;
-//   * the negative loop is unrolled by two with ping-pong row buffers (no register rotation), and
-//     the ids of the next group are fetched while this one computes.
+//   * the negative loop is unrolled by two with ping-pong row buffers (no register rotation);
+//   * ids never sit between a row and its request: the K corrupted ids of a group are ONE coalesced
+//     load held one per lane (and the positive's three ids one load in lanes 0-2), fetched a whole
+//     group ahead and handed out by shuffles, so the request for row k+1 leaves as soon as row k's
+//     arithmetic starts (with per-negative id loads the row request waited a full L2 round trip:
+//     48 % of the stall samples).
 template <bool L1, bool DENSE, bool MARGIN, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
-               float* __restrict__ group_loss, const kgrec_grads Gr, int32_t* status) {
+               float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
+               int64_t* __restrict__ slot_rel, int32_t* status) {
   const kgrec_tables& T = G.T;
   const LossCfg& L = G.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -437,18 +442,34 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
   };
 
   int j = blockIdx.x * kWarpsPerCta + wid;
-  uint32_t ih = 0, it = 0, ir = 0;
-  int32_t c0 = 0;
-  if (j < n_pos) {
-    ih = group_idx(G.ph, j, G.is64, T.n_ent, status);
-    it = group_idx(G.pt, j, G.is64, T.n_ent, status);
-    ir = group_idx(G.pr, j, G.is64, T.n_rel, status);
-    c0 = __ldg(G.corrupt + static_cast<uint32_t>(j) * K);
-  }
+  // ids of a group, one per lane: cv = corrupt[j*K + lane] (lane < K), pv = (h, t, r)[lane] (lane < 3)
+  const void* pcol = lane == 0 ? G.ph : (lane == 1 ? G.pt : G.pr);
+  auto fetch_ids = [&](int jj, int32_t& cv, int64_t& pv) {
+    cv = lane < K ? __ldg(G.corrupt + static_cast<uint32_t>(jj) * K + lane) : 0;
+    pv = lane < 3 ? load_idx(pcol, jj, G.is64) : 0;
+  };
+  int32_t cv = 0, cvn = 0;
+  int64_t pv = 0, pvn = 0;
+  if (j < n_pos) fetch_ids(j, cvn, pvn);
   for (; j < n_pos; j += stride) {
+    cv = cvn;
+    pv = pvn;
+    const int jn = j + stride;
+    if (jn < n_pos) fetch_ids(jn, cvn, pvn);     // the next group's ids travel while this group computes
+    const int64_t vh = __shfl_sync(FULL, pv, 0), vt = __shfl_sync(FULL, pv, 1), vr = __shfl_sync(FULL, pv, 2);
+    uint32_t ih = static_cast<uint32_t>(vh), it = static_cast<uint32_t>(vt), ir = static_cast<uint32_t>(vr);
+    if (static_cast<uint64_t>(vh) >= static_cast<uint64_t>(T.n_ent)) { bad = true; ih = 0; }
+    if (static_cast<uint64_t>(vt) >= static_cast<uint64_t>(T.n_ent)) { bad = true; it = 0; }
+    if (static_cast<uint64_t>(vr) >= static_cast<uint64_t>(T.n_rel)) { bad = true; ir = 0; }
+    if (slot_ent) {      // row ids of the gradient slots: [h, t, corrupted_1..K] per group, r per group
+      const uint32_t s0 = static_cast<uint32_t>(j) * (2 + K);
+      if (lane < 2) slot_ent[s0 + lane] = pv;
+      if (lane == 2) slot_rel[j] = pv;
+      if (lane < K) slot_ent[s0 + 2 + lane] = cv < 0 ? ~cv : cv;
+    }
     float4 h = z4, t = z4, r = z4, xa = z4, xb = z4;
     bool heada, headb = false;
-    uint32_t ida = ent_id(c0, heada), idb = 0;
+    uint32_t ida = ent_id(__shfl_sync(FULL, cv, 0), heada), idb = 0;
     if (act) {
       h = ldg_f4_hint(row(ent_b, ih), pol_keep);
       t = ldg_f4_hint(row(ent_b, it), pol_keep);
@@ -456,14 +477,6 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
       xa = ldg_f4_hint(row(ent_b, ida), pol_keep);
     }
     [[maybe_unused]] const uint32_t ih0 = ih, it0 = it, ir0 = ir;
-    const int jn = j + stride;
-    if (jn < n_pos) {   // the next group's ids travel while this group computes
-      ih = group_idx(G.ph, jn, G.is64, T.n_ent, status);
-      it = group_idx(G.pt, jn, G.is64, T.n_ent, status);
-      ir = group_idx(G.pr, jn, G.is64, T.n_rel, status);
-      c0 = __ldg(G.corrupt + static_cast<uint32_t>(jn) * K);
-    }
-    const int32_t* cj = G.corrupt + static_cast<uint32_t>(j) * K;
     float up = up0;
     if (!MARGIN) {
       const int b = j / bp;
@@ -517,13 +530,13 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
 
     for (int k = 0; k < K; k += 2) {
       if (k + 1 < K) {
-        idb = ent_id(__ldg(cj + k + 1), headb);
+        idb = ent_id(__shfl_sync(FULL, cv, k + 1), headb);
         if (act) xb = ldg_f4_hint(row(ent_b, idb), pol_keep);
       }
       negative(xa, heada, ida, k);
       if (k + 1 < K) {
         if (k + 2 < K) {
-          ida = ent_id(__ldg(cj + k + 2), heada);
+          ida = ent_id(__shfl_sync(FULL, cv, k + 2), heada);
           if (act) xa = ldg_f4_hint(row(ent_b, ida), pol_keep);
         }
         negative(xb, headb, idb, k + 1);
@@ -554,6 +567,22 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
     }
   }
   if (bad && status) *status = 1;
+}
+
+// slot row ids for the general step kernel (TransH, wide rows): one thread per slot
+__global__ void __launch_bounds__(256)
+k_group_slot_ids(const void* ph, const void* pt, const void* pr, const int is64, const int32_t* __restrict__ corrupt,
+                 const int64_t n_pos, const int K, int64_t* __restrict__ slot_ent, int64_t* __restrict__ slot_rel) {
+  const int64_t total = n_pos * (2 + K);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t j = i / (2 + K);
+    const int t = static_cast<int>(i - j * (2 + K));
+    int64_t v;
+    if (t == 0) { v = load_idx(ph, j, is64); slot_rel[j] = load_idx(pr, j, is64); }
+    else if (t == 1) v = load_idx(pt, j, is64);
+    else { const int32_t c = __ldg(corrupt + j * K + (t - 2)); v = c < 0 ? ~c : c; }
+    slot_ent[i] = v;
+  }
 }
 
 int make_plan(const kgrec_tables* T, int model, Plan* pl);
@@ -643,8 +672,8 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
                                        const void* pr, int idx_bytes, int64_t n_pos, const int32_t* corrupt,
                                        int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
                                        float grad_loss, float* pos_scores, float* neg_scores, float* loss,
-                                       const kgrec_grads* grads, void* workspace, int32_t* status,
-                                       kgrec_stream_t stream) {
+                                       const kgrec_grads* grads, int64_t* slot_ent_ids, int64_t* slot_rel_ids,
+                                       void* workspace, int32_t* status, kgrec_stream_t stream) {
   Plan pl;
   int rc = group_check(tables, model, &pl, ph, pt, pr, idx_bytes, n_pos, corrupt, n_neg, batch_pos, loss_kind);
   if (rc) return rc;
@@ -653,6 +682,7 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
     set_error("bad grads descriptor");
     return KGREC_ERR_INVALID;
   }
+  if ((slot_ent_ids == nullptr) != (slot_rel_ids == nullptr)) { set_error("slot_ent_ids and slot_rel_ids go together"); return KGREC_ERR_INVALID; }
   if (n_pos == 0) return KGREC_OK;
   const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos},
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
@@ -666,9 +696,9 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
 #define CALL_E(L1V, DV, MV)                                                                                      \
   {                                                                                                              \
     if (env && env[0] == '3')                                                                                    \
-      k_group_step_e<L1V, DV, MV, 3><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status); \
+      k_group_step_e<L1V, DV, MV, 3><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else                                                                                                         \
-      k_group_step_e<L1V, DV, MV, 4><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status); \
+      k_group_step_e<L1V, DV, MV, 4><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
   }
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
     if (tables->l1) { if (dn) { if (mg) CALL_E(true, true, true) else CALL_E(true, true, false) } else { if (mg) CALL_E(true, false, true) else CALL_E(true, false, false) } }
@@ -680,6 +710,12 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
   else k_group_step<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status);
   KGREC_GROUP_DISPATCH(CALL)
 #undef CALL
+    if (slot_ent_ids) {
+      const int64_t total = n_pos * (2 + static_cast<int64_t>(n_neg));
+      const int64_t ctas = (total + 255) / 256, cap = static_cast<int64_t>(sm_count()) * 16;
+      k_group_slot_ids<<<static_cast<unsigned>(ctas < cap ? ctas : cap), 256, 0, st>>>(ph, pt, pr, idx_bytes == 8, corrupt, n_pos, n_neg,
+                                                                                         slot_ent_ids, slot_rel_ids);
+    }
   }
   KGREC_CUDA_OK(cudaGetLastError());
   const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;

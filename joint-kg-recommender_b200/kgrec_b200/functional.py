@@ -364,24 +364,24 @@ def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, p
         bufs[name] = torch.zeros_like(weights[name]) if dense else \
             torch.empty((shapes[name], cfg.dim), dtype=torch.float32, device=dev)
         setattr(g, name, bufs[name].data_ptr())
+    # the COO index arrays of the slot gradients come out of the same kernel pass
+    ent_ids = rel_ids = None
+    if not dense:
+        ent_ids = torch.empty((1, n_pos * (2 + n_neg)), dtype=torch.int64, device=dev)
+        rel_ids = torch.empty((1, n_pos), dtype=torch.int64, device=dev)
     lib = _lib.load()
     _lib.check(lib.kgrec_corrupt_loss_step(
         C.byref(T), cfg.model, _ptr(ph), _ptr(pt), _ptr(pr), _idx_bytes(ph, pt, pr), n_pos, _ptr(corrupt), n_neg,
         batch_pos, loss_kind, float(param), float(grad_loss), _ptr(pos_s), _ptr(neg_s), _ptr(loss), C.byref(g),
-        _ptr(ws), _ptr(status), _stream()))
+        _ptr(ent_ids), _ptr(rel_ids), _ptr(ws), _ptr(status), _stream()))
     count_launches(2)
     grads = {}
     for name in names:
         if dense:
             grads[name] = bufs[name]
         else:
-            if name == "ent":
-                cid = torch.where(corrupt < 0, ~corrupt, corrupt).view(n_pos, n_neg).long()
-                idx = torch.cat([ph.long().view(-1, 1), pt.long().view(-1, 1), cid], dim=1).reshape(1, -1)
-            else:
-                idx = pr.long().view(1, -1)
-            grads[name] = torch.sparse_coo_tensor(idx, bufs[name], size=tuple(weights[name].shape),
-                                                  check_invariants=False)
+            grads[name] = torch.sparse_coo_tensor(ent_ids if name == "ent" else rel_ids, bufs[name],
+                                                  size=tuple(weights[name].shape), check_invariants=False)
     return loss, pos_s, neg_s, grads
 
 

@@ -62,14 +62,15 @@ class SparseRowOptimizer:
         out = torch.empty((n_pos + bp - 1) // bp, dtype=torch.float32, device=dev)
         ws = torch.empty(max(1, n_pos), dtype=torch.float32, device=dev)
         kind = {"margin": _lib.LOSS_MARGIN, "bpr": _lib.LOSS_BPR}[loss]
+        # the rows this batch touched come out of the same kernel pass (slot row ids)
+        ent_ids = torch.empty(n_pos * (2 + n_neg), dtype=torch.int64, device=dev)
+        rel_ids = torch.empty(n_pos, dtype=torch.int64, device=dev)
         _lib.check(lib.kgrec_corrupt_loss_step(
             C.byref(T), m.MODEL, ptr(pos[0]), ptr(pos[1]), ptr(pos[2]), pos[0].element_size(), n_pos, ptr(corrupt),
-            n_neg, bp, kind, float(margin), 1.0, ptr(pos_s), ptr(neg_s), ptr(out), C.byref(g), ptr(ws),
-            ptr(m._status_buf(dev)), stream))
+            n_neg, bp, kind, float(margin), 1.0, ptr(pos_s), ptr(neg_s), ptr(out), C.byref(g), ptr(ent_ids), ptr(rel_ids),
+            ptr(ws), ptr(m._status_buf(dev)), stream))
         KF.count_launches(2)
-        # the rows this batch touched
-        cid = torch.where(corrupt < 0, ~corrupt, corrupt)
-        ids = {"ent": torch.cat([pos[0].to(torch.int32), pos[1].to(torch.int32), cid]), "rel": pos[2], "norm": pos[2]}
+        ids = {"ent": ent_ids, "rel": rel_ids, "norm": rel_ids}
         self.t += 1
         use_clip = self.clip is not None
         if use_clip:
