@@ -171,7 +171,10 @@ int kgrec_rank_loss_bwd(const kgrec_tables* tables, int model,
  * TUP / KTUP pairs are scored, differentiated and reduced in a single kernel pass when a
  * positive and its negatives fit one warp's rows (n_neg <= 15, embedding_size <= 128,
  * preference_total <= 32); other shapes and models run the two kernels back to back.
- * Gradient slots as in kgrec_rank_loss_bwd. */
+ * Gradient slots as in kgrec_rank_loss_bwd.
+ * slot_user_ids / slot_item_ids / slot_ent_ids (optional, int64 [n_pos * (1 + n_neg)], TUP / KTUP
+ * only, ent for KTUP): the table row of every gradient slot, i.e. the index arrays of the sparse COO
+ * gradients, written by the same pass. */
 int kgrec_rank_loss_step(const kgrec_tables* tables, int model,
                          const void* pa, const void* pb, const void* pc,
                          const void* na, const void* nb, const void* nc,
@@ -179,8 +182,9 @@ int kgrec_rank_loss_step(const kgrec_tables* tables, int model,
                          int loss_kind, float margin_or_target, float grad_loss,
                          const float* gumbel_u, uint64_t seed,
                          float* pos_scores, float* neg_scores, float* loss,
-                         const kgrec_grads* grads, void* workspace, int32_t* status,
-                         kgrec_stream_t stream);
+                         const kgrec_grads* grads,
+                         int64_t* slot_user_ids, int64_t* slot_item_ids, int64_t* slot_ent_ids,
+                         void* workspace, int32_t* status, kgrec_stream_t stream);
 
 /* The same fused ranking loss in the group-compact negative format (TransE / TransH and the
  * KTUP KG branch).  The reference draws a negative by corrupting the head OR the tail of its

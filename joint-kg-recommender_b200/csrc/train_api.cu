@@ -188,6 +188,7 @@ extern "C" int kgrec_rank_loss_step(const kgrec_tables* tables, int model, const
                                     int64_t n_pos, int32_t n_neg, int64_t batch_pos, int loss_kind,
                                     float margin_or_target, float grad_loss, const float* gumbel_u, uint64_t seed,
                                     float* pos_scores, float* neg_scores, float* loss, const kgrec_grads* grads,
+                                    int64_t* slot_user_ids, int64_t* slot_item_ids, int64_t* slot_ent_ids,
                                     void* workspace, int32_t* status, kgrec_stream_t stream) {
   Plan pl;
   int rc = make_plan(tables, model, &pl);
@@ -197,6 +198,11 @@ extern "C" int kgrec_rank_loss_step(const kgrec_tables* tables, int model, const
     return rc;
   if ((rc = check_loss(loss_kind, n_pos, n_neg, batch_pos))) return rc;
   if (!pos_scores || !neg_scores || !loss || !workspace) { set_error("output / workspace pointer is NULL"); return KGREC_ERR_INVALID; }
+  const bool want_ids = slot_user_ids != nullptr;
+  if (want_ids && (pl.fam != FAM_REC || !slot_item_ids || (pl.ktup && !slot_ent_ids))) {
+    set_error("slot ids: TUP / KTUP only, user + item (+ entity for KTUP) together");
+    return KGREC_ERR_INVALID;
+  }
   if (n_pos == 0) return KGREC_OK;
   const IdxArgs I{pa, pb, pc, na, nb, nc, idx_bytes == 8};
   const LossCfg L{loss_kind, margin_or_target, n_neg, n_pos, batch_pos};
@@ -205,7 +211,8 @@ extern "C" int kgrec_rank_loss_step(const kgrec_tables* tables, int model, const
   const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
   rc = -1;
   if (pl.fam == FAM_REC)
-    rc = rec_tile_loss_step(*tables, pl, I, L, grad_loss, gumbel_u, seed, pos_scores, neg_scores, group_loss, *grads, status, st);
+    rc = rec_tile_loss_step(*tables, pl, I, L, grad_loss, gumbel_u, seed, pos_scores, neg_scores, group_loss, *grads,
+                            want_ids ? slot_user_ids : nullptr, slot_item_ids, slot_ent_ids, status, st);
   if (rc > 0) return rc;
   if (rc < 0) {   // shapes the single-pass kernel is not built for: forward, then backward from the saved scores
     rc = KGREC_BY_FAMILY(pl.fam, launch_rank_loss_fwd)(*tables, pl, I, L, gumbel_u, seed, pos_scores, neg_scores,
@@ -215,6 +222,9 @@ extern "C" int kgrec_rank_loss_step(const kgrec_tables* tables, int model, const
     rc = KGREC_BY_FAMILY(pl.fam, launch_score_bwd)(*tables, pl, I, n_pos * (1 + static_cast<int64_t>(n_neg)), L,
                                                    gumbel_u, seed, B, *grads, st);
     if (rc) return rc;
+    if (want_ids && (rc = rec_slot_ids(*tables, pl, I, n_pos, n_pos * (1 + static_cast<int64_t>(n_neg)), slot_user_ids,
+                                       slot_item_ids, slot_ent_ids, st)))
+      return rc;
   }
   k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(group_loss, L, loss);
   KGREC_CUDA_OK(cudaGetLastError());

@@ -726,7 +726,10 @@ int rec_tile_score_bwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, 
                        const float* gumbel_u, uint64_t seed, const BwdArgs& B, const kgrec_grads& G, cudaStream_t st);
 int rec_tile_loss_step(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, const LossCfg& L, float grad_loss,
                        const float* gumbel_u, uint64_t seed, float* pos_scores, float* neg_scores, float* group_loss,
-                       const kgrec_grads& G, int32_t* status, cudaStream_t st);
+                       const kgrec_grads& G, int64_t* slot_user, int64_t* slot_item, int64_t* slot_ent, int32_t* status,
+                       cudaStream_t st);
+int rec_slot_ids(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n_pos, int64_t n, int64_t* su, int64_t* si,
+                 int64_t* se, cudaStream_t st);
 
 template <int FAM>
 int launch_score_fwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n, const float* gumbel_u,

@@ -569,6 +569,192 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
   if (bad && status) *status = 1;
 }
 
+// --- TransH (and the KTUP KG branch), d <= 128: the same treatment ------------------------------
+// With proj(v) = v - (v.w) w the residual is e' = B - proj(x), B = proj(h) + r or proj(t) - r.  Writing
+// g = -eps' for the gradient arriving at proj(x), the group needs per negative only
+//   g_x = g - (g.w) w,   g_w -= (g.w) x + (x.w) g,   accT/accH -= g,   sT/sH -= g.w
+// and everything that involves the shared rows is linear in (accT, accH, sT, sH), so it is applied once
+// per group:  E_h = accT + eps_p, E_t = accH - eps_p,
+//   g_h = E_h - (E_h.w) w,  g_t = E_t - (E_t.w) w,  g_r = accT - accH + eps_p,
+//   g_w -= (E_h.w) h + (h.w) E_h + (E_t.w) t + (t.w) E_t.
+// The two reductions a negative needs after its residual (the score and g.w) share one shuffle tree.
+template <bool L1, bool DENSE, bool MARGIN, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
+               float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
+               int64_t* __restrict__ slot_rel, int32_t* status) {
+  const kgrec_tables& T = G.T;
+  const LossCfg& L = G.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K = L.n_neg;
+  const int n_pos = static_cast<int>(L.n_pos);
+  const uint32_t n_ent = static_cast<uint32_t>(T.n_ent);
+  const uint32_t ld4 = static_cast<uint32_t>(T.ld) * 4u, d4 = static_cast<uint32_t>(T.dim) * 4u;
+  const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
+  const uint64_t pol_keep = policy_evict_last(G.keep), pol_stream = policy_evict_first();
+  const bool act = lane * 4 < T.dim;
+  const char* ent_b = reinterpret_cast<const char*>(T.ent) + lane * 16;
+  const char* rel_b = reinterpret_cast<const char*>(T.rel) + lane * 16;
+  const char* nrm_b = reinterpret_cast<const char*>(T.norm) + lane * 16;
+  char* gent_b = reinterpret_cast<char*>(Gr.ent) + lane * 16;
+  char* grel_b = reinterpret_cast<char*>(Gr.rel) + lane * 16;
+  char* gnrm_b = reinterpret_cast<char*>(Gr.norm) + lane * 16;
+  const float prm = L.param;
+  const int stride = gridDim.x * kWarpsPerCta;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto row = [&](const char* base, uint32_t id) { return reinterpret_cast<const float4*>(base + static_cast<uint64_t>(id) * ld4); };
+  auto dot4 = [](const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); };
+  bool bad = false;
+  auto ent_id = [&](int32_t c, bool& head) {
+    head = c < 0;
+    uint32_t id = static_cast<uint32_t>(head ? ~c : c);
+    if (id >= n_ent) { bad = true; id = 0; }
+    return id;
+  };
+  int j = blockIdx.x * kWarpsPerCta + wid;
+  const void* pcol = lane == 0 ? G.ph : (lane == 1 ? G.pt : G.pr);
+  auto fetch_ids = [&](int jj, int32_t& cv, int64_t& pv) {
+    cv = lane < K ? __ldg(G.corrupt + static_cast<uint32_t>(jj) * K + lane) : 0;
+    pv = lane < 3 ? load_idx(pcol, jj, G.is64) : 0;
+  };
+  int32_t cv = 0, cvn = 0;
+  int64_t pv = 0, pvn = 0;
+  if (j < n_pos) fetch_ids(j, cvn, pvn);
+  for (; j < n_pos; j += stride) {
+    cv = cvn;
+    pv = pvn;
+    const int jn = j + stride;
+    if (jn < n_pos) fetch_ids(jn, cvn, pvn);
+    const int64_t vh = __shfl_sync(FULL, pv, 0), vt = __shfl_sync(FULL, pv, 1), vr = __shfl_sync(FULL, pv, 2);
+    uint32_t ih = static_cast<uint32_t>(vh), it = static_cast<uint32_t>(vt), ir = static_cast<uint32_t>(vr);
+    if (static_cast<uint64_t>(vh) >= static_cast<uint64_t>(T.n_ent)) { bad = true; ih = 0; }
+    if (static_cast<uint64_t>(vt) >= static_cast<uint64_t>(T.n_ent)) { bad = true; it = 0; }
+    if (static_cast<uint64_t>(vr) >= static_cast<uint64_t>(T.n_rel)) { bad = true; ir = 0; }
+    if (slot_ent) {
+      const uint32_t s0 = static_cast<uint32_t>(j) * (2 + K);
+      if (lane < 2) slot_ent[s0 + lane] = pv;
+      if (lane == 2) slot_rel[j] = pv;
+      if (lane < K) slot_ent[s0 + 2 + lane] = cv < 0 ? ~cv : cv;
+    }
+    float4 h = z4, t = z4, r = z4, w = z4, xa = z4, xb = z4;
+    bool heada, headb = false;
+    uint32_t ida = ent_id(__shfl_sync(FULL, cv, 0), heada), idb = 0;
+    if (act) {
+      h = ldg_f4_hint(row(ent_b, ih), pol_keep);
+      t = ldg_f4_hint(row(ent_b, it), pol_keep);
+      r = ldg_f4_hint(row(rel_b, ir), pol_keep);
+      w = ldg_f4_hint(row(nrm_b, ir), pol_keep);
+      xa = ldg_f4_hint(row(ent_b, ida), pol_keep);
+    }
+    float up = up0;
+    if (!MARGIN) {
+      const int b = j / bp;
+      up /= static_cast<float>(min(bp, n_pos - b * bp)) * static_cast<float>(K);
+    }
+    float a = dot4(h, w), b = dot4(t, w);
+    warp_sum2(a, b);
+    const float4 pt = make_float4(fmaf(-b, w.x, t.x), fmaf(-b, w.y, t.y), fmaf(-b, w.z, t.z), fmaf(-b, w.w, t.w));
+    const float4 bh = make_float4(fmaf(-a, w.x, h.x) + r.x, fmaf(-a, w.y, h.y) + r.y, fmaf(-a, w.z, h.z) + r.z, fmaf(-a, w.w, h.w) + r.w);
+    const float4 bt = make_float4(pt.x - r.x, pt.y - r.y, pt.z - r.z, pt.w - r.w);
+    const float4 ep = make_float4(bh.x - pt.x, bh.y - pt.y, bh.z - pt.z, bh.w - pt.w);
+    const float sp = warp_sum(dist_term(ep.x, L1) + dist_term(ep.y, L1) + dist_term(ep.z, L1) + dist_term(ep.w, L1));
+    float lsum = 0.f, cpos = 0.f, mys = 0.f, sT = 0.f, sH = 0.f;
+    float4 accT = z4, accH = z4, gwv = z4;
+    uint32_t goff = (static_cast<uint32_t>(j) * (2 + K) + 2) * d4;
+
+    auto negative = [&](const float4& x, const bool head, const uint32_t id, const int k) {
+      const float ax = warp_sum(dot4(x, w));
+      const float4 B = head ? bt : bh;
+      const float4 e = make_float4(B.x - fmaf(-ax, w.x, x.x), B.y - fmaf(-ax, w.y, x.y), B.z - fmaf(-ax, w.z, x.z), B.w - fmaf(-ax, w.w, x.w));
+      const float4 dd = L1 ? make_float4(ddist_term(e.x, 1), ddist_term(e.y, 1), ddist_term(e.z, 1), ddist_term(e.w, 1)) : e;   // L2: x2 below
+      float sn = dist_term(e.x, L1) + dist_term(e.y, L1) + dist_term(e.z, L1) + dist_term(e.w, L1);
+      float dw = dot4(dd, w);
+      warp_sum2(sn, dw);
+      if (lane == k) mys = sn;
+      float coef;
+      if (MARGIN) {
+        const float tt = sp - sn + prm;
+        lsum += fmaxf(tt, 0.f);
+        coef = tt > 0.f ? up : 0.f;
+        cpos += tt > 0.f ? 1.f : 0.f;
+      } else {
+        const float xx = prm * (sp - sn);
+        lsum += fmaxf(-xx, 0.f) + log1pf(expf(-fabsf(xx)));
+        const float dp = -prm / (1.f + expf(xx));
+        cpos += dp;
+        coef = dp * up;
+      }
+      if (coef != 0.f) {
+        const float c = L1 ? coef : 2.f * coef;
+        const float4 g = make_float4(c * dd.x, c * dd.y, c * dd.z, c * dd.w);       // -eps' at proj(x)
+        const float gdw = c * dw;                                                   // g . w
+        const float4 gx = make_float4(fmaf(-gdw, w.x, g.x), fmaf(-gdw, w.y, g.y), fmaf(-gdw, w.z, g.z), fmaf(-gdw, w.w, g.w));
+        gwv.x = fmaf(-gdw, x.x, fmaf(-ax, g.x, gwv.x));
+        gwv.y = fmaf(-gdw, x.y, fmaf(-ax, g.y, gwv.y));
+        gwv.z = fmaf(-gdw, x.z, fmaf(-ax, g.z, gwv.z));
+        gwv.w = fmaf(-gdw, x.w, fmaf(-ax, g.w, gwv.w));
+        if (head) { accH.x -= g.x; accH.y -= g.y; accH.z -= g.z; accH.w -= g.w; sH -= gdw; }
+        else { accT.x -= g.x; accT.y -= g.y; accT.z -= g.z; accT.w -= g.w; sT -= gdw; }
+        if (act) {
+          if (DENSE) red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(id) * d4), gx.x, gx.y, gx.z, gx.w);
+          else stg_f4_hint(reinterpret_cast<float4*>(gent_b + goff), gx.x, gx.y, gx.z, gx.w, pol_stream);
+        }
+      } else if (!DENSE) {
+        if (act) stg_f4_hint(reinterpret_cast<float4*>(gent_b + goff), 0.f, 0.f, 0.f, 0.f, pol_stream);
+      }
+      goff += d4;
+    };
+
+    for (int k = 0; k < K; k += 2) {
+      if (k + 1 < K) {
+        idb = ent_id(__shfl_sync(FULL, cv, k + 1), headb);
+        if (act) xb = ldg_f4_hint(row(ent_b, idb), pol_keep);
+      }
+      negative(xa, heada, ida, k);
+      if (k + 1 < K) {
+        if (k + 2 < K) {
+          ida = ent_id(__shfl_sync(FULL, cv, k + 2), heada);
+          if (act) xa = ldg_f4_hint(row(ent_b, ida), pol_keep);
+        }
+        negative(xb, headb, idb, k + 1);
+      }
+    }
+    const float cp = cpos * up;
+    const float4 eps = make_float4(cp * ddist_term(ep.x, L1), cp * ddist_term(ep.y, L1), cp * ddist_term(ep.z, L1), cp * ddist_term(ep.w, L1));
+    const float epw = warp_sum(dot4(eps, w));
+    const float4 EH = make_float4(accT.x + eps.x, accT.y + eps.y, accT.z + eps.z, accT.w + eps.w);
+    const float4 ET = make_float4(accH.x - eps.x, accH.y - eps.y, accH.z - eps.z, accH.w - eps.w);
+    const float eh = sT + epw, et = sH - epw;
+    const float4 gh = make_float4(fmaf(-eh, w.x, EH.x), fmaf(-eh, w.y, EH.y), fmaf(-eh, w.z, EH.z), fmaf(-eh, w.w, EH.w));
+    const float4 gt = make_float4(fmaf(-et, w.x, ET.x), fmaf(-et, w.y, ET.y), fmaf(-et, w.z, ET.z), fmaf(-et, w.w, ET.w));
+    const float4 gr = make_float4(accT.x - accH.x + eps.x, accT.y - accH.y + eps.y, accT.z - accH.z + eps.z, accT.w - accH.w + eps.w);
+    gwv.x -= fmaf(eh, h.x, a * EH.x) + fmaf(et, t.x, b * ET.x);
+    gwv.y -= fmaf(eh, h.y, a * EH.y) + fmaf(et, t.y, b * ET.y);
+    gwv.z -= fmaf(eh, h.z, a * EH.z) + fmaf(et, t.z, b * ET.z);
+    gwv.w -= fmaf(eh, h.w, a * EH.w) + fmaf(et, t.w, b * ET.w);
+    if (lane == 0) {
+      pos_scores[j] = sp;
+      group_loss[j] = lsum;
+    }
+    if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
+    if (act) {
+      if (DENSE) {
+        red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(ih) * d4), gh.x, gh.y, gh.z, gh.w);
+        red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(it) * d4), gt.x, gt.y, gt.z, gt.w);
+        red_add_f4(reinterpret_cast<float*>(grel_b + static_cast<uint64_t>(ir) * d4), gr.x, gr.y, gr.z, gr.w);
+        red_add_f4(reinterpret_cast<float*>(gnrm_b + static_cast<uint64_t>(ir) * d4), gwv.x, gwv.y, gwv.z, gwv.w);
+      } else {
+        const uint32_t g0 = static_cast<uint32_t>(j) * (2 + K) * d4;
+        stg_f4_hint(reinterpret_cast<float4*>(gent_b + g0), gh.x, gh.y, gh.z, gh.w, pol_stream);
+        stg_f4_hint(reinterpret_cast<float4*>(gent_b + g0 + d4), gt.x, gt.y, gt.z, gt.w, pol_stream);
+        stg_f4_hint(reinterpret_cast<float4*>(grel_b + static_cast<uint32_t>(j) * d4), gr.x, gr.y, gr.z, gr.w, pol_stream);
+        stg_f4_hint(reinterpret_cast<float4*>(gnrm_b + static_cast<uint32_t>(j) * d4), gwv.x, gwv.y, gwv.z, gwv.w, pol_stream);
+      }
+    }
+  }
+  if (bad && status) *status = 1;
+}
+
 // slot row ids for the general step kernel (TransH, wide rows): one thread per slot
 __global__ void __launch_bounds__(256)
 k_group_slot_ids(const void* ph, const void* pt, const void* pr, const int is64, const int32_t* __restrict__ corrupt,
@@ -704,6 +890,18 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
     if (tables->l1) { if (dn) { if (mg) CALL_E(true, true, true) else CALL_E(true, true, false) } else { if (mg) CALL_E(true, false, true) else CALL_E(true, false, false) } }
     else { if (dn) { if (mg) CALL_E(false, true, true) else CALL_E(false, true, false) } else { if (mg) CALL_E(false, false, true) else CALL_E(false, false, false) } }
 #undef CALL_E
+  } else if (pl.fam == FAM_H && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
+#define CALL_H(L1V, DV, MV)                                                                                      \
+  {                                                                                                              \
+    if (env && env[0] == '2')                                                                                    \
+      k_group_step_h<L1V, DV, MV, 2><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+    else                                                                                                         \
+      k_group_step_h<L1V, DV, MV, 3><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+  }
+    const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
+    if (tables->l1) { if (dn) { if (mg) CALL_H(true, true, true) else CALL_H(true, true, false) } else { if (mg) CALL_H(true, false, true) else CALL_H(true, false, false) } }
+    else { if (dn) { if (mg) CALL_H(false, true, true) else CALL_H(false, true, false) } else { if (mg) CALL_H(false, false, true) else CALL_H(false, false, false) } }
+#undef CALL_H
   } else {
 #define CALL(FAMV, NCHV)                                                                                        \
   if (tables->l1) k_group_step<FAMV, NCHV, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status); \

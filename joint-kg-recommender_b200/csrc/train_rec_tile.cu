@@ -46,6 +46,7 @@ struct TileArgs {
   // then its negatives), so the ranking loss and its gradient are formed between two passes
   int gsz, gw;
   float* group_loss;
+  int64_t *slot_user, *slot_item, *slot_ent;   // optional: table row of every gradient slot (COO indices)
 };
 
 enum { MODE_FWD = 0, MODE_BWD = 1, MODE_STEP = 2 };
@@ -516,6 +517,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
         float4 gi = E[r * lda4 + lane];
         const int ia = sid[2 * M + r];
         const bool pad = A.ktup && ia == T.n_ent - 1;     // padding row: no gradient (jTransUP.py:96)
+        if (A.slot_user && lane == 0) {
+          A.slot_user[i] = sid[r];
+          A.slot_item[i] = sid[M + r];
+          if (A.ktup) A.slot_ent[i] = ia;
+        }
         if (A.G.mode == 0) {
           __stcs(reinterpret_cast<float4*>(A.G.user + i * d) + lane, gu);
           __stcs(reinterpret_cast<float4*>(A.G.item + i * d) + lane, gi);
@@ -563,6 +569,20 @@ k_group_loss(const float* __restrict__ pos, const float* __restrict__ neg, const
   float s = 0.f;
   for (int k = 0; k < L.n_neg; ++k) s += loss_term(L, sp, neg[j * L.n_neg + k]);
   group_loss[j] = s;
+}
+
+// slot row ids when the step runs as two kernels (shapes outside the tile engine)
+__global__ void __launch_bounds__(256)
+k_rec_slot_ids(const void* a, const void* b, const void* na, const void* nb, const int is64, const int64_t n_pos, const int64_t n,
+               const int32_t* __restrict__ item2ent, int64_t* __restrict__ su, int64_t* __restrict__ si, int64_t* __restrict__ se) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const bool neg = i >= n_pos;
+    const int64_t li = neg ? i - n_pos : i;
+    const int64_t iu = load_idx(neg ? na : a, li, is64), ii = load_idx(neg ? nb : b, li, is64);
+    su[i] = iu;
+    si[i] = ii;
+    if (se) se[i] = __ldg(item2ent + ii);
+  }
 }
 
 struct TilePlan {
@@ -666,7 +686,8 @@ int rec_tile_score_bwd(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, 
 // forward + ranking loss + backward in one pass over groups of (positive, its negatives)
 int rec_tile_loss_step(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, const LossCfg& L, float grad_loss,
                        const float* gumbel_u, uint64_t seed, float* pos_scores, float* neg_scores, float* group_loss,
-                       const kgrec_grads& G, int32_t* status, cudaStream_t st) {
+                       const kgrec_grads& G, int64_t* slot_user, int64_t* slot_item, int64_t* slot_ent, int32_t* status,
+                       cudaStream_t st) {
   if (L.n_neg > kPairsPerWarp - 1) return -1;
   const int gsz = 1 + L.n_neg, gw = kPairsPerWarp / gsz;
   TilePlan tp;
@@ -677,7 +698,17 @@ int rec_tile_loss_step(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, 
   A.scores_a = pos_scores; A.scores_b = neg_scores; A.status = status;
   A.L = L; A.B = BwdArgs{nullptr, nullptr, nullptr, grad_loss, nullptr}; A.G = G;
   A.lda = tp.lda; A.n_tiles = tp.n_tiles; A.gsz = gsz; A.gw = gw; A.group_loss = group_loss;
+  A.slot_user = slot_user; A.slot_item = slot_item; A.slot_ent = slot_ent;
   return launch_tiles<MODE_STEP>(A, tp, st);
+}
+
+int rec_slot_ids(const kgrec_tables& T, const Plan& pl, const IdxArgs& I, int64_t n_pos, int64_t n, int64_t* su, int64_t* si,
+                 int64_t* se, cudaStream_t st) {
+  const int64_t ctas = (n + 255) / 256, cap = static_cast<int64_t>(sm_count()) * 16;
+  k_rec_slot_ids<<<static_cast<unsigned>(ctas < cap ? ctas : cap), 256, 0, st>>>(I.a, I.b, I.na, I.nb, I.is64, n_pos, n,
+                                                                                   T.item2ent, su, si, pl.ktup ? se : nullptr);
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
 }
 
 }  // namespace kgrec

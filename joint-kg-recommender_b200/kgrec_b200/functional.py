@@ -401,14 +401,21 @@ def rank_loss_step(cfg, weights, pos, neg, n_neg, batch_pos, loss_kind, param, g
     loss = torch.empty((n_pos + batch_pos - 1) // batch_pos, dtype=torch.float32, device=dev)
     ws = torch.empty(max(1, n_pos), dtype=torch.float32, device=dev)
     G, bufs = _alloc_grads(cfg.model, weights, n, cfg.grad_mode, cfg.dim)
+    rec = cfg.model in (_lib.TUP, _lib.KTUP)
+    sparse = cfg.grad_mode != "dense"
+    ids = {}
+    if rec and sparse:      # the COO index arrays come out of the same kernel pass
+        for k in ("user", "item") + (("ent",) if cfg.model == _lib.KTUP else ()):
+            ids[k] = torch.empty(n, dtype=torch.int64, device=dev)
     lib = _lib.load()
     _lib.check(lib.kgrec_rank_loss_step(
         C.byref(T), cfg.model, _ptr(pa), _ptr(pb), _ptr(pc), _ptr(na), _ptr(nb), _ptr(nc),
         _idx_bytes(pa, pb, pc, na, nb, nc), n_pos, n_neg, batch_pos, loss_kind, float(param), float(grad_loss),
-        _ptr(gumbel_u), cfg.seed, _ptr(pos_s), _ptr(neg_s), _ptr(loss), C.byref(G), _ptr(ws), _ptr(status), _stream()))
+        _ptr(gumbel_u), cfg.seed, _ptr(pos_s), _ptr(neg_s), _ptr(loss), C.byref(G),
+        _ptr(ids.get("user")), _ptr(ids.get("item")), _ptr(ids.get("ent")), _ptr(ws), _ptr(status), _stream()))
     count_launches(2)
-    idx = {}
-    if cfg.grad_mode != "dense":
+    idx = ids
+    if sparse and not rec:
         pi = _slot_indices(cfg.model, pa, pb, pc, cfg.item2ent)
         ni = _slot_indices(cfg.model, na, nb, nc, cfg.item2ent)
         for k in pi:

@@ -31,3 +31,24 @@ for l1 in (False, True):
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 20
         print(f"l1={l1} KGREC_GROUP_STEP={env}: {ms:.4f} ms/step  {n_tri / ms * 1e3 / 1e9:.3f} G triples/s", flush=True)
+for l1 in (False, True):
+    torch.manual_seed(0)
+    m = K.TransHModel(l1, 100, 100_000, 500)
+    m.grad_mode = "sparse"
+    for env in ("0", "2", "3", "2"):
+        os.environ["KGREC_GROUP_STEP"] = env
+        def step(s):
+            ix = sets[s % 3]
+            m.zero_grad(set_to_none=True)
+            m.loss_step_corrupt(tuple(ix[:3]), ix[6], margin=1.0, batch_pos=1024)
+        for s in range(3):
+            step(s)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for s in range(20):
+            step(s)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 20
+        print(f"transh l1={l1} KGREC_GROUP_STEP={env}: {ms:.4f} ms/step  {n_tri / ms * 1e3 / 1e9:.3f} G triples/s", flush=True)
