@@ -13,10 +13,16 @@ class DevicePrefetcher:
     of the next batch overlaps the consumer's kernels.  Every tensor of a batch is copied inside
     the iteration that precedes its use, so a timed region around the loop contains all copies."""
 
+    _streams = {}     # one copy stream per device for the life of the process: the caching allocator keeps
+                      # its free blocks per stream, a fresh stream per epoch would start every epoch with cudaMalloc
+
     def __init__(self, batches, device, depth=2):
         self.it = iter(batches)
         self.device = torch.device(device)
-        self.copy_stream = torch.cuda.Stream(device=self.device)
+        key = (self.device.type, self.device.index if self.device.index is not None else torch.cuda.current_device())
+        if key not in DevicePrefetcher._streams:
+            DevicePrefetcher._streams[key] = torch.cuda.Stream(device=self.device)
+        self.copy_stream = DevicePrefetcher._streams[key]
         self.queue = []
         self.depth = max(1, depth)
 
