@@ -90,6 +90,8 @@ __device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, 
                : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // ---- L2 cache policies ---------------------------------------------------------------------
 // Embedding rows are re-read (by other triples, by the backward, by the next step) while
 // gradient rows are written once and consumed later by a different kernel: table loads carry an

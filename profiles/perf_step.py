@@ -14,7 +14,7 @@ for l1 in (False, True):
     torch.manual_seed(0)
     m = K.TransEModel(l1, 100, 100_000, 500)
     m.grad_mode = "sparse"
-    for env in ("4", "3", "4"):
+    for env in ("p", "q", "p", "q"):
         os.environ["KGREC_GROUP_STEP"] = env
         def step(s):
             ix = sets[s % 3]
@@ -35,7 +35,7 @@ for l1 in (False, True):
     torch.manual_seed(0)
     m = K.TransHModel(l1, 100, 100_000, 500)
     m.grad_mode = "sparse"
-    for env in ("0", "2", "3", "2"):
+    for env in ("3", "p", "q", "p"):
         os.environ["KGREC_GROUP_STEP"] = env
         def step(s):
             ix = sets[s % 3]
