@@ -908,7 +908,8 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   float* group_loss = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // KGREC_GROUP_STEP=0: the general kernel for every shape (A/B runs, tests); =3: three CTAs per SM
+  // KGREC_GROUP_STEP (A/B runs, tests): 0 = the general kernel for every shape; n = no row prefetch;
+  // p / q = prefetch level 1 / 2; 3 (TransE) / 2 (TransH) = fewer CTAs per SM
   const char* env = getenv("KGREC_GROUP_STEP");
   const bool small32 = n_neg <= 32 && static_cast<double>(n_pos) * (2 + n_neg) * tables->dim * 4 < 4.0e9 &&
                        static_cast<double>(n_pos) * n_neg < 2.0e9;          // 32-bit slot offsets, scores kept in lanes
@@ -919,10 +920,12 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
       k_group_step_e<L1V, DV, MV, 4, 2><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (env && env[0] == 'p')                                                                               \
       k_group_step_e<L1V, DV, MV, 4, 1><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+    else if (env && env[0] == 'n')                                                                               \
+      k_group_step_e<L1V, DV, MV, 4, 0><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (env && env[0] == '3')                                                                               \
       k_group_step_e<L1V, DV, MV, 3, 0><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else                                                                                                         \
-      k_group_step_e<L1V, DV, MV, 4, 0><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 4, 1><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
   }
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
     if (tables->l1) { if (dn) { if (mg) CALL_E(true, true, true) else CALL_E(true, true, false) } else { if (mg) CALL_E(true, false, true) else CALL_E(true, false, false) } }

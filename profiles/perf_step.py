@@ -14,7 +14,7 @@ for l1 in (False, True):
     torch.manual_seed(0)
     m = K.TransEModel(l1, 100, 100_000, 500)
     m.grad_mode = "sparse"
-    for env in ("p", "q", "p", "q"):
+    for env in ("n", "4", "q", "4"):
         os.environ["KGREC_GROUP_STEP"] = env
         def step(s):
             ix = sets[s % 3]
