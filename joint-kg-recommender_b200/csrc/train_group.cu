@@ -410,7 +410,7 @@ k_group_step(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
 //     group ahead and handed out by shuffles, so the request for row k+1 leaves as soon as row k's
 //     arithmetic starts (with per-negative id loads the row request waited a full L2 round trip:
 //     48 % of the stall samples).
-template <bool L1, bool DENSE, bool MARGIN, int MINB, int PF>
+template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
                float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
@@ -572,15 +572,6 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
         stg_f4_hint(reinterpret_cast<float4*>(grel_b + static_cast<uint32_t>(j) * d4), gr.x, gr.y, gr.z, gr.w, pol_stream);
       }
     }
-    if (PF >= 2 && jn < n_pos && lane < 5) {   // the next group's first rows (h, t, r and two negatives): ids arrived long ago
-      const int32_t c2 = __shfl_sync(0x1fu, cvn, lane >= 3 ? lane - 3 : 0);
-      const uint64_t id = lane < 3 ? static_cast<uint64_t>(pvn) : static_cast<uint64_t>(static_cast<uint32_t>(c2 < 0 ? ~c2 : c2));
-      const uint64_t rows = lane == 2 ? static_cast<uint64_t>(T.n_rel) : static_cast<uint64_t>(T.n_ent);
-      if (id < rows) {
-        const char* pr = reinterpret_cast<const char*>(lane == 2 ? T.rel : T.ent) + id * ld4;
-        for (uint32_t o = 0; o < d4; o += 128) prefetch_l1(pr + o);
-      }
-    }
   }
   if (bad && status) *status = 1;
 }
@@ -594,7 +585,7 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
 //   g_h = E_h - (E_h.w) w,  g_t = E_t - (E_t.w) w,  g_r = accT - accH + eps_p,
 //   g_w -= (E_h.w) h + (h.w) E_h + (E_t.w) t + (t.w) E_t.
 // The two reductions a negative needs after its residual (the score and g.w) share one shuffle tree.
-template <bool L1, bool DENSE, bool MARGIN, int MINB, int PF>
+template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
                float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
@@ -774,17 +765,6 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
         stg_f4_hint(reinterpret_cast<float4*>(gnrm_b + static_cast<uint32_t>(j) * d4), gwv.x, gwv.y, gwv.z, gwv.w, pol_stream);
       }
     }
-    if (PF >= 2 && jn < n_pos && lane < 6) {   // the next group's first rows: h, t, r, w and two negatives
-      const int32_t c2 = __shfl_sync(0x3fu, cvn, lane >= 4 ? lane - 4 : 0);
-      const int64_t pq = __shfl_sync(0x3fu, pvn, lane == 3 ? 2 : (lane < 3 ? lane : 0));
-      const uint64_t id = lane < 4 ? static_cast<uint64_t>(pq) : static_cast<uint64_t>(static_cast<uint32_t>(c2 < 0 ? ~c2 : c2));
-      const bool isrel = lane == 2 || lane == 3;
-      const uint64_t rows = isrel ? static_cast<uint64_t>(T.n_rel) : static_cast<uint64_t>(T.n_ent);
-      if (id < rows) {
-        const char* pr = reinterpret_cast<const char*>(lane == 2 ? T.rel : (lane == 3 ? T.norm : T.ent)) + id * ld4;
-        for (uint32_t o = 0; o < d4; o += 128) prefetch_l1(pr + o);
-      }
-    }
   }
   if (bad && status) *status = 1;
 }
@@ -909,23 +889,19 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
   float* group_loss = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // KGREC_GROUP_STEP (A/B runs, tests): 0 = the general kernel for every shape; n = no row prefetch;
-  // p / q = prefetch level 1 / 2; 3 (TransE) / 2 (TransH) = fewer CTAs per SM
+  // 3 (TransE) / 2 (TransH) = fewer CTAs per SM, no prefetch
   const char* env = getenv("KGREC_GROUP_STEP");
   const bool small32 = n_neg <= 32 && static_cast<double>(n_pos) * (2 + n_neg) * tables->dim * 4 < 4.0e9 &&
                        static_cast<double>(n_pos) * n_neg < 2.0e9;          // 32-bit slot offsets, scores kept in lanes
   if (pl.fam == FAM_E && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
 #define CALL_E(L1V, DV, MV)                                                                                      \
   {                                                                                                              \
-    if (env && env[0] == 'q')                                                                                    \
-      k_group_step_e<L1V, DV, MV, 4, 2><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
-    else if (env && env[0] == 'p')                                                                               \
-      k_group_step_e<L1V, DV, MV, 4, 1><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
-    else if (env && env[0] == 'n')                                                                               \
-      k_group_step_e<L1V, DV, MV, 4, 0><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+    if (env && env[0] == 'n')                                                                                    \
+      k_group_step_e<L1V, DV, MV, 4, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (env && env[0] == '3')                                                                               \
-      k_group_step_e<L1V, DV, MV, 3, 0><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 3, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else                                                                                                         \
-      k_group_step_e<L1V, DV, MV, 4, 1><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 4, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
   }
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
     if (tables->l1) { if (dn) { if (mg) CALL_E(true, true, true) else CALL_E(true, true, false) } else { if (mg) CALL_E(true, false, true) else CALL_E(true, false, false) } }
@@ -934,14 +910,12 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
   } else if (pl.fam == FAM_H && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
 #define CALL_H(L1V, DV, MV)                                                                                      \
   {                                                                                                              \
-    if (env && env[0] == 'q')                                                                                    \
-      k_group_step_h<L1V, DV, MV, 3, 2><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
-    else if (env && env[0] == 'p')                                                                               \
-      k_group_step_h<L1V, DV, MV, 3, 1><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+    if (env && env[0] == 'n')                                                                                    \
+      k_group_step_h<L1V, DV, MV, 3, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (env && env[0] == '2')                                                                               \
-      k_group_step_h<L1V, DV, MV, 2, 0><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, MV, 2, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else                                                                                                         \
-      k_group_step_h<L1V, DV, MV, 3, 0><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, MV, 3, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
   }
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
     if (tables->l1) { if (dn) { if (mg) CALL_H(true, true, true) else CALL_H(true, true, false) } else { if (mg) CALL_H(true, false, true) else CALL_H(true, false, false) } }

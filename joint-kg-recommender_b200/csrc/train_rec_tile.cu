@@ -15,7 +15,10 @@
 //   * pass F (the [P, d] table gradients, a [P x M] . [M x d] contraction over the tile): a
 //     thread owns a (16-byte column chunk, half of the preferences) register tile that stays
 //     in registers over all the tiles of the CTA and is flushed once with red.global.add.v4.
-// Row gradients are staged in shared memory and leave as whole coalesced rows.
+// Row gradients are staged in shared memory and leave as whole coalesced rows (with the COO row id
+// of every slot).  Rows arrive by cp.async, every contraction is packed FFMA2, and in MODE_STEP a
+// warp's 16 rows hold whole (positive, negatives) groups so that one launch does forward, ranking
+// loss and backward (kgrec_rank_loss_step).  Measurements and the ncu reading: DESIGN.md 4.1.
 #include <cstdlib>
 #include "train_dev.cuh"
 
@@ -75,14 +78,8 @@ __device__ __forceinline__ void axpy4p(float2& ylo, float2& yhi, const float2& a
   ylo = __ffma2_rn(aa, lo(x), ylo);
   yhi = __ffma2_rn(aa, hi(x), yhi);
 }
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
-}
 __device__ __forceinline__ float dot4acc(const float4& a, const float4& b, float acc) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
-}
-__device__ __forceinline__ void axpy4(float4& y, float a, const float4& x) {
-  y.x = fmaf(a, x.x, y.x); y.y = fmaf(a, x.y, y.y); y.z = fmaf(a, x.z, y.z); y.w = fmaf(a, x.w, y.w);
 }
 
 // upstream dLoss/dscore of flat pair i, one thread (train_dev.cuh upstream_grad is its warp form)

@@ -1,4 +1,4 @@
-"""k_group_step A/B timing (CUDA events): KGREC_GROUP_STEP = 0 (general kernel) | 3 | 4 (issue-optimised, CTAs per SM)"""
+"""k_group_step A/B timing (CUDA events): KGREC_GROUP_STEP = 0 (general kernel) | n (issue-optimised kernel, no row prefetch) | other (default)"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "joint-kg-recommender_b200")]
@@ -14,7 +14,7 @@ for l1 in (False, True):
     torch.manual_seed(0)
     m = K.TransEModel(l1, 100, 100_000, 500)
     m.grad_mode = "sparse"
-    for env in ("n", "4", "q", "4"):
+    for env in ("n", "4"):
         os.environ["KGREC_GROUP_STEP"] = env
         def step(s):
             ix = sets[s % 3]
@@ -35,7 +35,7 @@ for l1 in (False, True):
     torch.manual_seed(0)
     m = K.TransHModel(l1, 100, 100_000, 500)
     m.grad_mode = "sparse"
-    for env in ("3", "p", "q", "p"):
+    for env in ("0", "n", "3"):
         os.environ["KGREC_GROUP_STEP"] = env
         def step(s):
             ix = sets[s % 3]
