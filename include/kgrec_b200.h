@@ -216,11 +216,16 @@ int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model,
  * slot_ent_ids [n_pos * (2 + n_neg)] / slot_rel_ids [n_pos] (optional, int64): the table row of every
  * gradient slot, i.e. the index array of the sparse COO gradient whose values the slots are
  * (torch.sparse_coo_tensor(ids, slots)); written by the same pass so that no host-side index
- * building is left in a training step. */
+ * building is left in a training step.
+ * reg_flags = 1 adds the KG drivers' regularisers to each batch loss and to the gradients
+ * (knowledge_representation.py:197-204): normLoss (loss.py:21-23) over the entity rows of
+ * cat[ph, pt, nh, nt] and the relation rows of cat[pr, nr], and for TransH orthogonalLoss
+ * (loss.py:18-19) over (rel, norm) rows of cat[pr, nr] -- every row with the multiplicity it has in
+ * those lists.  Margin loss and embedding_size <= 128 only. */
 int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model,
                             const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
                             const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
-                            int loss_kind, float margin_or_target, float grad_loss,
+                            int loss_kind, float margin_or_target, float grad_loss, int32_t reg_flags,
                             float* pos_scores, float* neg_scores, float* loss,
                             const kgrec_grads* grads, int64_t* slot_ent_ids, int64_t* slot_rel_ids,
                             void* workspace, int32_t* status, kgrec_stream_t stream);

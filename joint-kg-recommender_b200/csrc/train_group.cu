@@ -410,7 +410,7 @@ k_group_step(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
 //     group ahead and handed out by shuffles, so the request for row k+1 leaves as soon as row k's
 //     arithmetic starts (with per-negative id loads the row request waited a full L2 round trip:
 //     48 % of the stall samples).
-template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF>
+template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
                float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
@@ -496,11 +496,32 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
     float lsum = 0.f, cpos = 0.f, mys = 0.f;
     float4 accT = z4, accH = z4;
     uint32_t goff = (static_cast<uint32_t>(j) * (2 + K) + 2) * d4;      // byte offset of the first corrupted-row slot
+    // REG: the drivers' regulariser normLoss over the rows the batch gathers (loss.py:21-23 on
+    // cat[ph, pt, nh, nt] and cat[pr, nr], knowledge_representation.py:197-204): sum max(|row|^2 - 1, 0)
+    // with the multiplicity each row has in those lists; the rows are in registers already.
+    [[maybe_unused]] float nh2 = 0.f, nt2 = 0.f, nr2 = 0.f, lreg = 0.f, n_tail = 0.f;
+    [[maybe_unused]] const float r2 = 2.f * up0;
+    if (REG) {
+      nh2 = h.x * h.x + h.y * h.y + h.z * h.z + h.w * h.w;
+      nt2 = t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+      nr2 = r.x * r.x + r.y * r.y + r.z * r.z + r.w * r.w;
+      warp_sum2(nh2, nt2);
+      nr2 = warp_sum(nr2);
+    }
 
     auto negative = [&](const float4& x, const bool head, const uint32_t id, const int k) {
       const float4 B = head ? bt : bh;
       const float4 e = make_float4(B.x - x.x, B.y - x.y, B.z - x.z, B.w - x.w);
-      const float sn = warp_sum(dist_term(e.x, L1) + dist_term(e.y, L1) + dist_term(e.z, L1) + dist_term(e.w, L1));
+      float sn = dist_term(e.x, L1) + dist_term(e.y, L1) + dist_term(e.z, L1) + dist_term(e.w, L1);
+      [[maybe_unused]] float nx2 = 0.f;
+      if (REG) {
+        nx2 = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        warp_sum2(sn, nx2);
+        lreg += fmaxf(nx2 - 1.f, 0.f);
+        n_tail += head ? 0.f : 1.f;
+      } else {
+        sn = warp_sum(sn);
+      }
       if (lane == k) mys = sn;
       float coef;      // -(dLoss/dsn): the corrupted row's gradient is coef * dL(e')/de'
       if (MARGIN) {
@@ -515,16 +536,20 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
         cpos += dp;
         coef = dp * up;
       }
-      if (coef != 0.f) {                    // warp-uniform: an inactive hinge has no gradient
-        float4 gc;                          // = -eps'
-        if (L1) {
-          gc = make_float4(coef * ddist_term(e.x, 1), coef * ddist_term(e.y, 1), coef * ddist_term(e.z, 1), coef * ddist_term(e.w, 1));
-        } else {
-          const float c2 = 2.f * coef;
-          gc = make_float4(c2 * e.x, c2 * e.y, c2 * e.z, c2 * e.w);
+      const bool regx = REG && nx2 > 1.f;
+      if (coef != 0.f || regx) {            // warp-uniform: an inactive hinge has no gradient
+        float4 gc = z4;                     // = -eps' (+ the regulariser's 2 x)
+        if (coef != 0.f) {
+          if (L1) {
+            gc = make_float4(coef * ddist_term(e.x, 1), coef * ddist_term(e.y, 1), coef * ddist_term(e.z, 1), coef * ddist_term(e.w, 1));
+          } else {
+            const float c2 = 2.f * coef;
+            gc = make_float4(c2 * e.x, c2 * e.y, c2 * e.z, c2 * e.w);
+          }
+          if (head) { accH.x -= gc.x; accH.y -= gc.y; accH.z -= gc.z; accH.w -= gc.w; }
+          else { accT.x -= gc.x; accT.y -= gc.y; accT.z -= gc.z; accT.w -= gc.w; }
         }
-        if (head) { accH.x -= gc.x; accH.y -= gc.y; accH.z -= gc.z; accH.w -= gc.w; }
-        else { accT.x -= gc.x; accT.y -= gc.y; accT.z -= gc.z; accT.w -= gc.w; }
+        if (regx) { gc.x = fmaf(r2, x.x, gc.x); gc.y = fmaf(r2, x.y, gc.y); gc.z = fmaf(r2, x.z, gc.z); gc.w = fmaf(r2, x.w, gc.w); }
         if (act) {
           if (DENSE) red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(id) * d4), gc.x, gc.y, gc.z, gc.w);
           else stg_f4_hint(reinterpret_cast<float4*>(gent_b + goff), gc.x, gc.y, gc.z, gc.w, pol_stream);
@@ -552,12 +577,20 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
     // the positive's own contribution, with the coefficient summed over its negatives
     const float cp = cpos * up;
     const float4 eps = make_float4(cp * ddist_term(ep.x, L1), cp * ddist_term(ep.y, L1), cp * ddist_term(ep.z, L1), cp * ddist_term(ep.w, L1));
-    const float4 gh = make_float4(accT.x + eps.x, accT.y + eps.y, accT.z + eps.z, accT.w + eps.w);
-    const float4 gt = make_float4(accH.x - eps.x, accH.y - eps.y, accH.z - eps.z, accH.w - eps.w);
-    const float4 gr = make_float4(accT.x - accH.x + eps.x, accT.y - accH.y + eps.y, accT.z - accH.z + eps.z, accT.w - accH.w + eps.w);
+    float4 gh = make_float4(accT.x + eps.x, accT.y + eps.y, accT.z + eps.z, accT.w + eps.w);
+    float4 gt = make_float4(accH.x - eps.x, accH.y - eps.y, accH.z - eps.z, accH.w - eps.w);
+    float4 gr = make_float4(accT.x - accH.x + eps.x, accT.y - accH.y + eps.y, accT.z - accH.z + eps.z, accT.w - accH.w + eps.w);
+    if (REG) {      // h is listed once as ph and once per tail-replaced negative (nh); t likewise; r once per triple
+      const float mh = 1.f + n_tail, mt = 1.f + (static_cast<float>(K) - n_tail), mr = 1.f + static_cast<float>(K);
+      lreg += mh * fmaxf(nh2 - 1.f, 0.f) + mt * fmaxf(nt2 - 1.f, 0.f) + mr * fmaxf(nr2 - 1.f, 0.f);
+      const float ch = nh2 > 1.f ? mh * r2 : 0.f, ct = nt2 > 1.f ? mt * r2 : 0.f, cr = nr2 > 1.f ? mr * r2 : 0.f;
+      gh.x = fmaf(ch, h.x, gh.x); gh.y = fmaf(ch, h.y, gh.y); gh.z = fmaf(ch, h.z, gh.z); gh.w = fmaf(ch, h.w, gh.w);
+      gt.x = fmaf(ct, t.x, gt.x); gt.y = fmaf(ct, t.y, gt.y); gt.z = fmaf(ct, t.z, gt.z); gt.w = fmaf(ct, t.w, gt.w);
+      gr.x = fmaf(cr, r.x, gr.x); gr.y = fmaf(cr, r.y, gr.y); gr.z = fmaf(cr, r.z, gr.z); gr.w = fmaf(cr, r.w, gr.w);
+    }
     if (lane == 0) {
       pos_scores[j] = sp;
-      group_loss[j] = lsum;
+      group_loss[j] = lsum + (REG ? lreg : 0.f);
     }
     if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
     if (act) {
@@ -585,7 +618,7 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
 //   g_h = E_h - (E_h.w) w,  g_t = E_t - (E_t.w) w,  g_r = accT - accH + eps_p,
 //   g_w -= (E_h.w) h + (h.w) E_h + (E_t.w) t + (t.w) E_t.
 // The two reductions a negative needs after its residual (the score and g.w) share one shuffle tree.
-template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF>
+template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
                float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
@@ -675,6 +708,18 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
     float lsum = 0.f, cpos = 0.f, mys = 0.f, sT = 0.f, sH = 0.f;
     float4 accT = z4, accH = z4, gwv = z4;
     uint32_t goff = (static_cast<uint32_t>(j) * (2 + K) + 2) * d4;
+    // REG: normLoss over the gathered entity / relation rows and orthogonalLoss(rel, norm) (loss.py:18-23,
+    // knowledge_representation.py:197-204), with each row's multiplicity in the driver's lists
+    [[maybe_unused]] float nh2 = 0.f, nt2 = 0.f, nr2 = 0.f, wr = 0.f, lreg = 0.f, n_tail = 0.f;
+    [[maybe_unused]] const float r2 = 2.f * up0;
+    if (REG) {
+      nh2 = dot4(h, h);
+      nt2 = dot4(t, t);
+      nr2 = dot4(r, r);
+      wr = dot4(w, r);
+      warp_sum2(nh2, nt2);
+      warp_sum2(nr2, wr);
+    }
 
     auto negative = [&](const float4& x, const bool head, const uint32_t id, const int k) {
       const float ax = warp_sum(dot4(x, w));
@@ -684,6 +729,12 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
       float sn = dist_term(e.x, L1) + dist_term(e.y, L1) + dist_term(e.z, L1) + dist_term(e.w, L1);
       float dw = dot4(dd, w);
       warp_sum2(sn, dw);
+      [[maybe_unused]] float nx2 = 0.f;
+      if (REG) {
+        nx2 = warp_sum(dot4(x, x));
+        lreg += fmaxf(nx2 - 1.f, 0.f);
+        n_tail += head ? 0.f : 1.f;
+      }
       if (lane == k) mys = sn;
       float coef;
       if (MARGIN) {
@@ -698,17 +749,22 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
         cpos += dp;
         coef = dp * up;
       }
-      if (coef != 0.f) {
-        const float c = L1 ? coef : 2.f * coef;
-        const float4 g = make_float4(c * dd.x, c * dd.y, c * dd.z, c * dd.w);       // -eps' at proj(x)
-        const float gdw = c * dw;                                                   // g . w
-        const float4 gx = make_float4(fmaf(-gdw, w.x, g.x), fmaf(-gdw, w.y, g.y), fmaf(-gdw, w.z, g.z), fmaf(-gdw, w.w, g.w));
-        gwv.x = fmaf(-gdw, x.x, fmaf(-ax, g.x, gwv.x));
-        gwv.y = fmaf(-gdw, x.y, fmaf(-ax, g.y, gwv.y));
-        gwv.z = fmaf(-gdw, x.z, fmaf(-ax, g.z, gwv.z));
-        gwv.w = fmaf(-gdw, x.w, fmaf(-ax, g.w, gwv.w));
-        if (head) { accH.x -= g.x; accH.y -= g.y; accH.z -= g.z; accH.w -= g.w; sH -= gdw; }
-        else { accT.x -= g.x; accT.y -= g.y; accT.z -= g.z; accT.w -= g.w; sT -= gdw; }
+      const bool regx = REG && nx2 > 1.f;
+      if (coef != 0.f || regx) {
+        float4 gx = z4;
+        if (coef != 0.f) {
+          const float c = L1 ? coef : 2.f * coef;
+          const float4 g = make_float4(c * dd.x, c * dd.y, c * dd.z, c * dd.w);       // -eps' at proj(x)
+          const float gdw = c * dw;                                                   // g . w
+          gx = make_float4(fmaf(-gdw, w.x, g.x), fmaf(-gdw, w.y, g.y), fmaf(-gdw, w.z, g.z), fmaf(-gdw, w.w, g.w));
+          gwv.x = fmaf(-gdw, x.x, fmaf(-ax, g.x, gwv.x));
+          gwv.y = fmaf(-gdw, x.y, fmaf(-ax, g.y, gwv.y));
+          gwv.z = fmaf(-gdw, x.z, fmaf(-ax, g.z, gwv.z));
+          gwv.w = fmaf(-gdw, x.w, fmaf(-ax, g.w, gwv.w));
+          if (head) { accH.x -= g.x; accH.y -= g.y; accH.z -= g.z; accH.w -= g.w; sH -= gdw; }
+          else { accT.x -= g.x; accT.y -= g.y; accT.z -= g.z; accT.w -= g.w; sT -= gdw; }
+        }
+        if (regx) { gx.x = fmaf(r2, x.x, gx.x); gx.y = fmaf(r2, x.y, gx.y); gx.z = fmaf(r2, x.z, gx.z); gx.w = fmaf(r2, x.w, gx.w); }
         if (act) {
           if (DENSE) red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(id) * d4), gx.x, gx.y, gx.z, gx.w);
           else stg_f4_hint(reinterpret_cast<float4*>(gent_b + goff), gx.x, gx.y, gx.z, gx.w, pol_stream);
@@ -739,16 +795,28 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
     const float4 EH = make_float4(accT.x + eps.x, accT.y + eps.y, accT.z + eps.z, accT.w + eps.w);
     const float4 ET = make_float4(accH.x - eps.x, accH.y - eps.y, accH.z - eps.z, accH.w - eps.w);
     const float eh = sT + epw, et = sH - epw;
-    const float4 gh = make_float4(fmaf(-eh, w.x, EH.x), fmaf(-eh, w.y, EH.y), fmaf(-eh, w.z, EH.z), fmaf(-eh, w.w, EH.w));
-    const float4 gt = make_float4(fmaf(-et, w.x, ET.x), fmaf(-et, w.y, ET.y), fmaf(-et, w.z, ET.z), fmaf(-et, w.w, ET.w));
-    const float4 gr = make_float4(accT.x - accH.x + eps.x, accT.y - accH.y + eps.y, accT.z - accH.z + eps.z, accT.w - accH.w + eps.w);
+    float4 gh = make_float4(fmaf(-eh, w.x, EH.x), fmaf(-eh, w.y, EH.y), fmaf(-eh, w.z, EH.z), fmaf(-eh, w.w, EH.w));
+    float4 gt = make_float4(fmaf(-et, w.x, ET.x), fmaf(-et, w.y, ET.y), fmaf(-et, w.z, ET.z), fmaf(-et, w.w, ET.w));
+    float4 gr = make_float4(accT.x - accH.x + eps.x, accT.y - accH.y + eps.y, accT.z - accH.z + eps.z, accT.w - accH.w + eps.w);
     gwv.x -= fmaf(eh, h.x, a * EH.x) + fmaf(et, t.x, b * ET.x);
     gwv.y -= fmaf(eh, h.y, a * EH.y) + fmaf(et, t.y, b * ET.y);
     gwv.z -= fmaf(eh, h.z, a * EH.z) + fmaf(et, t.z, b * ET.z);
     gwv.w -= fmaf(eh, h.w, a * EH.w) + fmaf(et, t.w, b * ET.w);
+    if (REG) {
+      const float mh = 1.f + n_tail, mt = 1.f + (static_cast<float>(K) - n_tail), mr = 1.f + static_cast<float>(K);
+      const float inv = nr2 > 0.f ? 1.f / nr2 : 0.f, q = wr * inv;                       // (w.r) / |r|^2
+      lreg += mh * fmaxf(nh2 - 1.f, 0.f) + mt * fmaxf(nt2 - 1.f, 0.f) + mr * (fmaxf(nr2 - 1.f, 0.f) + wr * q);
+      const float ch = nh2 > 1.f ? mh * r2 : 0.f, ct = nt2 > 1.f ? mt * r2 : 0.f;
+      const float cr = (nr2 > 1.f ? mr * r2 : 0.f) - mr * r2 * q * q, cw = mr * r2 * q;   // d/dr, d/dw of (w.r)^2 / |r|^2
+      gh.x = fmaf(ch, h.x, gh.x); gh.y = fmaf(ch, h.y, gh.y); gh.z = fmaf(ch, h.z, gh.z); gh.w = fmaf(ch, h.w, gh.w);
+      gt.x = fmaf(ct, t.x, gt.x); gt.y = fmaf(ct, t.y, gt.y); gt.z = fmaf(ct, t.z, gt.z); gt.w = fmaf(ct, t.w, gt.w);
+      gr.x = fmaf(cr, r.x, fmaf(cw, w.x, gr.x)); gr.y = fmaf(cr, r.y, fmaf(cw, w.y, gr.y));
+      gr.z = fmaf(cr, r.z, fmaf(cw, w.z, gr.z)); gr.w = fmaf(cr, r.w, fmaf(cw, w.w, gr.w));
+      gwv.x = fmaf(cw, r.x, gwv.x); gwv.y = fmaf(cw, r.y, gwv.y); gwv.z = fmaf(cw, r.z, gwv.z); gwv.w = fmaf(cw, r.w, gwv.w);
+    }
     if (lane == 0) {
       pos_scores[j] = sp;
-      group_loss[j] = lsum;
+      group_loss[j] = lsum + (REG ? lreg : 0.f);
     }
     if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
     if (act) {
@@ -871,7 +939,7 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
 extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, const void* ph, const void* pt,
                                        const void* pr, int idx_bytes, int64_t n_pos, const int32_t* corrupt,
                                        int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
-                                       float grad_loss, float* pos_scores, float* neg_scores, float* loss,
+                                       float grad_loss, int32_t reg_flags, float* pos_scores, float* neg_scores, float* loss,
                                        const kgrec_grads* grads, int64_t* slot_ent_ids, int64_t* slot_rel_ids,
                                        void* workspace, int32_t* status, kgrec_stream_t stream) {
   Plan pl;
@@ -888,6 +956,8 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   float* group_loss = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (reg_flags != 0 && reg_flags != 1) { set_error("reg_flags must be 0 or 1"); return KGREC_ERR_INVALID; }
+  if (reg_flags && loss_kind != KGREC_LOSS_MARGIN) { set_error("fused regularisers go with the margin loss (the KG drivers' loss)"); return KGREC_ERR_UNSUPPORTED; }
   // KGREC_GROUP_STEP (A/B runs, tests): 0 = the general kernel for every shape; n = no row prefetch;
   // 3 (TransE) / 2 (TransH) = fewer CTAs per SM, no prefetch
   const char* env = getenv("KGREC_GROUP_STEP");
@@ -897,11 +967,13 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
 #define CALL_E(L1V, DV, MV)                                                                                      \
   {                                                                                                              \
     if (env && env[0] == 'n')                                                                                    \
-      k_group_step_e<L1V, DV, MV, 4, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 4, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (env && env[0] == '3')                                                                               \
-      k_group_step_e<L1V, DV, MV, 3, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 3, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+    else if (MV && reg_flags)                                                                                    \
+      k_group_step_e<L1V, DV, true, 4, true, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else                                                                                                         \
-      k_group_step_e<L1V, DV, MV, 4, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 4, true, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
   }
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
     if (tables->l1) { if (dn) { if (mg) CALL_E(true, true, true) else CALL_E(true, true, false) } else { if (mg) CALL_E(true, false, true) else CALL_E(true, false, false) } }
@@ -911,17 +983,20 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
 #define CALL_H(L1V, DV, MV)                                                                                      \
   {                                                                                                              \
     if (env && env[0] == 'n')                                                                                    \
-      k_group_step_h<L1V, DV, MV, 3, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, MV, 3, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (env && env[0] == '2')                                                                               \
-      k_group_step_h<L1V, DV, MV, 2, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, MV, 2, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+    else if (MV && reg_flags)                                                                                    \
+      k_group_step_h<L1V, DV, true, 3, true, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else                                                                                                         \
-      k_group_step_h<L1V, DV, MV, 3, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, MV, 3, true, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
   }
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
     if (tables->l1) { if (dn) { if (mg) CALL_H(true, true, true) else CALL_H(true, true, false) } else { if (mg) CALL_H(true, false, true) else CALL_H(true, false, false) } }
     else { if (dn) { if (mg) CALL_H(false, true, true) else CALL_H(false, true, false) } else { if (mg) CALL_H(false, false, true) else CALL_H(false, false, false) } }
 #undef CALL_H
   } else {
+    if (reg_flags) { set_error("fused regularisers are built for the d <= 128 margin-loss step kernels only"); return KGREC_ERR_UNSUPPORTED; }
 #define CALL(FAMV, NCHV)                                                                                        \
   if (tables->l1) k_group_step<FAMV, NCHV, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status); \
   else k_group_step<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, status);

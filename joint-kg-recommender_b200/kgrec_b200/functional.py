@@ -343,7 +343,7 @@ def encode_corrupt(pos, neg):
     return c.contiguous().view(-1)
 
 
-def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, param, status, grad_loss=1.0):
+def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, param, status, grad_loss=1.0, reg=False):
     """Scores, per-batch losses and gradients of grad_loss * sum(loss) in one kernel
     (kgrec_corrupt_loss_step).  Returns (loss, pos_scores, neg_scores, {table: grad})."""
     names = MODEL_TABLES[cfg.model]
@@ -372,8 +372,8 @@ def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, p
     lib = _lib.load()
     _lib.check(lib.kgrec_corrupt_loss_step(
         C.byref(T), cfg.model, _ptr(ph), _ptr(pt), _ptr(pr), _idx_bytes(ph, pt, pr), n_pos, _ptr(corrupt), n_neg,
-        batch_pos, loss_kind, float(param), float(grad_loss), _ptr(pos_s), _ptr(neg_s), _ptr(loss), C.byref(g),
-        _ptr(ent_ids), _ptr(rel_ids), _ptr(ws), _ptr(status), _stream()))
+        batch_pos, loss_kind, float(param), float(grad_loss), 1 if reg else 0, _ptr(pos_s), _ptr(neg_s), _ptr(loss),
+        C.byref(g), _ptr(ent_ids), _ptr(rel_ids), _ptr(ws), _ptr(status), _stream()))
     count_launches(2)
     grads = {}
     for name in names:

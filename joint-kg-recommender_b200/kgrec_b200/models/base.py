@@ -151,7 +151,7 @@ class KGRecModule(nn.Module):
                                             batch_pos or n_pos, kind, param, self._status_buf(dev),
                                             *self._tables_for(model))
 
-    def _loss_step_corrupt(self, model, pos, corrupt, loss, param, batch_pos=None, grad_loss=1.0):
+    def _loss_step_corrupt(self, model, pos, corrupt, loss, param, batch_pos=None, grad_loss=1.0, reg=False):
         dev = self._require_cuda()
         pos = tuple(KF.as_index(x, dev) for x in pos)
         corrupt = corrupt.to(dev, torch.int32, non_blocking=True).contiguous().view(-1)
@@ -163,7 +163,7 @@ class KGRecModule(nn.Module):
         w = self._weights()
         out, ps, ns, grads = KF.corrupt_loss_step(self._cfg(model, 0), {k: w[k] for k in names}, pos, corrupt,
                                                   corrupt.numel() // n_pos, batch_pos or n_pos, kind, param,
-                                                  self._status_buf(dev), grad_loss)
+                                                  self._status_buf(dev), grad_loss, reg)
         for k in names:          # what loss.sum().backward() would have left in .grad
             p = w[k]
             if p.requires_grad:

@@ -93,9 +93,10 @@ class jTransUPModel(RecModelBase):
     def kg_rank_loss_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None):
         return self._rank_loss_corrupt(_lib.TRANSH, pos, corrupt, loss, margin, batch_pos)
 
-    def kg_loss_step_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None, grad_loss=1.0):
-        """KG branch forward + loss + backward in one kernel (the TransH group kernel on ent / rel / norm)."""
-        return self._loss_step_corrupt(_lib.TRANSH, pos, corrupt, loss, margin, batch_pos, grad_loss)
+    def kg_loss_step_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None, grad_loss=1.0, reg=False):
+        """KG branch forward + loss + backward in one kernel (the TransH group kernel on ent / rel / norm);
+        grad_loss carries kg_lambda, reg the regularisers (knowledgable_recommendation.py:368-383)."""
+        return self._loss_step_corrupt(_lib.TRANSH, pos, corrupt, loss, margin, batch_pos, grad_loss, reg)
 
     # -- evaluation ----------------------------------------------------------------------------
     def _rec_catalog(self):

@@ -41,12 +41,15 @@ class KGModelBase(KGRecModule):
         Reads and writes (3 + K) rows per group instead of 3 (1 + K).  TransE / TransH."""
         return self._rank_loss_corrupt(self.MODEL, pos, corrupt, loss, margin, batch_pos)
 
-    def loss_step_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None, grad_loss=1.0):
+    def loss_step_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None, grad_loss=1.0, reg=False):
         """rank_loss_corrupt(...) followed by (grad_loss * loss.sum()).backward(), in ONE kernel:
         returns (loss per batch, pos_scores, neg_scores) and leaves the gradients in .grad
         (accumulating like autograd does).  Use when nothing else feeds the ranking-loss term's
-        upstream -- the case in all the reference drivers, which call backward() on the loss."""
-        return self._loss_step_corrupt(self.MODEL, pos, corrupt, loss, margin, batch_pos, grad_loss)
+        upstream -- the case in all the reference drivers, which call backward() on the loss.
+        reg=True: the loss of knowledge_representation.py:189-204 in full -- the ranking loss plus
+        normLoss over the gathered entity / relation rows (and orthogonalLoss for TransH) -- values
+        and gradients from the same kernel pass."""
+        return self._loss_step_corrupt(self.MODEL, pos, corrupt, loss, margin, batch_pos, grad_loss, reg)
 
     # -- evaluation: [B, ent_total] matrices for the unchanged drivers ---------------------
     def _catalog(self):

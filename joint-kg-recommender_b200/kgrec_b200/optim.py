@@ -35,9 +35,10 @@ class SparseRowOptimizer:
         self.s2 = {k: torch.zeros_like(w[k]) for k in self.names} if self.kind == 2 else {k: None for k in self.names}
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
 
-    def step_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None):
+    def step_corrupt(self, pos, corrupt, margin=1.0, loss="margin", batch_pos=None, reg=False):
         """One training step on positives (h, t, r) and group-compact negatives; returns the
-        per-batch losses (device tensor; nothing synchronises)."""
+        per-batch losses (device tensor; nothing synchronises).  reg=True adds the KG drivers'
+        normLoss / orthogonalLoss regularisers inside the same kernel (kgrec_corrupt_loss_step)."""
         m = self.model
         if m.MODEL not in (_lib.TRANSE, _lib.TRANSH):
             raise NotImplementedError("SparseRowOptimizer.step_corrupt is built for TransE / TransH")
@@ -67,7 +68,7 @@ class SparseRowOptimizer:
         rel_ids = torch.empty(n_pos, dtype=torch.int64, device=dev)
         _lib.check(lib.kgrec_corrupt_loss_step(
             C.byref(T), m.MODEL, ptr(pos[0]), ptr(pos[1]), ptr(pos[2]), pos[0].element_size(), n_pos, ptr(corrupt),
-            n_neg, bp, kind, float(margin), 1.0, ptr(pos_s), ptr(neg_s), ptr(out), C.byref(g), ptr(ent_ids), ptr(rel_ids),
+            n_neg, bp, kind, float(margin), 1.0, 1 if reg else 0, ptr(pos_s), ptr(neg_s), ptr(out), C.byref(g), ptr(ent_ids), ptr(rel_ids),
             ptr(ws), ptr(m._status_buf(dev)), stream))
         KF.count_launches(2)
         ids = {"ent": ent_ids, "rel": rel_ids, "norm": rel_ids}

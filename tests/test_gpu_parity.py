@@ -398,6 +398,60 @@ def test_rec_tile_engine_large(d, P, gumbel, l1, ktup):
             assert torch.allclose(got[k], two_pass[k], rtol=2e-3, atol=1e-4 * max(1.0, float(two_pass[k].abs().max())))
 
 
+@pytest.mark.parametrize("cls_name", ["TransEModel", "TransHModel"])
+@pytest.mark.parametrize("l1", [False, True])
+def test_step_with_fused_regularisers(cls_name, l1):
+    """loss_step_corrupt(reg=True) == the loss of knowledge_representation.py:189-204 built from the
+    autograd ranking loss plus torch normLoss / orthogonalLoss on the rows the driver gathers."""
+    import kgrec_b200 as K
+    torch.manual_seed(21)
+    rng = np.random.RandomState(21)
+    d, E, R, n_pos, Kn, bp = 100, 900, 7, 1531, 3, 512
+    m = getattr(K, cls_name)(l1, d, E, R)
+    with torch.no_grad():          # off the kink of max(|x|^2 - 1, 0): half of the rows above 1, half below
+        scale = torch.where(torch.arange(E, device=dev()) % 2 == 0, 1.05, 0.95).view(-1, 1)
+        m.ent_embeddings.weight.mul_(scale)
+        m.rel_embeddings.weight.mul_(torch.where(torch.arange(R, device=dev()) % 2 == 0, 1.07, 0.9).view(-1, 1))
+    h, t, r = rng.randint(0, E, n_pos), rng.randint(0, E, n_pos), rng.randint(0, R, n_pos)
+    ce = rng.randint(0, E, n_pos * Kn)
+    head = rng.rand(n_pos * Kn) < 0.4
+    corrupt = torch.as_tensor(np.where(head, ~ce, ce).astype(np.int32), device=dev())
+    nh = np.where(head, ce, np.repeat(h, Kn))
+    nt = np.where(head, np.repeat(t, Kn), ce)
+    nr = np.repeat(r, Kn)
+    pos = (lt(h), lt(t), lt(r))
+    m.grad_mode = "dense"
+    m.zero_grad()
+    l, _, _ = m.rank_loss_corrupt(pos, corrupt, margin=1.0, batch_pos=bp)
+
+    def norm_loss(x):
+        return torch.clamp((x ** 2).sum(1) - 1.0, min=0).sum()
+    nb = (n_pos + bp - 1) // bp
+    regs = []
+    for b in range(nb):
+        ps, ns = slice(b * bp, (b + 1) * bp), slice(b * bp * Kn, (b + 1) * bp * Kn)
+        er = m.ent_embeddings(lt(np.concatenate([h[ps], t[ps], nh[ns], nt[ns]])))
+        rr_ids = lt(np.concatenate([r[ps], nr[ns]]))
+        rr = m.rel_embeddings(rr_ids)
+        reg = norm_loss(er) + norm_loss(rr)
+        if cls_name == "TransHModel":
+            w = m.norm_embeddings(rr_ids)
+            reg = reg + (((w * rr).sum(1) ** 2) / (rr ** 2).sum(1)).sum()
+        regs.append(reg)
+    regs = torch.stack(regs)
+    (l + regs).sum().backward()
+    want = {k: v.clone() for k, v in grads_by_name(m).items()}
+    want_loss = (l + regs).detach()
+    for gm in ("dense", "sparse"):
+        m.grad_mode = gm
+        m.zero_grad()
+        sl, _, _ = m.loss_step_corrupt(pos, corrupt, margin=1.0, batch_pos=bp, reg=True)
+        assert torch.allclose(sl, want_loss, rtol=2e-4), (sl, want_loss)
+        got = grads_by_name(m)
+        for k in want:
+            assert torch.allclose(got[k], want[k], rtol=2e-3, atol=2e-4 * max(1.0, float(want[k].abs().max()))), k
+
+
 def test_rank_loss_step_other_shapes():
     """kgrec_rank_loss_step outside the single-pass kernel's shapes (KG model; many negatives) falls
     back to forward + backward kernels behind the same call."""
