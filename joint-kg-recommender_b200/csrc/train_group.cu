@@ -410,11 +410,14 @@ k_group_step(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
 //     group ahead and handed out by shuffles, so the request for row k+1 leaves as soon as row k's
 //     arithmetic starts (with per-negative id loads the row request waited a full L2 round trip:
 //     48 % of the stall samples).
-template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG>
+template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG, bool BWD>
 __global__ void __launch_bounds__(kThreads, MINB)
-k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
-               float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
-               int64_t* __restrict__ slot_rel, int32_t* status) {
+k_group_step_e(const GroupArgs G, const float up0, const float* __restrict__ up_dev, float* __restrict__ pos_scores,
+               float* __restrict__ neg_scores, float* __restrict__ group_loss, const kgrec_grads Gr,
+               int64_t* __restrict__ slot_ent, int64_t* __restrict__ slot_rel, int32_t* status) {
+  // BWD: the autograd backward of kgrec_corrupt_loss_fwd -- the hinge / BPR coefficients come from the SAVED
+  // scores (one coalesced load per group, handed out by shuffles), the upstream is up0 * up_dev[batch], and
+  // nothing but the gradients is written.
   const kgrec_tables& T = G.T;
   const LossCfg& L = G.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -461,7 +464,7 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
     if (static_cast<uint64_t>(vh) >= static_cast<uint64_t>(T.n_ent)) { bad = true; ih = 0; }
     if (static_cast<uint64_t>(vt) >= static_cast<uint64_t>(T.n_ent)) { bad = true; it = 0; }
     if (static_cast<uint64_t>(vr) >= static_cast<uint64_t>(T.n_rel)) { bad = true; ir = 0; }
-    if (slot_ent) {      // row ids of the gradient slots: [h, t, corrupted_1..K] per group, r per group
+    if (!BWD && slot_ent) {      // row ids of the gradient slots: [h, t, corrupted_1..K] per group, r per group
       const uint32_t s0 = static_cast<uint32_t>(j) * (2 + K);
       if (lane < 2) slot_ent[s0 + lane] = pv;
       if (lane == 2) slot_rel[j] = pv;
@@ -485,14 +488,17 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
     }
     [[maybe_unused]] const uint32_t ih0 = ih, it0 = it, ir0 = ir;
     float up = up0;
+    if (BWD && up_dev) up *= __ldg(up_dev + j / bp);
     if (!MARGIN) {
       const int b = j / bp;
       up /= static_cast<float>(min(bp, n_pos - b * bp)) * static_cast<float>(K);
     }
+    [[maybe_unused]] const float svec = (BWD && lane < K) ? __ldg(neg_scores + static_cast<uint32_t>(j) * K + lane) : 0.f;
     const float4 bh = make_float4(h.x + r.x, h.y + r.y, h.z + r.z, h.w + r.w);        // h + r
     const float4 bt = make_float4(t.x - r.x, t.y - r.y, t.z - r.z, t.w - r.w);        // t - r
     const float4 ep = make_float4(bh.x - t.x, bh.y - t.y, bh.z - t.z, bh.w - t.w);    // (h + r) - t
-    const float sp = warp_sum(dist_term(ep.x, L1) + dist_term(ep.y, L1) + dist_term(ep.z, L1) + dist_term(ep.w, L1));
+    const float sp = BWD ? __ldg(pos_scores + j)
+                         : warp_sum(dist_term(ep.x, L1) + dist_term(ep.y, L1) + dist_term(ep.z, L1) + dist_term(ep.w, L1));
     float lsum = 0.f, cpos = 0.f, mys = 0.f;
     float4 accT = z4, accH = z4;
     uint32_t goff = (static_cast<uint32_t>(j) * (2 + K) + 2) * d4;      // byte offset of the first corrupted-row slot
@@ -514,7 +520,9 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
       const float4 e = make_float4(B.x - x.x, B.y - x.y, B.z - x.z, B.w - x.w);
       float sn = dist_term(e.x, L1) + dist_term(e.y, L1) + dist_term(e.z, L1) + dist_term(e.w, L1);
       [[maybe_unused]] float nx2 = 0.f;
-      if (REG) {
+      if (BWD) {
+        sn = __shfl_sync(FULL, svec, k);
+      } else if (REG) {
         nx2 = x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
         warp_sum2(sn, nx2);
         lreg += fmaxf(nx2 - 1.f, 0.f);
@@ -522,7 +530,7 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
       } else {
         sn = warp_sum(sn);
       }
-      if (lane == k) mys = sn;
+      if (!BWD && lane == k) mys = sn;
       float coef;      // -(dLoss/dsn): the corrupted row's gradient is coef * dL(e')/de'
       if (MARGIN) {
         const float tt = sp - sn + prm;
@@ -588,11 +596,13 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
       gt.x = fmaf(ct, t.x, gt.x); gt.y = fmaf(ct, t.y, gt.y); gt.z = fmaf(ct, t.z, gt.z); gt.w = fmaf(ct, t.w, gt.w);
       gr.x = fmaf(cr, r.x, gr.x); gr.y = fmaf(cr, r.y, gr.y); gr.z = fmaf(cr, r.z, gr.z); gr.w = fmaf(cr, r.w, gr.w);
     }
-    if (lane == 0) {
-      pos_scores[j] = sp;
-      group_loss[j] = lsum + (REG ? lreg : 0.f);
+    if (!BWD) {
+      if (lane == 0) {
+        pos_scores[j] = sp;
+        group_loss[j] = lsum + (REG ? lreg : 0.f);
+      }
+      if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
     }
-    if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
     if (act) {
       if (DENSE) {
         red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(ih0) * d4), gh.x, gh.y, gh.z, gh.w);
@@ -618,11 +628,14 @@ k_group_step_e(const GroupArgs G, const float up0, float* __restrict__ pos_score
 //   g_h = E_h - (E_h.w) w,  g_t = E_t - (E_t.w) w,  g_r = accT - accH + eps_p,
 //   g_w -= (E_h.w) h + (h.w) E_h + (E_t.w) t + (t.w) E_t.
 // The two reductions a negative needs after its residual (the score and g.w) share one shuffle tree.
-template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG>
+template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG, bool BWD>
 __global__ void __launch_bounds__(kThreads, MINB)
-k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
-               float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
-               int64_t* __restrict__ slot_rel, int32_t* status) {
+k_group_step_h(const GroupArgs G, const float up0, const float* __restrict__ up_dev, float* __restrict__ pos_scores,
+               float* __restrict__ neg_scores, float* __restrict__ group_loss, const kgrec_grads Gr,
+               int64_t* __restrict__ slot_ent, int64_t* __restrict__ slot_rel, int32_t* status) {
+  // BWD: the autograd backward of kgrec_corrupt_loss_fwd -- the hinge / BPR coefficients come from the SAVED
+  // scores (one coalesced load per group, handed out by shuffles), the upstream is up0 * up_dev[batch], and
+  // nothing but the gradients is written.
   const kgrec_tables& T = G.T;
   const LossCfg& L = G.L;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -670,7 +683,7 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
     if (static_cast<uint64_t>(vh) >= static_cast<uint64_t>(T.n_ent)) { bad = true; ih = 0; }
     if (static_cast<uint64_t>(vt) >= static_cast<uint64_t>(T.n_ent)) { bad = true; it = 0; }
     if (static_cast<uint64_t>(vr) >= static_cast<uint64_t>(T.n_rel)) { bad = true; ir = 0; }
-    if (slot_ent) {
+    if (!BWD && slot_ent) {
       const uint32_t s0 = static_cast<uint32_t>(j) * (2 + K);
       if (lane < 2) slot_ent[s0 + lane] = pv;
       if (lane == 2) slot_rel[j] = pv;
@@ -694,17 +707,20 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
       }
     }
     float up = up0;
+    if (BWD && up_dev) up *= __ldg(up_dev + j / bp);
     if (!MARGIN) {
       const int b = j / bp;
       up /= static_cast<float>(min(bp, n_pos - b * bp)) * static_cast<float>(K);
     }
+    [[maybe_unused]] const float svec = (BWD && lane < K) ? __ldg(neg_scores + static_cast<uint32_t>(j) * K + lane) : 0.f;
     float a = dot4(h, w), b = dot4(t, w);
     warp_sum2(a, b);
     const float4 pt = make_float4(fmaf(-b, w.x, t.x), fmaf(-b, w.y, t.y), fmaf(-b, w.z, t.z), fmaf(-b, w.w, t.w));
     const float4 bh = make_float4(fmaf(-a, w.x, h.x) + r.x, fmaf(-a, w.y, h.y) + r.y, fmaf(-a, w.z, h.z) + r.z, fmaf(-a, w.w, h.w) + r.w);
     const float4 bt = make_float4(pt.x - r.x, pt.y - r.y, pt.z - r.z, pt.w - r.w);
     const float4 ep = make_float4(bh.x - pt.x, bh.y - pt.y, bh.z - pt.z, bh.w - pt.w);
-    const float sp = warp_sum(dist_term(ep.x, L1) + dist_term(ep.y, L1) + dist_term(ep.z, L1) + dist_term(ep.w, L1));
+    const float sp = BWD ? __ldg(pos_scores + j)
+                         : warp_sum(dist_term(ep.x, L1) + dist_term(ep.y, L1) + dist_term(ep.z, L1) + dist_term(ep.w, L1));
     float lsum = 0.f, cpos = 0.f, mys = 0.f, sT = 0.f, sH = 0.f;
     float4 accT = z4, accH = z4, gwv = z4;
     uint32_t goff = (static_cast<uint32_t>(j) * (2 + K) + 2) * d4;
@@ -728,14 +744,19 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
       const float4 dd = L1 ? make_float4(ddist_term(e.x, 1), ddist_term(e.y, 1), ddist_term(e.z, 1), ddist_term(e.w, 1)) : e;   // L2: x2 below
       float sn = dist_term(e.x, L1) + dist_term(e.y, L1) + dist_term(e.z, L1) + dist_term(e.w, L1);
       float dw = dot4(dd, w);
-      warp_sum2(sn, dw);
+      if (BWD) {
+        dw = warp_sum(dw);
+        sn = __shfl_sync(FULL, svec, k);
+      } else {
+        warp_sum2(sn, dw);
+      }
       [[maybe_unused]] float nx2 = 0.f;
       if (REG) {
         nx2 = warp_sum(dot4(x, x));
         lreg += fmaxf(nx2 - 1.f, 0.f);
         n_tail += head ? 0.f : 1.f;
       }
-      if (lane == k) mys = sn;
+      if (!BWD && lane == k) mys = sn;
       float coef;
       if (MARGIN) {
         const float tt = sp - sn + prm;
@@ -814,11 +835,13 @@ k_group_step_h(const GroupArgs G, const float up0, float* __restrict__ pos_score
       gr.z = fmaf(cr, r.z, fmaf(cw, w.z, gr.z)); gr.w = fmaf(cr, r.w, fmaf(cw, w.w, gr.w));
       gwv.x = fmaf(cw, r.x, gwv.x); gwv.y = fmaf(cw, r.y, gwv.y); gwv.z = fmaf(cw, r.z, gwv.z); gwv.w = fmaf(cw, r.w, gwv.w);
     }
-    if (lane == 0) {
-      pos_scores[j] = sp;
-      group_loss[j] = lsum + (REG ? lreg : 0.f);
+    if (!BWD) {
+      if (lane == 0) {
+        pos_scores[j] = sp;
+        group_loss[j] = lsum + (REG ? lreg : 0.f);
+      }
+      if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
     }
-    if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
     if (act) {
       if (DENSE) {
         red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(ih) * d4), gh.x, gh.y, gh.z, gh.w);
@@ -927,11 +950,32 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
   const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos},
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* env = getenv("KGREC_GROUP_STEP");
+  const bool small32 = n_neg <= 32 && static_cast<double>(n_pos) * (2 + n_neg) * tables->dim * 4 < 4.0e9 &&
+                       static_cast<double>(n_pos) * n_neg < 2.0e9;
+  if ((pl.fam == FAM_E || pl.fam == FAM_H) && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
+    // the step kernels in backward mode (coefficients from the saved scores, upstream per batch)
+    float* ps = const_cast<float*>(pos_scores);
+    float* ns = const_cast<float*>(neg_scores);
+#define CALL_B(KERN, MINBV, L1V, DV, MV) KERN<L1V, DV, MV, MINBV, true, false, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, grad_loss_dev, ps, ns, nullptr, *grads, nullptr, nullptr, nullptr)
+#define CALL_B8(KERN, MINBV)                                                                                                   \
+  {                                                                                                                            \
+    const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;                                                     \
+    if (tables->l1) { if (dn) { if (mg) CALL_B(KERN, MINBV, true, true, true); else CALL_B(KERN, MINBV, true, true, false); }  \
+                      else { if (mg) CALL_B(KERN, MINBV, true, false, true); else CALL_B(KERN, MINBV, true, false, false); } } \
+    else { if (dn) { if (mg) CALL_B(KERN, MINBV, false, true, true); else CALL_B(KERN, MINBV, false, true, false); }           \
+           else { if (mg) CALL_B(KERN, MINBV, false, false, true); else CALL_B(KERN, MINBV, false, false, false); } }          \
+  }
+    if (pl.fam == FAM_E) CALL_B8(k_group_step_e, 4) else CALL_B8(k_group_step_h, 3)
+#undef CALL_B8
+#undef CALL_B
+  } else {
 #define CALL(FAMV, NCHV)                                                                                                  \
   if (tables->l1) k_group_bwd<FAMV, NCHV, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, grad_loss, grad_loss_dev, *grads); \
   else k_group_bwd<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, grad_loss, grad_loss_dev, *grads);
   KGREC_GROUP_DISPATCH(CALL)
 #undef CALL
+  }
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;
 }
@@ -967,13 +1011,13 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
 #define CALL_E(L1V, DV, MV)                                                                                      \
   {                                                                                                              \
     if (env && env[0] == 'n')                                                                                    \
-      k_group_step_e<L1V, DV, MV, 4, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 4, false, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, nullptr, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (env && env[0] == '3')                                                                               \
-      k_group_step_e<L1V, DV, MV, 3, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 3, false, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, nullptr, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (MV && reg_flags)                                                                                    \
-      k_group_step_e<L1V, DV, true, 4, true, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, true, 4, true, true, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, nullptr, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else                                                                                                         \
-      k_group_step_e<L1V, DV, MV, 4, true, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_e<L1V, DV, MV, 4, true, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, nullptr, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
   }
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
     if (tables->l1) { if (dn) { if (mg) CALL_E(true, true, true) else CALL_E(true, true, false) } else { if (mg) CALL_E(true, false, true) else CALL_E(true, false, false) } }
@@ -983,13 +1027,13 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
 #define CALL_H(L1V, DV, MV)                                                                                      \
   {                                                                                                              \
     if (env && env[0] == 'n')                                                                                    \
-      k_group_step_h<L1V, DV, MV, 3, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, MV, 3, false, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, nullptr, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (env && env[0] == '2')                                                                               \
-      k_group_step_h<L1V, DV, MV, 2, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, MV, 2, false, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, nullptr, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else if (MV && reg_flags)                                                                                    \
-      k_group_step_h<L1V, DV, true, 3, true, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, true, 3, true, true, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, nullptr, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
     else                                                                                                         \
-      k_group_step_h<L1V, DV, MV, 3, true, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
+      k_group_step_h<L1V, DV, MV, 3, true, false, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, nullptr, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status); \
   }
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
     if (tables->l1) { if (dn) { if (mg) CALL_H(true, true, true) else CALL_H(true, true, false) } else { if (mg) CALL_H(true, false, true) else CALL_H(true, false, false) } }
