@@ -206,7 +206,9 @@ int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model,
                            const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
                            int loss_kind, float margin_or_target,
                            const float* pos_scores, const float* neg_scores, float grad_loss,
-                           const float* grad_loss_dev, const kgrec_grads* grads, kgrec_stream_t stream);
+                           const float* grad_loss_dev, const kgrec_grads* grads,
+                           int64_t* slot_ent_ids, int64_t* slot_rel_ids,   /* optional, as in kgrec_corrupt_loss_step */
+                           kgrec_stream_t stream);
 
 /* Forward + loss + backward of the group-compact ranking loss in ONE pass: scores, per-batch
  * losses and the row gradients of grad_loss * sum_b loss[b] (every reference driver calls

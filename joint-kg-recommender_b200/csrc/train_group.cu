@@ -464,7 +464,7 @@ k_group_step_e(const GroupArgs G, const float up0, const float* __restrict__ up_
     if (static_cast<uint64_t>(vh) >= static_cast<uint64_t>(T.n_ent)) { bad = true; ih = 0; }
     if (static_cast<uint64_t>(vt) >= static_cast<uint64_t>(T.n_ent)) { bad = true; it = 0; }
     if (static_cast<uint64_t>(vr) >= static_cast<uint64_t>(T.n_rel)) { bad = true; ir = 0; }
-    if (!BWD && slot_ent) {      // row ids of the gradient slots: [h, t, corrupted_1..K] per group, r per group
+    if (slot_ent) {      // row ids of the gradient slots: [h, t, corrupted_1..K] per group, r per group
       const uint32_t s0 = static_cast<uint32_t>(j) * (2 + K);
       if (lane < 2) slot_ent[s0 + lane] = pv;
       if (lane == 2) slot_rel[j] = pv;
@@ -683,7 +683,7 @@ k_group_step_h(const GroupArgs G, const float up0, const float* __restrict__ up_
     if (static_cast<uint64_t>(vh) >= static_cast<uint64_t>(T.n_ent)) { bad = true; ih = 0; }
     if (static_cast<uint64_t>(vt) >= static_cast<uint64_t>(T.n_ent)) { bad = true; it = 0; }
     if (static_cast<uint64_t>(vr) >= static_cast<uint64_t>(T.n_rel)) { bad = true; ir = 0; }
-    if (!BWD && slot_ent) {
+    if (slot_ent) {
       const uint32_t s0 = static_cast<uint32_t>(j) * (2 + K);
       if (lane < 2) slot_ent[s0 + lane] = pv;
       if (lane == 2) slot_rel[j] = pv;
@@ -937,11 +937,13 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
                                       const void* pr, int idx_bytes, int64_t n_pos, const int32_t* corrupt,
                                       int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
                                       const float* pos_scores, const float* neg_scores, float grad_loss,
-                                      const float* grad_loss_dev, const kgrec_grads* grads, kgrec_stream_t stream) {
+                                      const float* grad_loss_dev, const kgrec_grads* grads, int64_t* slot_ent_ids,
+                                      int64_t* slot_rel_ids, kgrec_stream_t stream) {
   Plan pl;
   int rc = group_check(tables, model, &pl, ph, pt, pr, idx_bytes, n_pos, corrupt, n_neg, batch_pos, loss_kind);
   if (rc) return rc;
   if (!pos_scores || !neg_scores) { set_error("saved scores are NULL"); return KGREC_ERR_INVALID; }
+  if ((slot_ent_ids == nullptr) != (slot_rel_ids == nullptr)) { set_error("slot_ent_ids and slot_rel_ids go together"); return KGREC_ERR_INVALID; }
   if (!grads || (grads->mode != 0 && grads->mode != 1) || !grads->ent || !grads->rel || (pl.fam == FAM_H && !grads->norm)) {
     set_error("bad grads descriptor");
     return KGREC_ERR_INVALID;
@@ -957,7 +959,7 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
     // the step kernels in backward mode (coefficients from the saved scores, upstream per batch)
     float* ps = const_cast<float*>(pos_scores);
     float* ns = const_cast<float*>(neg_scores);
-#define CALL_B(KERN, MINBV, L1V, DV, MV) KERN<L1V, DV, MV, MINBV, true, false, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, grad_loss_dev, ps, ns, nullptr, *grads, nullptr, nullptr, nullptr)
+#define CALL_B(KERN, MINBV, L1V, DV, MV) KERN<L1V, DV, MV, MINBV, true, false, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, grad_loss, grad_loss_dev, ps, ns, nullptr, *grads, slot_ent_ids, slot_rel_ids, nullptr)
 #define CALL_B8(KERN, MINBV)                                                                                                   \
   {                                                                                                                            \
     const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;                                                     \
@@ -975,6 +977,12 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
   else k_group_bwd<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, grad_loss, grad_loss_dev, *grads);
   KGREC_GROUP_DISPATCH(CALL)
 #undef CALL
+    if (slot_ent_ids) {
+      const int64_t total = n_pos * (2 + static_cast<int64_t>(n_neg));
+      const int64_t ctas = (total + 255) / 256, cap = static_cast<int64_t>(sm_count()) * 16;
+      k_group_slot_ids<<<static_cast<unsigned>(ctas < cap ? ctas : cap), 256, 0, st>>>(ph, pt, pr, idx_bytes == 8, corrupt, n_pos, n_neg,
+                                                                                         slot_ent_ids, slot_rel_ids);
+    }
   }
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;

@@ -64,7 +64,8 @@ _SIGNATURES = {
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kgrec_corrupt_loss_bwd": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_float,
-                                         C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(Grads), C.c_void_p]),
+                                         C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.POINTER(Grads), C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
     "kgrec_corrupt_loss_step": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                           C.c_int64, C.c_void_p, C.c_int32, C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Grads), C.c_void_p, C.c_void_p,

@@ -310,10 +310,15 @@ class CorruptLossFunction(torch.autograd.Function):
                 torch.empty((shapes[name], cfg.dim), dtype=torch.float32, device=dev)
             bufs[name] = buf
             setattr(g, name, buf.data_ptr())
+        ent_ids = rel_ids = None
+        if not dense:        # the COO index arrays come out of the same kernel pass
+            ent_ids = torch.empty((1, n_pos * (2 + n_neg)), dtype=torch.int64, device=dev)
+            rel_ids = torch.empty((1, n_pos), dtype=torch.int64, device=dev)
         lib = _lib.load()
         _lib.check(lib.kgrec_corrupt_loss_bwd(
             C.byref(T), cfg.model, _ptr(ph), _ptr(pt), _ptr(pr), _idx_bytes(ph, pt, pr), n_pos, _ptr(corrupt),
-            n_neg, batch_pos, loss_kind, param, _ptr(pos_s), _ptr(neg_s), 1.0, _ptr(gl), C.byref(g), _stream()))
+            n_neg, batch_pos, loss_kind, param, _ptr(pos_s), _ptr(neg_s), 1.0, _ptr(gl), C.byref(g),
+            _ptr(ent_ids), _ptr(rel_ids), _stream()))
         count_launches(1)
         out = []
         for name in names:
@@ -322,12 +327,8 @@ class CorruptLossFunction(torch.autograd.Function):
             elif dense:
                 out.append(bufs[name])
             else:
-                if name == "ent":
-                    cid = torch.where(corrupt < 0, ~corrupt, corrupt).view(n_pos, n_neg).long()
-                    idx = torch.cat([ph.long().view(-1, 1), pt.long().view(-1, 1), cid], dim=1).reshape(1, -1)
-                else:
-                    idx = pr.long().view(1, -1)
-                out.append(torch.sparse_coo_tensor(idx, bufs[name], size=tuple(weights[name].shape), check_invariants=False))
+                out.append(torch.sparse_coo_tensor(ent_ids if name == "ent" else rel_ids, bufs[name],
+                                                   size=tuple(weights[name].shape), check_invariants=False))
         return (None,) * 8 + tuple(out)
 
 
