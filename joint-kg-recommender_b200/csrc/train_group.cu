@@ -410,7 +410,7 @@ k_group_step(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
 //     group ahead and handed out by shuffles, so the request for row k+1 leaves as soon as row k's
 //     arithmetic starts (with per-negative id loads the row request waited a full L2 round trip:
 //     48 % of the stall samples).
-template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG, bool BWD>
+template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG, bool BWD, bool FWD = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_group_step_e(const GroupArgs G, const float up0, const float* __restrict__ up_dev, float* __restrict__ pos_scores,
                float* __restrict__ neg_scores, float* __restrict__ group_loss, const kgrec_grads Gr,
@@ -544,6 +544,7 @@ k_group_step_e(const GroupArgs G, const float up0, const float* __restrict__ up_
         cpos += dp;
         coef = dp * up;
       }
+      if (FWD) return;                      // forward only (kgrec_corrupt_loss_fwd): scores and loss terms
       const bool regx = REG && nx2 > 1.f;
       if (coef != 0.f || regx) {            // warp-uniform: an inactive hinge has no gradient
         float4 gc = z4;                     // = -eps' (+ the regulariser's 2 x)
@@ -603,7 +604,7 @@ k_group_step_e(const GroupArgs G, const float up0, const float* __restrict__ up_
       }
       if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
     }
-    if (act) {
+    if (!FWD && act) {
       if (DENSE) {
         red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(ih0) * d4), gh.x, gh.y, gh.z, gh.w);
         red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(it0) * d4), gt.x, gt.y, gt.z, gt.w);
@@ -628,7 +629,7 @@ k_group_step_e(const GroupArgs G, const float up0, const float* __restrict__ up_
 //   g_h = E_h - (E_h.w) w,  g_t = E_t - (E_t.w) w,  g_r = accT - accH + eps_p,
 //   g_w -= (E_h.w) h + (h.w) E_h + (E_t.w) t + (t.w) E_t.
 // The two reductions a negative needs after its residual (the score and g.w) share one shuffle tree.
-template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG, bool BWD>
+template <bool L1, bool DENSE, bool MARGIN, int MINB, bool PF, bool REG, bool BWD, bool FWD = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_group_step_h(const GroupArgs G, const float up0, const float* __restrict__ up_dev, float* __restrict__ pos_scores,
                float* __restrict__ neg_scores, float* __restrict__ group_loss, const kgrec_grads Gr,
@@ -770,6 +771,7 @@ k_group_step_h(const GroupArgs G, const float up0, const float* __restrict__ up_
         cpos += dp;
         coef = dp * up;
       }
+      if (FWD) return;
       const bool regx = REG && nx2 > 1.f;
       if (coef != 0.f || regx) {
         float4 gx = z4;
@@ -842,7 +844,7 @@ k_group_step_h(const GroupArgs G, const float up0, const float* __restrict__ up_
       }
       if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
     }
-    if (act) {
+    if (!FWD && act) {
       if (DENSE) {
         red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(ih) * d4), gh.x, gh.y, gh.z, gh.w);
         red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(it) * d4), gt.x, gt.y, gt.z, gt.w);
@@ -921,11 +923,29 @@ extern "C" int kgrec_corrupt_loss_fwd(const kgrec_tables* tables, int model, con
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   float* group_loss = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const char* env = getenv("KGREC_GROUP_STEP");
+  const bool small32 = n_neg <= 32 && static_cast<double>(n_pos) * (2 + n_neg) * tables->dim * 4 < 4.0e9 &&
+                       static_cast<double>(n_pos) * n_neg < 2.0e9;
+  if (pl.fam == FAM_E && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
+    // the TransE step kernel in forward-only mode (TransH: k_group_fwd measured faster, 1.06 vs 1.09 ms fwd+bwd)
+    const kgrec_grads nog{};
+#define CALL_F(KERN, MINBV, L1V, MV) KERN<L1V, false, MV, MINBV, true, false, false, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, 1.f, nullptr, pos_scores, neg_scores, group_loss, nog, nullptr, nullptr, status)
+#define CALL_F4(KERN, MINBV)                                                                                        \
+  {                                                                                                                 \
+    const bool mg = loss_kind == KGREC_LOSS_MARGIN;                                                                 \
+    if (tables->l1) { if (mg) CALL_F(KERN, MINBV, true, true); else CALL_F(KERN, MINBV, true, false); }             \
+    else { if (mg) CALL_F(KERN, MINBV, false, true); else CALL_F(KERN, MINBV, false, false); }                      \
+  }
+    CALL_F4(k_group_step_e, 4)
+#undef CALL_F4
+#undef CALL_F
+  } else {
 #define CALL(FAMV, NCHV)                                                                                                  \
   if (tables->l1) k_group_fwd<FAMV, NCHV, true><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, group_loss, status); \
   else k_group_fwd<FAMV, NCHV, false><<<grid_for(n_pos), kThreads, 0, st>>>(G, pos_scores, neg_scores, group_loss, status);
   KGREC_GROUP_DISPATCH(CALL)
 #undef CALL
+  }
   KGREC_CUDA_OK(cudaGetLastError());
   const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
   k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(group_loss, G.L, loss);
