@@ -158,21 +158,29 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
 
   // ids of a tile's rows, one per lane: lanes 0-15 hold the user id of row wid*16 + lane, lanes
   // 16-31 the item id of row wid*16 + lane - 16; -1 past the end.  Fetched one tile ahead.
+  // (group, member) of a local row in step mode: fixed per row, so the divisions happen once per thread
+  struct RowPos { int gl, tt; };
+  auto row_pos = [&](int rl) {
+    RowPos p{0, 0};
+    if constexpr (STEP) { p.gl = rl / A.gsz; p.tt = rl - p.gl * A.gsz; }
+    return p;
+  };
+  const RowPos rp_a[kMP] = {row_pos(slot), row_pos(8 + slot)};
+  const RowPos rp_l = row_pos(lane & 15);
   // flat pair index (positives first, then negatives) of the warp's local row rl of tile t; -1 = none
-  auto pair_of = [&](int t, int rl) -> int64_t {
+  auto pair_at = [&](int t, int rl, const RowPos& rp) -> int64_t {
     if (t >= A.n_tiles) return -1;
     if constexpr (STEP) {
-      const int gl = rl / A.gsz, tt = rl - gl * A.gsz;
-      const int64_t j = (static_cast<int64_t>(t) * nw + wid) * A.gw + gl;
-      if (gl >= A.gw || j >= A.n_pos) return -1;
-      return tt == 0 ? j : A.n_pos + j * (A.gsz - 1) + (tt - 1);
+      const int64_t j = (static_cast<int64_t>(t) * nw + wid) * A.gw + rp.gl;
+      if (rp.gl >= A.gw || j >= A.n_pos) return -1;
+      return rp.tt == 0 ? j : A.n_pos + j * (A.gsz - 1) + (rp.tt - 1);
     } else {
       const int64_t i = static_cast<int64_t>(t) * M + wid * kPairsPerWarp + rl;
       return i < A.n ? i : -1;
     }
   };
   auto fetch_ids = [&](int t) -> int64_t {
-    const int64_t i = pair_of(t, lane & 15);
+    const int64_t i = pair_at(t, lane & 15, rp_l);
     if (i < 0) return -1;
     const bool neg = i >= A.n_pos;
     const int64_t li = neg ? i - A.n_pos : i;
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
   // Rows wid*16 .. wid*16+15 of the tile belong to this warp from the gather to the flush; only
   // pass F reads other warps' rows (two CTA barriers per tile in the backward, none in the forward).
   for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-    const int64_t pidx[kMP] = {pair_of(tile, slot), pair_of(tile, 8 + slot)};
+    const int64_t pidx[kMP] = {pair_at(tile, slot, rp_a[0]), pair_at(tile, 8 + slot, rp_a[1])};
 
     // ---- gather: raw rows by cp.async (u -> E, item -> W, aligned entity -> S), all 16 rows of
     // the warp in flight at once, then S = u + i', X = u - i'  (i' = item + entity for KTUP,
@@ -200,7 +208,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
       if (lane < 16) sid[rl] = static_cast<int>(id);
       else { sid[M + rl] = static_cast<int>(id); sid[2 * M + rl] = static_cast<int>(ia); }
       if constexpr (MODE == MODE_BWD) {
-        if (lane < 16) sg[rl] = id >= 0 ? upstream_one(A.B, A.L, pair_of(tile, lane)) : 0.f;
+        if (lane < 16) sg[rl] = id >= 0 ? upstream_one(A.B, A.L, pair_at(tile, lane & 15, rp_l)) : 0.f;
       }
 #pragma unroll 4
       for (int j = 0; j < kPairsPerWarp; ++j) {
@@ -354,10 +362,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
         const int K = A.gsz - 1;
 #pragma unroll
         for (int a = 0; a < kMP; ++a) {
-          const int rl = mloc[a] - wid * kPairsPerWarp, gl = rl / A.gsz, tt = rl - gl * A.gsz;
+          const int gl = rp_a[a].gl, tt = rp_a[a].tt;
           const int64_t i = pidx[a];
           if (i >= 0) {
-            const int64_t j = i < A.n_pos ? i : (i - A.n_pos) / K;
+            const int64_t j = (static_cast<int64_t>(tile) * nw + wid) * A.gw + gl;
             const float* gs = sg + wid * kPairsPerWarp + gl * A.gsz;    // [pos, neg_1 .. neg_K]
             const float up = A.B.grad_loss * loss_batch_scale(A.L, j);
             if (tt == 0) {
@@ -506,9 +514,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_rec_tile(const TileArgs A
       __syncwarp();
 
       // ---- flush the row gradients: whole rows, the warp's own 16
+      RowPos fp{0, 0};
       for (int j = 0; j < kPairsPerWarp; ++j) {
         const int r = wid * kPairsPerWarp + j;
-        const int64_t i = pair_of(tile, j);
+        const int64_t i = pair_at(tile, j, fp);
+        if constexpr (STEP) { if (++fp.tt == A.gsz) { fp.tt = 0; ++fp.gl; } }
         if (i < 0 || lane >= NC) continue;
         const float4 gu = S[r * lda4 + lane];
         float4 gi = E[r * lda4 + lane];
