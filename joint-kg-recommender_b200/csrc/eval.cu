@@ -1040,17 +1040,20 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
   if constexpr (MODE == MODE_TOPK)
     lists = reinterpret_cast<uint64_t*>(smem_raw + L.lists) + static_cast<size_t>(wid) * RQ * A.k;
   const float* cq = sQ + wid * RQ * lda;
+  const ulonglong2* cq2 = reinterpret_cast<const ulonglong2*>(cq);
   const int nk4 = d >> 2;
   int64_t cur_qt = -1, q0 = 0;
   auto begin_qtile = [&](int64_t qt) {
     cur_qt = qt;
     q0 = qt * TQT + wid * RQ;
     __syncwarp();
+    // chunk-major: chunk e of query qi sits at cq4[e * RQ + qi], so inside the dimension loops the eight queries
+    // of a chunk are immediate offsets from one pointer (row-major cost one IMAD per query and load)
     for (int qi = 0; qi < RQ; ++qi) {
       const int64_t q = q0 + qi;
-      float4* dst = reinterpret_cast<float4*>(sQ + (wid * RQ + qi) * lda);
+      float4* dst = reinterpret_cast<float4*>(sQ + wid * RQ * lda);
       const float4* src = reinterpret_cast<const float4*>(A.qvec + q * lda);
-      for (int c = lane; c < lda / 4; c += 32) dst[c] = (q < A.nq) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = lane; c < lda / 4; c += 32) dst[c * RQ + qi] = (q < A.nq) ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int qi = 0; qi < RQ; ++qi) thr_hi[qi] = 0xffffffffu;
@@ -1095,15 +1098,15 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       const ulonglong2 xw = *reinterpret_cast<const ulonglong2*>(xr + 2 * d + 4 * k4);
 #pragma unroll
       for (int qi = 0; qi < RQ; ++qi) {
-        const ulonglong2 qu = *reinterpret_cast<const ulonglong2*>(cq + qi * lda + 4 * k4);
-        const ulonglong2 qn = *reinterpret_cast<const ulonglong2*>(cq + qi * lda + 2 * d + 4 * k4);
+        const ulonglong2 qu = cq2[k4 * RQ + qi];
+        const ulonglong2 qn = cq2[(2 * nk4 + k4) * RQ + qi];
         sd2[qi] = fma2(qu.x, xw.x, fma2(qu.y, xw.y, fma2(xi.x, qn.x, fma2(xi.y, qn.y, sd2[qi]))));
       }
     }
     const float dn = xr[3 * d];
     float sv[RQ];
 #pragma unroll
-    for (int qi = 0; qi < RQ; ++qi) sv[qi] = sum2(sd2[qi]) + cq[qi * lda + 3 * d] - dn;
+    for (int qi = 0; qi < RQ; ++qi) sv[qi] = sum2(sd2[qi]) + cq[(3 * nk4 * RQ + qi) * 4] - dn;
     // pass 2: L( (A_q - s UB_q) - (B_n + s IB_n) )
     f32x2 acc2[RQ];
 #pragma unroll
@@ -1114,8 +1117,8 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       const ulonglong2 xw = *reinterpret_cast<const ulonglong2*>(xr + 2 * d + 4 * k4);
 #pragma unroll
       for (int qi = 0; qi < RQ; ++qi) {
-        const ulonglong2 qa = *reinterpret_cast<const ulonglong2*>(cq + qi * lda + d + 4 * k4);
-        const ulonglong2 qn = *reinterpret_cast<const ulonglong2*>(cq + qi * lda + 2 * d + 4 * k4);
+        const ulonglong2 qa = cq2[(nk4 + k4) * RQ + qi];
+        const ulonglong2 qn = cq2[(2 * nk4 + k4) * RQ + qi];
         const f32x2 s2 = splat2(sv[qi]);
         const f32x2 e01 = sub2(fma2(s2, qn.x, qa.x), fma2(s2, xw.x, xb.x));
         const f32x2 e23 = sub2(fma2(s2, qn.y, qa.y), fma2(s2, xw.y, xb.y));
