@@ -708,8 +708,17 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
           for (int e = 0; e < 8; ++e) cv[e] = (A.side == KGREC_SIDE_HEAD) ? cv[e] - rv[e] : cv[e] + rv[e];
         }
       }
-      R::store(sQ + (wid * RQ + qi) * d, cv, d, lane);
-      if (KIND == KIND_HYPER) R::store(sW + (wid * RQ + qi) * d, wv, d, lane);
+      // chunk-major: chunk c of query qi at [c * RQ + qi], so the eight queries of a chunk are immediate
+      // offsets from one pointer inside the dimension loops (row-major cost one IMAD per query and load)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int c = lane + 32 * i;
+        if (c * 4 < d) {
+          reinterpret_cast<float4*>(sQ + wid * RQ * d)[c * RQ + qi] = make_float4(cv[4 * i], cv[4 * i + 1], cv[4 * i + 2], cv[4 * i + 3]);
+          if (KIND == KIND_HYPER)
+            reinterpret_cast<float4*>(sW + wid * RQ * d)[c * RQ + qi] = make_float4(wv[4 * i], wv[4 * i + 1], wv[4 * i + 2], wv[4 * i + 3]);
+        }
+      }
       if constexpr (MODE == MODE_RANK) {
         if (lane == 0) {
           sGold[(wid * RQ + qi) * 2] = q < A.nq ? __float_as_uint(__ldg(A.gold_scores + q)) : 0u;
@@ -787,7 +796,7 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       if constexpr (IDS) { kj[j] = (k4) + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }         \
       xv[j] = *reinterpret_cast<const ulonglong2*>(xrow + j * 32 * d + 4 * kj[j]);          \
     }
-#define KGREC_QVEC(base, qi, j) (*reinterpret_cast<const ulonglong2*>((base) + (qi) * d + 4 * (IDS ? kj[j] : kk)))
+#define KGREC_QVEC(base, qi, j) (reinterpret_cast<const ulonglong2*>(base)[(IDS ? kj[j] : kk) * RQ + (qi)])
 
     if constexpr (KIND == KIND_HYPER) {
       f32x2 sd2[RQ][RN];                       // phase 1: sd[q][n] = x_n . w_q
