@@ -452,6 +452,38 @@ def test_step_with_fused_regularisers(cls_name, l1):
             assert torch.allclose(got[k], want[k], rtol=2e-3, atol=2e-4 * max(1.0, float(want[k].abs().max()))), k
 
 
+@pytest.mark.parametrize("cls_name", ["TransEModel", "TransHModel"])
+@pytest.mark.parametrize("Kn", [1, 2, 31, 32, 40])
+def test_step_kernel_negative_counts(cls_name, Kn):
+    """The step kernels hold a group's corrupted ids one per lane: 1 and 2 negatives (the reference's own 1 per
+    positive), the lane-count edges 31 / 32, and 40 (falls back to the general kernel) against the two-kernel
+    autograd path on the same inputs; the slot row ids are checked through the sparse gradients."""
+    import kgrec_b200 as K
+    torch.manual_seed(Kn)
+    rng = np.random.RandomState(Kn)
+    d, E, R, n_pos, bp = 64, 700, 5, 517, 128
+    m = getattr(K, cls_name)(Kn % 2 == 0, d, E, R)
+    h, t, r = rng.randint(0, E, n_pos), rng.randint(0, E, n_pos), rng.randint(0, R, n_pos)
+    ce = rng.randint(0, E, n_pos * Kn)
+    corrupt = torch.as_tensor(np.where(rng.rand(n_pos * Kn) < 0.5, ~ce, ce).astype(np.int32), device=dev())
+    pos = (lt(h), lt(t), lt(r))
+    for loss, param in (("margin", 1.0), ("bpr", -1.0)):
+        m.grad_mode = "dense"
+        m.zero_grad()
+        l, ps, ns = m.rank_loss_corrupt(pos, corrupt, margin=param, loss=loss, batch_pos=bp)
+        l.sum().backward()
+        want = {k: v.clone() for k, v in grads_by_name(m).items()}
+        for gm in ("dense", "sparse"):
+            m.grad_mode = gm
+            m.zero_grad()
+            sl, sp, sn = m.loss_step_corrupt(pos, corrupt, margin=param, loss=loss, batch_pos=bp)
+            assert torch.allclose(sp, ps, rtol=1e-5, atol=1e-6) and torch.allclose(sn, ns, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(sl, l, rtol=1e-4, atol=1e-5)
+            got = grads_by_name(m)
+            for k in want:
+                assert torch.allclose(got[k], want[k], rtol=2e-3, atol=2e-4 * max(1.0, float(want[k].abs().max()))), (k, gm, loss)
+
+
 def test_rank_loss_step_other_shapes():
     """kgrec_rank_loss_step outside the single-pass kernel's shapes (KG model; many negatives) falls
     back to forward + backward kernels behind the same call."""
