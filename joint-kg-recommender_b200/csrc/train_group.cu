@@ -862,6 +862,245 @@ k_group_step_h(const GroupArgs G, const float up0, const float* __restrict__ up_
   if (bad && status) *status = 1;
 }
 
+// --- TransR, d <= 128: forward + ranking loss + backward of a group in one pass ------------------
+// (transR.py:65-78, misc.py:21-26.)  The generic path re-reads the relation's d x d matrix M for every
+// triple and adds its gradient with d*d atomics per triple.  A group shares one relation, so here a warp
+//   * stages the 2 + K entity rows V = [h, t, c_1..c_K] in shared memory and computes Y = M V with every
+//     lane owning rows of M (its own 3-4 rows, read once, 16 bytes at a time; V chunks are broadcast loads):
+//     no cross-lane reduction for the projections, one shuffle tree per score only;
+//   * forms residuals, losses and dL/dY = G in registers (row-owner layout), writes the relation-row gradient;
+//   * adds the matrix gradient G V^T for the whole group with ONE set of d*d/4 vector atomics;
+//   * transposes G through shared memory and computes the entity-row gradients M^T G with lanes owning
+//     16-byte column chunks (coalesced second pass over M), storing the 2 + K slot rows.
+// M is read twice per group instead of twice per triple, the atomics drop by 1 + K.
+template <int NVT, bool MARGIN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_group_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
+               float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
+               int64_t* __restrict__ slot_rel, int32_t* status) {
+  extern __shared__ __align__(16) float rsm[];
+  const kgrec_tables& T = G.T;
+  const LossCfg& L = G.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K = L.n_neg, nv = 2 + K;
+  const int d = T.dim, NC = d >> 2;
+  const int n_pos = static_cast<int>(L.n_pos);
+  const uint32_t n_ent = static_cast<uint32_t>(T.n_ent);
+  const int l1 = T.l1;
+  const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
+  const float prm = L.param;
+  float4* Vs = reinterpret_cast<float4*>(rsm) + static_cast<size_t>(wid) * (NVT * NC + d * (NVT / 4));   // [nv][NC]
+  float4* GT = Vs + NVT * NC;                                                                            // [d][NVT / 4]
+  const int stride = gridDim.x * kWarpsPerCta;
+  const void* pcol = lane == 0 ? G.ph : (lane == 1 ? G.pt : G.pr);
+  bool bad = false;
+
+  for (int j = blockIdx.x * kWarpsPerCta + wid; j < n_pos; j += stride) {
+    const int32_t cv = lane < K ? __ldg(G.corrupt + static_cast<int64_t>(j) * K + lane) : 0;
+    const int64_t pv = lane < 3 ? load_idx(pcol, j, G.is64) : 0;
+    const int64_t vh = __shfl_sync(FULL, pv, 0), vt = __shfl_sync(FULL, pv, 1), vr = __shfl_sync(FULL, pv, 2);
+    uint32_t ih = static_cast<uint32_t>(vh), it = static_cast<uint32_t>(vt), ir = static_cast<uint32_t>(vr);
+    if (static_cast<uint64_t>(vh) >= static_cast<uint64_t>(T.n_ent)) { bad = true; ih = 0; }
+    if (static_cast<uint64_t>(vt) >= static_cast<uint64_t>(T.n_ent)) { bad = true; it = 0; }
+    if (static_cast<uint64_t>(vr) >= static_cast<uint64_t>(T.n_rel)) { bad = true; ir = 0; }
+    const int64_t slot0 = static_cast<int64_t>(j) * nv;
+    if (slot_ent) {
+      if (lane < 2) slot_ent[slot0 + lane] = pv;
+      if (lane == 2) slot_rel[j] = pv;
+      if (lane < K) slot_ent[slot0 + 2 + lane] = cv < 0 ? ~cv : cv;
+    }
+    // ---- stage V = [h, t, c_1..c_K]
+    __syncwarp();
+    for (int v = 0; v < nv; ++v) {
+      uint32_t id;
+      if (v == 0) id = ih;
+      else if (v == 1) id = it;
+      else {
+        const int32_t c = __shfl_sync(FULL, cv, v - 2);
+        id = static_cast<uint32_t>(c < 0 ? ~c : c);
+        if (id >= n_ent) { bad = true; id = 0; }
+      }
+      if (lane < NC) Vs[v * NC + lane] = ldg_f4(reinterpret_cast<const float4*>(T.ent + static_cast<uint64_t>(id) * T.ld) + lane);
+    }
+    __syncwarp();
+    const float* M = T.proj + static_cast<uint64_t>(ir) * d * d;
+
+    // ---- Y = M V, lane owns rows a = lane + 32 i
+    float y[4][NVT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int v = 0; v < NVT; ++v) y[i][v] = 0.f;
+    for (int c = 0; c < NC; ++c) {
+      float4 m[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = lane + 32 * i;
+        m[i] = a < d ? __ldg(reinterpret_cast<const float4*>(M + static_cast<size_t>(a) * d) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int v = 0; v < NVT; ++v) {
+        if (v < nv) {
+          const float4 x = Vs[v * NC + c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i][v] = fmaf(m[i].x, x.x, fmaf(m[i].y, x.y, fmaf(m[i].z, x.z, fmaf(m[i].w, x.w, y[i][v]))));
+        }
+      }
+    }
+    float rr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int a = lane + 32 * i;
+      rr[i] = a < d ? __ldg(T.rel + static_cast<uint64_t>(ir) * T.ld + a) : 0.f;
+    }
+    // ---- scores, loss, coefficients
+    float up = up0;
+    if (!MARGIN) {
+      const int b = j / bp;
+      up /= static_cast<float>(min(bp, n_pos - b * bp)) * static_cast<float>(K);
+    }
+    float sp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sp += (lane + 32 * i < d) ? dist_term(y[i][0] + rr[i] - y[i][1], l1) : 0.f;
+    sp = warp_sum(sp);
+    float lsum = 0.f, cpos = 0.f, mys = 0.f;
+    float gp[4] = {0.f, 0.f, 0.f, 0.f};       // sum of dLoss/de over the group's triples (= relation-row gradient), per owned row
+    float gh[4] = {0.f, 0.f, 0.f, 0.f}, gt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int v = 2; v < NVT; ++v) {
+      if (v < nv) {
+        const int k = v - 2;
+        const bool head = __shfl_sync(FULL, cv, k) < 0;
+        float e[4], sn = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          e[i] = head ? y[i][v] + rr[i] - y[i][1] : y[i][0] + rr[i] - y[i][v];
+          sn += (lane + 32 * i < d) ? dist_term(e[i], l1) : 0.f;
+        }
+        sn = warp_sum(sn);
+        if (lane == k) mys = sn;
+        float coef;                        // dLoss/dsn
+        if (MARGIN) {
+          const float tt = sp - sn + prm;
+          lsum += fmaxf(tt, 0.f);
+          coef = tt > 0.f ? -up : 0.f;
+          cpos += tt > 0.f ? 1.f : 0.f;
+        } else {
+          const float xx = prm * (sp - sn);
+          lsum += fmaxf(-xx, 0.f) + log1pf(expf(-fabsf(xx)));
+          const float dp = -prm / (1.f + expf(xx));
+          cpos += dp;
+          coef = -dp * up;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float g = coef * ddist_term(e[i], l1);          // dLoss/de of this negative
+          gp[i] += g;
+          if (head) { y[i][v] = g; gt[i] -= g; }                   // e = y_c + r - y_t
+          else { y[i][v] = -g; gh[i] += g; }                       // e = y_h + r - y_c
+        }
+      }
+    }
+    {
+      const float cp = cpos * up;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float g = cp * ddist_term(y[i][0] + rr[i] - y[i][1], l1);
+        gp[i] += g;
+        y[i][0] = gh[i] + g;                                       // G for h
+        y[i][1] = gt[i] - g;                                       // G for t
+      }
+    }
+    if (lane == 0) {
+      pos_scores[j] = sp;
+      group_loss[j] = lsum;
+    }
+    if (lane < K) neg_scores[static_cast<int64_t>(j) * K + lane] = mys;
+    // relation-row gradient
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int a = lane + 32 * i;
+      if (a < d) {
+        if (Gr.mode == 0) Gr.rel[static_cast<int64_t>(j) * d + a] = gp[i];
+        else atomicAdd(Gr.rel + static_cast<uint64_t>(ir) * d + a, gp[i]);
+      }
+    }
+    // ---- matrix gradient G V^T: one vector atomic per (row, chunk) for the whole group; and G^T to shared memory
+    float* gM = Gr.proj + static_cast<uint64_t>(ir) * d * d;
+    for (int c = 0; c < NC; ++c) {
+      float4 acc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int v = 0; v < NVT; ++v) {
+        if (v < nv) {
+          const float4 x = Vs[v * NC + c];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i].x = fmaf(y[i][v], x.x, acc[i].x); acc[i].y = fmaf(y[i][v], x.y, acc[i].y);
+            acc[i].z = fmaf(y[i][v], x.z, acc[i].z); acc[i].w = fmaf(y[i][v], x.w, acc[i].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = lane + 32 * i;
+        if (a < d) red_add_f4(gM + static_cast<size_t>(a) * d + 4 * c, acc[i].x, acc[i].y, acc[i].z, acc[i].w);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int a = lane + 32 * i;
+      if (a < d) {
+#pragma unroll
+        for (int v4 = 0; v4 < NVT / 4; ++v4)
+          GT[a * (NVT / 4) + v4] = make_float4(y[i][4 * v4], y[i][4 * v4 + 1], y[i][4 * v4 + 2], y[i][4 * v4 + 3]);
+      }
+    }
+    __syncwarp();
+    // ---- entity-row gradients M^T G, lane owns column chunk `lane`
+    float4 gv[NVT];
+#pragma unroll
+    for (int v = 0; v < NVT; ++v) gv[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < NC) {
+      for (int a = 0; a < d; ++a) {
+        const float4 mrow = __ldg(reinterpret_cast<const float4*>(M + static_cast<size_t>(a) * d) + lane);
+#pragma unroll
+        for (int v4 = 0; v4 < NVT / 4; ++v4) {
+          const float4 g4 = GT[a * (NVT / 4) + v4];
+          const float gs[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int v = 4 * v4 + u;
+            gv[v].x = fmaf(gs[u], mrow.x, gv[v].x); gv[v].y = fmaf(gs[u], mrow.y, gv[v].y);
+            gv[v].z = fmaf(gs[u], mrow.z, gv[v].z); gv[v].w = fmaf(gs[u], mrow.w, gv[v].w);
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < NVT; ++v) {
+        if (v < nv) {
+          if (Gr.mode == 0) {
+            __stcs(reinterpret_cast<float4*>(Gr.ent + (slot0 + v) * d) + lane, gv[v]);
+          } else {
+            uint32_t id;
+            if (v == 0) id = ih;
+            else if (v == 1) id = it;
+            else {
+              const int32_t c = G.corrupt[static_cast<int64_t>(j) * K + (v - 2)];
+              id = static_cast<uint32_t>(c < 0 ? ~c : c);
+              if (id >= n_ent) id = 0;
+            }
+            red_add_f4(Gr.ent + static_cast<uint64_t>(id) * d + 4 * lane, gv[v].x, gv[v].y, gv[v].z, gv[v].w);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (bad && status) *status = 1;
+}
+
 // slot row ids for the general step kernel (TransH, wide rows): one thread per slot
 __global__ void __launch_bounds__(256)
 k_group_slot_ids(const void* ph, const void* pt, const void* pr, const int is64, const int32_t* __restrict__ corrupt,
@@ -882,10 +1121,10 @@ int make_plan(const kgrec_tables* T, int model, Plan* pl);
 
 static int group_check(const kgrec_tables* T, int model, Plan* pl, const void* ph, const void* pt, const void* pr,
                        int idx_bytes, int64_t n_pos, const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
-                       int loss_kind) {
+                       int loss_kind, bool allow_r = false) {
   int rc = make_plan(T, model, pl);
   if (rc) return rc;
-  if (pl->fam != FAM_E && pl->fam != FAM_H) {
+  if (pl->fam != FAM_E && pl->fam != FAM_H && !(allow_r && pl->fam == FAM_R)) {
     set_error("corrupt-format ranking loss is built for TransE / TransH (model %d)", model);
     return KGREC_ERR_UNSUPPORTED;
   }
@@ -1015,14 +1254,41 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
                                        const kgrec_grads* grads, int64_t* slot_ent_ids, int64_t* slot_rel_ids,
                                        void* workspace, int32_t* status, kgrec_stream_t stream) {
   Plan pl;
-  int rc = group_check(tables, model, &pl, ph, pt, pr, idx_bytes, n_pos, corrupt, n_neg, batch_pos, loss_kind);
+  int rc = group_check(tables, model, &pl, ph, pt, pr, idx_bytes, n_pos, corrupt, n_neg, batch_pos, loss_kind, true);
   if (rc) return rc;
   if (!pos_scores || !neg_scores || !loss || !workspace) { set_error("output / workspace pointer is NULL"); return KGREC_ERR_INVALID; }
-  if (!grads || (grads->mode != 0 && grads->mode != 1) || !grads->ent || !grads->rel || (pl.fam == FAM_H && !grads->norm)) {
+  if (!grads || (grads->mode != 0 && grads->mode != 1) || !grads->ent || !grads->rel || (pl.fam == FAM_H && !grads->norm) ||
+      (pl.fam == FAM_R && !grads->proj)) {
     set_error("bad grads descriptor");
     return KGREC_ERR_INVALID;
   }
   if ((slot_ent_ids == nullptr) != (slot_rel_ids == nullptr)) { set_error("slot_ent_ids and slot_rel_ids go together"); return KGREC_ERR_INVALID; }
+  if (pl.fam == FAM_R) {
+    if (reg_flags) { set_error("fused regularisers are built for TransE / TransH"); return KGREC_ERR_UNSUPPORTED; }
+    if (pl.nch != 1 || n_neg > 14) { set_error("TransR step kernel: embedding_size <= 128 and at most 14 negatives per positive"); return KGREC_ERR_UNSUPPORTED; }
+    if (n_pos == 0) return KGREC_OK;
+    const GroupArgs GA{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos}, 1.f};
+    float* gl = static_cast<float*>(workspace);
+    cudaStream_t s2 = static_cast<cudaStream_t>(stream);
+    const int nvt = n_neg <= 2 ? 4 : (n_neg <= 10 ? 12 : 16);
+    const size_t smem = static_cast<size_t>(kWarpsPerCta) * (static_cast<size_t>(nvt) * (tables->dim / 4) + static_cast<size_t>(tables->dim) * (nvt / 4)) * 16;
+    const bool mg = loss_kind == KGREC_LOSS_MARGIN;
+#define CALL_R(NVTV, MV)                                                                                             \
+  {                                                                                                                  \
+    auto kern = k_group_step_r<NVTV, MV>;                                                                            \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));   \
+    kern<<<grid_for(n_pos), kThreads, smem, s2>>>(GA, grad_loss, pos_scores, neg_scores, gl, *grads, slot_ent_ids, slot_rel_ids, status); \
+  }
+    if (nvt == 4) { if (mg) CALL_R(4, true) else CALL_R(4, false) }
+    else if (nvt == 12) { if (mg) CALL_R(12, true) else CALL_R(12, false) }
+    else { if (mg) CALL_R(16, true) else CALL_R(16, false) }
+#undef CALL_R
+    KGREC_CUDA_OK(cudaGetLastError());
+    const int64_t nbt = (n_pos + batch_pos - 1) / batch_pos;
+    k_batch_loss<<<static_cast<unsigned>(nbt), 256, 0, s2>>>(gl, GA.L, loss);
+    KGREC_CUDA_OK(cudaGetLastError());
+    return KGREC_OK;
+  }
   if (n_pos == 0) return KGREC_OK;
   const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos},
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};

@@ -362,8 +362,8 @@ def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, p
     shapes = {"ent": n_pos * (2 + n_neg), "rel": n_pos, "norm": n_pos}
     bufs = {}
     for name in names:
-        bufs[name] = torch.zeros_like(weights[name]) if dense else \
-            torch.empty((shapes[name], cfg.dim), dtype=torch.float32, device=dev)
+        bufs[name] = torch.zeros_like(weights[name]) if (dense or name not in shapes) else \
+            torch.empty((shapes[name], cfg.dim), dtype=torch.float32, device=dev)      # TransR proj: dense accumulate
         setattr(g, name, bufs[name].data_ptr())
     # the COO index arrays of the slot gradients come out of the same kernel pass
     ent_ids = rel_ids = None
@@ -378,7 +378,7 @@ def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, p
     count_launches(2)
     grads = {}
     for name in names:
-        if dense:
+        if dense or name not in shapes:
             grads[name] = bufs[name]
         else:
             grads[name] = torch.sparse_coo_tensor(ent_ids if name == "ent" else rel_ids, bufs[name],

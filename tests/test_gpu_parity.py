@@ -484,6 +484,39 @@ def test_step_kernel_negative_counts(cls_name, Kn):
                 assert torch.allclose(got[k], want[k], rtol=2e-3, atol=2e-4 * max(1.0, float(want[k].abs().max()))), (k, gm, loss)
 
 
+@pytest.mark.parametrize("Kn,l1,loss,param", [(10, False, "margin", 1.0), (1, True, "margin", 2.0), (13, False, "bpr", -1.0)])
+def test_transr_group_step(Kn, l1, loss, param):
+    """TransR single-pass group kernel (one pass over the relation's matrix per group, its gradient added once
+    per group) against the generic kernels on the expanded triples."""
+    import kgrec_b200 as K
+    torch.manual_seed(Kn)
+    rng = np.random.RandomState(Kn)
+    d, E, R, n_pos, bp = 100, 600, 7, 403, 128
+    m = K.TransRModel(l1, d, E, R)
+    h, t, r = rng.randint(0, E, n_pos), rng.randint(0, E, n_pos), rng.randint(0, R, n_pos)
+    ce = rng.randint(0, E, n_pos * Kn)
+    head = rng.rand(n_pos * Kn) < 0.5
+    corrupt = torch.as_tensor(np.where(head, ~ce, ce).astype(np.int32), device=dev())
+    nh = np.where(head, ce, np.repeat(h, Kn))
+    nt = np.where(head, np.repeat(t, Kn), ce)
+    nr = np.repeat(r, Kn)
+    pos, neg = (lt(h), lt(t), lt(r)), (lt(nh), lt(nt), lt(nr))
+    m.grad_mode = "dense"
+    m.zero_grad()
+    l, ps, ns = m.rank_loss(pos, neg, margin=param, loss=loss, batch_pos=bp)
+    l.sum().backward()
+    want = {k: v.clone() for k, v in grads_by_name(m).items()}
+    for gm in ("dense", "sparse"):
+        m.grad_mode = gm
+        m.zero_grad()
+        sl, sp, sn = m.loss_step_corrupt(pos, corrupt, margin=param, loss=loss, batch_pos=bp)
+        assert torch.allclose(sp, ps, rtol=2e-4, atol=1e-5) and torch.allclose(sn, ns, rtol=2e-4, atol=1e-5)
+        assert torch.allclose(sl, l, rtol=2e-4, atol=1e-4)
+        got = grads_by_name(m)
+        for k in want:
+            assert torch.allclose(got[k], want[k], rtol=3e-3, atol=3e-4 * max(1.0, float(want[k].abs().max()))), (k, gm)
+
+
 def test_rank_loss_step_other_shapes():
     """kgrec_rank_loss_step outside the single-pass kernel's shapes (KG model; many negatives) falls
     back to forward + backward kernels behind the same call."""
