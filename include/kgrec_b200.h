@@ -223,7 +223,10 @@ int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model,
  * (knowledge_representation.py:197-204): normLoss (loss.py:21-23) over the entity rows of
  * cat[ph, pt, nh, nt] and the relation rows of cat[pr, nr], and for TransH orthogonalLoss
  * (loss.py:18-19) over (rel, norm) rows of cat[pr, nr] -- every row with the multiplicity it has in
- * those lists.  Margin loss and embedding_size <= 128 only. */
+ * those lists.  Margin loss and embedding_size <= 128 only.
+ * KGREC_TRANSR is accepted by this entry point as well (embedding_size <= 128, n_neg <= 14,
+ * reg_flags 0): the relation's d x d matrix is read twice per GROUP and its gradient
+ * (grads->proj, always a dense [n_rel, d*d] accumulate) added once per group. */
 int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model,
                             const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
                             const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
