@@ -397,6 +397,20 @@ def norm_loss(rows):
     return np.maximum((rows ** 2).sum(1) - 1, 0).sum()
 
 
+def norm_loss_grads(rows):
+    """d normLoss / d rows: 2 x on the rows outside the unit sphere (torch's max(., 0) passes the
+    gradient where the first argument is the larger one)."""
+    return (2 * rows * ((rows ** 2).sum(1, keepdims=True) > 1)).astype(rows.dtype)
+
+
+def orthogonal_loss_grads(rel_rows, norm_rows):
+    """(d/d rel, d/d norm) of orthogonalLoss = sum (w.r)^2 / |r|^2."""
+    wr = (norm_rows * rel_rows).sum(1, keepdims=True)
+    n2 = (rel_rows ** 2).sum(1, keepdims=True)
+    q = wr / n2
+    return (2 * q * norm_rows - 2 * q * q * rel_rows).astype(rel_rows.dtype), (2 * q * rel_rows).astype(rel_rows.dtype)
+
+
 # --------------------------------------------------------------------------
 # full-catalog ranking  (utils/misc.py:125-146, 213-248; utils/evaluation.py)
 # --------------------------------------------------------------------------

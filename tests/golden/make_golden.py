@@ -182,7 +182,27 @@ def ranking_case(name, seed):
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
+def regs_case(name, seed):
+    """The drivers' regularisers (utils/loss.py:18-23) on rows on both sides of the unit sphere:
+    values and autograd gradients."""
+    torch.manual_seed(seed)
+    ent = torch.randn(B * 3, D) * torch.linspace(0.12, 0.34, B * 3).view(-1, 1)      # |row|^2 from ~0.3 to ~2.3
+    rel = torch.randn(B, D) * 0.25
+    nrm = torch.randn(B, D) * 0.22
+    ent.requires_grad_(True); rel.requires_grad_(True); nrm.requires_grad_(True)
+    nl_e = ref_loss.normLoss(ent)
+    nl_r = ref_loss.normLoss(rel)
+    ol = ref_loss.orthogonalLoss(rel, nrm)
+    (nl_e + nl_r + ol).backward()
+    out = {"ent": npy(ent), "rel": npy(rel), "norm": npy(nrm), "norm_loss_ent": npy(nl_e), "norm_loss_rel": npy(nl_r),
+           "orth_loss": npy(ol), "grad_ent": npy(ent.grad), "grad_rel": npy(rel.grad), "grad_norm": npy(nrm.grad)}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "regs":          # add one file without rewriting the others
+        regs_case("regularisers", 12)
+        return
     seed = 7
     for l1 in (False, True):
         tag = "l1" if l1 else "l2"
@@ -194,6 +214,7 @@ def main():
             tup_case(f"transup_{tag}_{gt}", l1, gumbel, seed + 3)
             ktup_case(f"jtransup_{tag}_{gt}", l1, gumbel, seed + 4)
     ranking_case("ranking", seed + 5)
+    regs_case("regularisers", 12)
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 

@@ -179,3 +179,18 @@ def test_torch_port_matches_golden(golden, name, with_norm, tag):
         close(getattr(m, k + "_embeddings").weight.grad.numpy(), g[f"grad_{k}_embeddings"], rtol=1e-4, atol=1e-6)
     close(m.evaluate_side(LT(g["q"]), LT(g["qr"]), True).detach().numpy(), g["eval_head"])
     close(m.evaluate_side(LT(g["q"]), LT(g["qr"]), False).detach().numpy(), g["eval_tail"])
+
+
+def test_regularisers_against_reference(golden):
+    """normLoss / orthogonalLoss (utils/loss.py:18-23): values and autograd gradients recorded from the
+    reference functions; the step kernels' fused regularisers (reg_flags) are checked against the same
+    formulas on the GPU."""
+    g = golden("regularisers")
+    ent, rel, nrm = g["ent"], g["rel"], g["norm"]
+    np.testing.assert_allclose(O.norm_loss(ent), g["norm_loss_ent"], rtol=1e-5)
+    np.testing.assert_allclose(O.norm_loss(rel), g["norm_loss_rel"], rtol=1e-5)
+    np.testing.assert_allclose(O.orthogonal_loss(rel, nrm), g["orth_loss"], rtol=1e-5)
+    np.testing.assert_allclose(O.norm_loss_grads(ent), g["grad_ent"], rtol=1e-5, atol=1e-7)
+    gr, gw = O.orthogonal_loss_grads(rel, nrm)
+    np.testing.assert_allclose(gr + O.norm_loss_grads(rel), g["grad_rel"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gw, g["grad_norm"], rtol=1e-4, atol=1e-6)
