@@ -229,3 +229,28 @@ def test_dataio_round_trip(tmp_path):
     dataio.save_checkpoint(str(ck), e)
     dataio.load_checkpoint(str(ck), m2)
     assert torch.equal(m2.ent_embeddings.weight, e.ent_embeddings.weight)
+
+
+def test_corrupt_format_encoding_round_trip():
+    """functional.encode_corrupt: (nh, nt) triples of the reference sampler -> one int32 per negative
+    (>= 0 tail replaced, < 0 head replaced by ~id) and back; pure host logic, runs on CPU tensors."""
+    import numpy as np
+    import torch
+    from kgrec_b200 import functional as KF
+    rng = np.random.RandomState(3)
+    n_pos, K, E = 57, 4, 1000
+    h, t, r = (torch.from_numpy(rng.randint(0, E, n_pos)) for _ in range(3))
+    ce = torch.from_numpy(rng.randint(0, E, n_pos * K))
+    head = torch.from_numpy(rng.rand(n_pos * K) < 0.5)
+    # make every corrupted id differ from the row it replaces (the sampler's own guarantee, data.py:23-56)
+    ce = torch.where(head & (ce == h.repeat_interleave(K)), (ce + 1) % E, ce)
+    ce = torch.where(~head & (ce == t.repeat_interleave(K)), (ce + 1) % E, ce)
+    nh = torch.where(head, ce, h.repeat_interleave(K))
+    nt = torch.where(head, t.repeat_interleave(K), ce)
+    c = KF.encode_corrupt((h, t, r), (nh, nt, r.repeat_interleave(K)))
+    assert c.dtype == torch.int32 and c.shape == (n_pos * K,)
+    assert torch.equal(c < 0, head)
+    assert torch.equal(torch.where(c < 0, ~c, c).long(), ce)
+    # the slot row ids the step kernels emit are [h, t, corrupted_1..K] per group
+    want = torch.cat([h.view(-1, 1), t.view(-1, 1), ce.view(n_pos, K)], dim=1).reshape(-1)
+    assert want.numel() == n_pos * (2 + K)
