@@ -39,6 +39,29 @@ def _embedding(weight, **kw):
     return emb
 
 
+def _make_tables(module, specs):
+    """Create the attribute ``nn.Embedding``s of a model the way the reference constructors
+    consume torch's global generator: every ``xavier_uniform`` draw of the group first, in the
+    listed order, then the ``nn.Embedding`` constructors (whose own normal init is discarded)
+    -- transE.py:31-38, transH.py:31-40, transR.py:36-51, transUP.py:36-49, jTransUP.py:52-66,
+    83-94.  With the same ``torch.manual_seed`` the tables therefore start bit-identical to the
+    reference's, which is what lets a driver run be compared step for step.
+
+    specs: (attribute, rows, dim, normalize[, extra zero rows, Embedding kwargs])."""
+    raw = [_init_table(s[1], s[2], normalize=False) for s in specs]
+    for s, w in zip(specs, raw):
+        attr, rows, dim, normalize = s[:4]
+        pad_rows = s[4] if len(s) > 4 else 0
+        kw = s[5] if len(s) > 5 else {}
+        emb = nn.Embedding(rows + pad_rows, dim, **kw)
+        if normalize:
+            w = torch.nn.functional.normalize(w, p=2, dim=1)
+        if pad_rows:
+            w = torch.cat([w, torch.zeros(pad_rows, dim)], dim=0)
+        emb.weight = nn.Parameter(w)
+        setattr(module, attr, emb)
+
+
 class KGRecModule(nn.Module):
     """Common base: table registry, grad switches, device handling, counters."""
 

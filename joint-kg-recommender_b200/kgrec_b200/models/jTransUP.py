@@ -6,7 +6,7 @@ import torch.nn as nn
 
 from .. import _lib
 from .. import functional as KF
-from .base import _embedding, _init_table
+from .base import _make_tables
 from .transUP import RecModelBase
 
 
@@ -37,14 +37,12 @@ class jTransUPModel(RecModelBase):
         self.i_map = i_map
         self.new_map = new_map
         d = embedding_size
-        self.user_embeddings = _embedding(_init_table(user_total, d))
-        self.item_embeddings = _embedding(_init_table(item_total, d))
-        self.pref_embeddings = _embedding(_init_table(relation_total, d))
-        self.pref_norm_embeddings = _embedding(_init_table(relation_total, d))
-        ent = torch.cat([_init_table(entity_total, d), torch.zeros(1, d)], dim=0)
-        self.ent_embeddings = _embedding(ent, padding_idx=self.ent_total - 1)
-        self.rel_embeddings = _embedding(_init_table(relation_total, d))
-        self.norm_embeddings = _embedding(_init_table(relation_total, d))
+        # two groups, as the reference draws them: the TUP tables (jTransUP.py:52-66), then TransH's (83-94)
+        _make_tables(self, [("user_embeddings", user_total, d, True), ("item_embeddings", item_total, d, True),
+                            ("pref_embeddings", relation_total, d, True),
+                            ("pref_norm_embeddings", relation_total, d, True)])
+        _make_tables(self, [("ent_embeddings", entity_total, d, True, 1, {"padding_idx": self.ent_total - 1}),
+                            ("rel_embeddings", relation_total, d, True), ("norm_embeddings", relation_total, d, True)])
         # paddingItems (jTransUP.py:114-120) as a device lookup table built once:
         # item -> aligned entity row, unaligned -> the padding row
         pad = self.ent_total - 1

@@ -1,7 +1,7 @@
 """TransE on the CUDA engine.  Mirrors jTransUP/models/transE.py (constructor 18-49,
 forward 51-63, evaluateHead/Tail 65-105) with every method one kernel call."""
 from .. import _lib
-from .base import KGRecModule, _embedding, _init_table
+from .base import KGRecModule, _make_tables
 
 
 def build_model(FLAGS, user_total, item_total, entity_total, relation_total, i_map=None, e_map=None, new_map=None):
@@ -21,8 +21,11 @@ class KGModelBase(KGRecModule):
         self.embedding_size = embedding_size
         self.ent_total = ent_total
         self.rel_total = rel_total
-        self.ent_embeddings = _embedding(_init_table(ent_total, embedding_size))
-        self.rel_embeddings = _embedding(_init_table(rel_total, embedding_size))
+        _make_tables(self, self._table_specs())
+
+    def _table_specs(self):
+        d = self.embedding_size
+        return [("ent_embeddings", self.ent_total, d, True), ("rel_embeddings", self.rel_total, d, True)]
 
     def forward(self, h, t, r):
         """score[b] of the triples (h[b], r[b], t[b]); argument order as the reference."""

@@ -1,7 +1,6 @@
 """TransH on the CUDA engine.  Mirrors jTransUP/models/transH.py (constructor 17-56,
 forward 58-71, evaluateHead/Tail 73-121; projection utils/misc.py:18-19)."""
 from .. import _lib
-from .base import _embedding, _init_table
 from .transE import KGModelBase
 
 
@@ -16,6 +15,8 @@ class TransHModel(KGModelBase):
 
     def __init__(self, L1_flag, embedding_size, ent_total, rel_total):
         super().__init__(L1_flag, embedding_size, ent_total, rel_total)
-        # per-relation hyperplane normals, unit length at init, never re-normalised in forward
-        self.norm_embeddings = _embedding(_init_table(rel_total, embedding_size))
         self._finish_init()
+
+    def _table_specs(self):
+        # per-relation hyperplane normals, unit length at init, never re-normalised in forward
+        return super()._table_specs() + [("norm_embeddings", self.rel_total, self.embedding_size, True)]

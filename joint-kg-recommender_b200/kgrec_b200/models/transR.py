@@ -4,7 +4,6 @@ import torch
 
 from .. import _lib
 from .. import functional as KF
-from .base import _embedding, _init_table
 from .transE import KGModelBase
 
 
@@ -20,9 +19,12 @@ class TransRModel(KGModelBase):
     def __init__(self, L1_flag, embedding_size, ent_total, rel_total):
         super().__init__(L1_flag, embedding_size, ent_total, rel_total)
         self.max_entity_batch = 10
-        # d x d matrix per relation stored as a row of d*d; xavier, NOT normalised (transR.py:42,55)
-        self.proj_embeddings = _embedding(_init_table(rel_total, embedding_size * embedding_size, normalize=False))
         self._finish_init()
+
+    def _table_specs(self):
+        # d x d matrix per relation stored as a row of d*d; xavier, NOT normalised (transR.py:42,55)
+        d = self.embedding_size
+        return super()._table_specs() + [("proj_embeddings", self.rel_total, d * d, False)]
 
     # Full-catalog TransR (the reference's one dense contraction, misc.py:29-33): queries are
     # grouped by relation, the catalog is projected once per distinct relation by a library

@@ -5,7 +5,7 @@ import torch
 
 from .. import _lib
 from .. import functional as KF
-from .base import KGRecModule, _embedding, _init_table
+from .base import KGRecModule, _make_tables
 
 
 def build_model(FLAGS, user_total, item_total, entity_total, relation_total, i_map=None, e_map=None, new_map=None):
@@ -113,10 +113,10 @@ class TransUPModel(RecModelBase):
         self.item_total = item_total
         self.preference_total = preference_total
         self.use_st_gumbel = use_st_gumbel
-        self.user_embeddings = _embedding(_init_table(user_total, embedding_size))
-        self.item_embeddings = _embedding(_init_table(item_total, embedding_size))
-        self.pref_embeddings = _embedding(_init_table(preference_total, embedding_size))
-        self.pref_norm_embeddings = _embedding(_init_table(preference_total, embedding_size))
+        d = embedding_size
+        _make_tables(self, [("user_embeddings", user_total, d, True), ("item_embeddings", item_total, d, True),
+                            ("pref_embeddings", preference_total, d, True),
+                            ("pref_norm_embeddings", preference_total, d, True)])
         self._finish_init()
 
     def forward(self, u_ids, i_ids, gumbel_u=None):
