@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KGREC_ABI_VERSION 1
+#define KGREC_ABI_VERSION 2
 
 typedef void* kgrec_stream_t; /* cudaStream_t */
 
@@ -259,23 +259,67 @@ int kgrec_sample_neg_items(const void* u, const void* pi, int idx_bytes, int64_t
 
 /* ---- sparse-row optimizer -----------------------------------------
  * Replaces the reference's dense optimizer step and clip_grad_norm (utils/trainer.py:63-81,
- * knowledge_representation.py:213) at a cost proportional to the rows the batch touched.
- * acc: persistent dense accumulator [rows, dim] the backward kernels wrote with grads->mode 1
- * (all-zero outside a step); idx: the ids of the batch (duplicates allowed); flags: int32
- * [rows] scratch, all-zero outside a step. */
-/* adds to *sqnorm the squared L2 norm of the accumulated gradient rows of idx (each once) */
-int kgrec_rows_sqnorm(const float* acc, int32_t* flags, const void* idx, int idx_bytes, int64_t n,
-                      int64_t rows, int32_t dim, float* sqnorm, kgrec_stream_t stream);
-/* one optimizer update of every distinct row of idx, then acc rows and flags are cleared.
- * kind 0 SGD, 1 Adagrad (state1 = sum), 2 Adam on the touched rows (state1 = m, state2 = v,
- * step = 1-based count).  sqnorm (optional, device): gradients are scaled by
- * min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) as clip_grad_norm does; norm_claimed = 1 when
- * kgrec_rows_sqnorm ran on the same idx in this step. */
-int kgrec_rows_step(float* table, float* acc, float* state1, float* state2, int32_t* flags,
-                    const void* idx, int idx_bytes, int64_t n, int64_t rows, int32_t dim,
-                    int kind, float lr, float eps, float beta1, float beta2, int64_t step,
-                    float weight_decay, const float* sqnorm, float max_norm, int norm_claimed,
+ * knowledge_representation.py:213; item_recommendation.py:189-192;
+ * knowledgable_recommendation.py:398-402) at a cost proportional to the rows the batch touched.
+ * Gradients sit in persistent dense accumulators the training kernels wrote with grads->mode 1
+ * (all-zero outside a step).  The rows a step touched carry an epoch mark (marks[row] == epoch,
+ * int32 [rows], never cleared: the caller bumps the epoch every step); marks == NULL means every
+ * row (the small tables: pref / pref_norm / proj, KTUP's rel / norm).  Up to 8 tables per call,
+ * one launch for all of them. */
+typedef struct kgrec_opt_table {
+  float* table;          /* [rows, dim] parameters (contiguous)                                */
+  float* acc;            /* [rows, dim] accumulated gradient, zeroed again by kgrec_rows_update */
+  float* state1;         /* Adagrad sum / Adam m, or NULL (SGD)                                */
+  float* state2;         /* Adam v, or NULL                                                    */
+  const int32_t* marks;  /* [rows] epoch marks, or NULL = all rows                             */
+  int64_t rows;
+  int32_t dim;
+  int32_t keep_acc;      /* 1: leave acc as it is (another table entry shares it and clears it) */
+  int32_t vec;           /* set by the library (128-bit path usable)                           */
+  int32_t reserved;
+} kgrec_opt_table;
+
+/* One id array of the batch and the mark array of the table it indexes. */
+typedef struct kgrec_mark_seg {
+  const void* ids;       /* n ids, idx_bytes wide                                              */
+  int64_t n;
+  int32_t idx_bytes;
+  int32_t compact;       /* 1: group-compact corrupted ids (v < 0 names entity ~v)             */
+  const int32_t* remap;  /* optional [n_remap] lookup applied first (KTUP: item2ent)           */
+  int64_t n_remap;
+  int32_t* marks;        /* [rows]                                                             */
+  int64_t rows;
+} kgrec_mark_seg;
+
+/* marks[id] = epoch for every id of every segment (<= 8 segments, one launch).  Out-of-range ids
+ * are skipped and reported through status (optional int32[1]). */
+int kgrec_rows_mark(const kgrec_mark_seg* segs_host, int n_segs, int32_t epoch, int32_t* status,
                     kgrec_stream_t stream);
+/* adds to *sqnorm the squared L2 norm of the marked accumulator rows of all tables:
+ * clip_grad_norm's total norm */
+int kgrec_rows_sqnorm(const kgrec_opt_table* tabs_host, int n_tabs, int32_t epoch, float* sqnorm,
+                      kgrec_stream_t stream);
+/* one optimizer update of every marked row, then its acc row is cleared.  kind 0 SGD, 1 Adagrad
+ * (state1 = sum), 2 Adam on the touched rows (state1 = m, state2 = v, step = 1-based count).
+ * sqnorm (optional, device): gradients are scaled by min(1, max_norm / (sqrt(*sqnorm) + 1e-6))
+ * as clip_grad_norm does. */
+int kgrec_rows_update(const kgrec_opt_table* tabs_host, int n_tabs, int32_t epoch, int kind, float lr,
+                      float eps, float beta1, float beta2, int64_t step, float weight_decay,
+                      const float* sqnorm, float max_norm, kgrec_stream_t stream);
+
+/* ---- the drivers' recommendation-side regularisers (utils/loss.py:18-23) -------------------------
+ * item_recommendation.py:177-180: normLoss(user rows) + normLoss(item rows of cat[pos, neg]) +
+ * normLoss(pref table) + orthogonalLoss(pref, pref_norm); knowledgable_recommendation.py:343-344:
+ * orthogonalLoss(pref, pref_norm).  Each adds scale * value to *loss_out (device float, optional)
+ * and scale * gradient to the dense accumulators (optional) the sparse-row optimizer consumes.
+ * (The KG drivers' terms over the triples' rows are fused into kgrec_corrupt_loss_step, reg_flags.) */
+/* normLoss over table[ids[i]], i < n -- every listed occurrence counts; ids == NULL: rows 0..n-1 */
+int kgrec_reg_norm_rows(const float* table, int64_t rows, int32_t dim, const void* ids, int idx_bytes,
+                        int64_t n, float scale, float* loss_out, float* acc, int32_t* status,
+                        kgrec_stream_t stream);
+/* orthogonalLoss(rel, norm) = sum_rows (norm.rel)^2 / |rel|^2 over two whole [rows, dim] tables */
+int kgrec_reg_orth_tables(const float* rel, const float* norm, int64_t rows, int32_t dim, float scale,
+                          float* loss_out, float* acc_rel, float* acc_norm, kgrec_stream_t stream);
 
 /* ---- full-catalog evaluation path ---------------------------------------- */
 /* Common arguments of the three evaluation modes:

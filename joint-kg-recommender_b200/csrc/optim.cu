@@ -1,151 +1,252 @@
 // Sparse-row optimizer: the first "next" row of SURVEY 8(f).  Replaces the reference's dense
 // torch.optim step + clip_grad_norm (utils/trainer.py:63-81, knowledge_representation.py:213),
-// whose cost is O(table) per step, by kernels whose cost is O(rows touched by the batch).
+// whose cost is O(table) per step, by kernels whose cost is O(rows touched by the batch) plus one
+// 4-byte flag per table row.
 //
-// Gradients arrive accumulated per row in a persistent dense accumulator `acc` (the kernels'
-// "dense" gradient mode; it is all-zero outside a step), together with the id list of the
-// batch (duplicates allowed).  A row is owned by the first id-list entry that claims it
-// (flags: 0 free -> 1 claimed for the norm -> 2 claimed for the update); the owner applies the
-// update and clears the accumulator row, a last pass frees the flags.
+// Layout.  Gradients arrive accumulated per row in a persistent dense accumulator `acc` (the training
+// kernels' "dense" gradient mode; it is all-zero outside a step).  Which rows a step touched is recorded
+// as an EPOCH MARK: marks[row] = step number, written by k_rows_mark from the batch's own id arrays (plain
+// idempotent stores -- duplicates cost nothing, nothing is ever cleared, no atomics).  Two sweeps then
+// visit the tables, ALL of them in one launch each:
+//   k_rows_sqnorm   sum of |acc[row]|^2 over marked rows            (clip_grad_norm's total norm)
+//   k_rows_update   clip scale, weight decay, SGD / Adagrad / Adam on the marked rows, acc row := 0
+// A warp reads 32 marks with one coalesced load, ballots, and walks the set bits; a marked row is
+// processed with 128-bit loads / stores (lane = 16-byte chunk).  Per step the cost is
+// rows * 4 B of marks + touched rows * (2..4 reads + 2..4 writes) of d floats -- at configs[1]
+// (100k entities, every row touched) ~0.25 GB, against ~1.3 GB for the id-list + CAS version it replaces.
 #include "common.cuh"
 
 namespace kgrec {
 
 enum { OPT_SGD = 0, OPT_ADAGRAD = 1, OPT_ADAM = 2 };
+constexpr int kMaxOptTables = 8;
+constexpr int kMaxMarkSegs = 8;
 
-struct OptArgs {
-  float* table; float* acc; float* s1; float* s2;   // s1: Adagrad sum / Adam m ; s2: Adam v
-  int32_t* flags;
-  const void* idx; int is64; int64_t n; int64_t rows; int d;
-  int kind; float lr, eps, beta1, beta2, wd, bias1, bias2;
-  const float* sqnorm; float max_norm;               // optional clip: scale = min(1, max_norm / (sqrt(*sqnorm) + 1e-6))
+struct MarkArgs {
+  kgrec_mark_seg seg[kMaxMarkSegs];
+  int64_t begin[kMaxMarkSegs + 1];      // prefix sums of seg[].n
+  int n_segs;
+  int32_t epoch;
 };
 
-__device__ __forceinline__ int64_t opt_row(const OptArgs& A, int64_t i) {
-  const int64_t r = load_idx(A.idx, i, A.is64);
-  return (static_cast<uint64_t>(r) < static_cast<uint64_t>(A.rows)) ? r : -1;
-}
-
-// sum over distinct touched rows of |acc[row]|^2  (+= into *out)
-__global__ void __launch_bounds__(kThreads) k_rows_sqnorm(const OptArgs A, float* out) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float local = 0.f;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + wid; i < A.n; i += static_cast<int64_t>(gridDim.x) * kWarpsPerCta) {
-    const int64_t r = opt_row(A, i);
-    if (r < 0) continue;
-    int own = 0;
-    if (lane == 0) own = atomicCAS(A.flags + r, 0, 1) == 0;
-    own = __shfl_sync(FULL, own, 0);
-    if (!own) continue;
-    const float* g = A.acc + r * A.d;
-    for (int j = lane; j < A.d; j += 32) { const float v = g[j]; local = fmaf(v, v, local); }
-  }
-  local = warp_sum(local);
-  __shared__ float part[kWarpsPerCta];
-  if (lane == 0) part[wid] = local;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < kWarpsPerCta; ++w) t += part[w];
-    if (t != 0.f) atomicAdd(out, t);
+// marks[id] = epoch for every id of every segment.  compact: the group-compact corrupted-id format
+// (v < 0 names entity ~v).  remap: ids are looked up first (KTUP: item -> aligned entity row).
+__global__ void __launch_bounds__(256) k_rows_mark(const MarkArgs A, int32_t* status) {
+  const int64_t total = A.begin[A.n_segs];
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxMarkSegs; ++k) s += (k < A.n_segs && i >= A.begin[k]) ? 1 : 0;
+    const kgrec_mark_seg& S = A.seg[s];
+    int64_t v = load_idx(S.ids, i - A.begin[s], S.idx_bytes == 8);
+    if (S.compact && v < 0) v = ~v;
+    if (S.remap) {
+      if (static_cast<uint64_t>(v) >= static_cast<uint64_t>(S.n_remap)) { if (status) *status = 1; continue; }
+      v = __ldg(S.remap + v);
+    }
+    if (static_cast<uint64_t>(v) >= static_cast<uint64_t>(S.rows)) { if (status) *status = 1; continue; }
+    S.marks[v] = A.epoch;
   }
 }
 
-__global__ void __launch_bounds__(kThreads) k_rows_step(const OptArgs A, const int claimed_from) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float scale = 1.f;
-  if (A.sqnorm) scale = fminf(1.f, A.max_norm / (sqrtf(__ldg(A.sqnorm)) + 1e-6f));   // clip_grad_norm's coefficient
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + wid; i < A.n; i += static_cast<int64_t>(gridDim.x) * kWarpsPerCta) {
-    const int64_t r = opt_row(A, i);
-    if (r < 0) continue;
-    int own = 0;
-    if (lane == 0) own = atomicCAS(A.flags + r, claimed_from, 2) == claimed_from;
-    own = __shfl_sync(FULL, own, 0);
-    if (!own) continue;
-    float* p = A.table + r * A.d;
-    float* g = A.acc + r * A.d;
-    for (int j = lane; j < A.d; j += 32) {
-      float gv = g[j] * scale;
-      g[j] = 0.f;                                     // the accumulator is zero again after the step
-      float pv = p[j];
-      if (A.wd != 0.f) gv = fmaf(A.wd, pv, gv);       // weight_decay = l2_lambda, on touched rows only
-      if (A.kind == OPT_SGD) {
-        pv -= A.lr * gv;
-      } else if (A.kind == OPT_ADAGRAD) {             // torch.optim.Adagrad: sum += g^2 ; p -= lr g / (sqrt(sum) + eps)
-        const float s = fmaf(gv, gv, A.s1[r * A.d + j]);
-        A.s1[r * A.d + j] = s;
-        pv -= A.lr * gv / (sqrtf(s) + A.eps);
-      } else {                                        // torch.optim.Adam on the touched rows ("lazy")
-        const float m = A.beta1 * A.s1[r * A.d + j] + (1.f - A.beta1) * gv;
-        const float v = A.beta2 * A.s2[r * A.d + j] + (1.f - A.beta2) * gv * gv;
-        A.s1[r * A.d + j] = m;
-        A.s2[r * A.d + j] = v;
-        pv -= (A.lr / A.bias1) * m / (sqrtf(v) / sqrtf(A.bias2) + A.eps);
-      }
-      p[j] = pv;
+struct SweepArgs {
+  kgrec_opt_table tab[kMaxOptTables];
+  int64_t chunk_begin[kMaxOptTables + 1];    // prefix sums of ceil(rows / 32)
+  int n_tabs;
+  int32_t epoch;
+  int kind;
+  float lr, eps, beta1, beta2, wd, bias1, bias2_sqrt;
+  const float* sqnorm;
+  float max_norm;
+};
+
+// Visit every marked row of every table: f(table, row, chunk index of this lane, active).
+template <typename F>
+__device__ __forceinline__ void sweep_rows(const SweepArgs& A, F&& f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t total = A.chunk_begin[A.n_tabs];
+  for (int64_t c = warp; c < total; c += n_warps) {
+    int t = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxOptTables; ++k) t += (k < A.n_tabs && c >= A.chunk_begin[k]) ? 1 : 0;
+    const kgrec_opt_table& T = A.tab[t];
+    const int64_t row0 = (c - A.chunk_begin[t]) * 32;
+    const int64_t row = row0 + lane;
+    bool mine = row < T.rows;
+    if (mine && T.marks) mine = __ldg(T.marks + row) == A.epoch;
+    unsigned m = __ballot_sync(FULL, mine);
+    const int nch = (T.dim + 3) >> 2;                     // 16-byte chunks per row
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int64_t r = row0 + b;
+      for (int ch = lane; ch < nch; ch += 32) f(T, r, ch);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) k_rows_release(const OptArgs A) {
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < A.n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = opt_row(A, i);
-    if (r >= 0) A.flags[r] = 0;
+__global__ void __launch_bounds__(256) k_rows_sqnorm(const SweepArgs A, float* out) {
+  float local = 0.f;
+  sweep_rows(A, [&](const kgrec_opt_table& T, int64_t r, int ch) {
+    const float* g = T.acc + r * T.dim + ch * 4;
+    if (T.vec) {
+      const float4 v = *reinterpret_cast<const float4*>(g);
+      local = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, local))));
+    } else {
+      for (int e = 0; e < 4 && ch * 4 + e < T.dim; ++e) local = fmaf(g[e], g[e], local);
+    }
+  });
+  local = warp_sum(local);
+  __shared__ float part[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) part[wid] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    if (t != 0.f) atomicAdd(out, t);
   }
+}
+
+__device__ __forceinline__ float opt_elem(const SweepArgs& A, float pv, float gv, float* s1, float* s2) {
+  if (A.wd != 0.f) gv = fmaf(A.wd, pv, gv);          // weight_decay = l2_lambda, on touched rows only
+  if (A.kind == OPT_SGD) return pv - A.lr * gv;
+  if (A.kind == OPT_ADAGRAD) {                        // torch.optim.Adagrad: sum += g^2 ; p -= lr g / (sqrt(sum) + eps)
+    const float s = fmaf(gv, gv, *s1);
+    *s1 = s;
+    return pv - A.lr * gv / (sqrtf(s) + A.eps);
+  }
+  const float m = A.beta1 * *s1 + (1.f - A.beta1) * gv;          // torch.optim.Adam on the touched rows ("lazy")
+  const float v = A.beta2 * *s2 + (1.f - A.beta2) * gv * gv;
+  *s1 = m;
+  *s2 = v;
+  return pv - (A.lr / A.bias1) * m / (sqrtf(v) / A.bias2_sqrt + A.eps);
+}
+
+__global__ void __launch_bounds__(256) k_rows_update(const SweepArgs A) {
+  float scale = 1.f;
+  if (A.sqnorm) scale = fminf(1.f, A.max_norm / (sqrtf(__ldg(A.sqnorm)) + 1e-6f));   // clip_grad_norm's coefficient
+  sweep_rows(A, [&](const kgrec_opt_table& T, int64_t r, int ch) {
+    const int64_t o = r * T.dim + ch * 4;
+    if (T.vec) {
+      float4 g = *reinterpret_cast<float4*>(T.acc + o);
+      if (!T.keep_acc) *reinterpret_cast<float4*>(T.acc + o) = make_float4(0.f, 0.f, 0.f, 0.f);   // zero again after the step
+      float4 p = *reinterpret_cast<float4*>(T.table + o);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (A.kind != OPT_SGD) a = *reinterpret_cast<float4*>(T.state1 + o);
+      if (A.kind == OPT_ADAM) b = *reinterpret_cast<float4*>(T.state2 + o);
+      p.x = opt_elem(A, p.x, g.x * scale, &a.x, &b.x);
+      p.y = opt_elem(A, p.y, g.y * scale, &a.y, &b.y);
+      p.z = opt_elem(A, p.z, g.z * scale, &a.z, &b.z);
+      p.w = opt_elem(A, p.w, g.w * scale, &a.w, &b.w);
+      *reinterpret_cast<float4*>(T.table + o) = p;
+      if (A.kind != OPT_SGD) *reinterpret_cast<float4*>(T.state1 + o) = a;
+      if (A.kind == OPT_ADAM) *reinterpret_cast<float4*>(T.state2 + o) = b;
+    } else {
+      for (int e = 0; e < 4 && ch * 4 + e < T.dim; ++e) {
+        const float g = T.acc[o + e];
+        if (!T.keep_acc) T.acc[o + e] = 0.f;
+        float a = A.kind != OPT_SGD ? T.state1[o + e] : 0.f, b = A.kind == OPT_ADAM ? T.state2[o + e] : 0.f;
+        T.table[o + e] = opt_elem(A, T.table[o + e], g * scale, &a, &b);
+        if (A.kind != OPT_SGD) T.state1[o + e] = a;
+        if (A.kind == OPT_ADAM) T.state2[o + e] = b;
+      }
+    }
+  });
 }
 
 }  // namespace kgrec
 
 using namespace kgrec;
 
-static int opt_check(const float* acc, const int32_t* flags, const void* idx, int idx_bytes, int64_t n, int64_t rows, int d) {
-  if (!acc || !flags || !idx || (idx_bytes != 4 && idx_bytes != 8) || n < 0 || rows <= 0 || d <= 0) {
-    set_error("sparse row optimizer: bad arguments");
+static int sweep_args(const kgrec_opt_table* tabs, int n_tabs, int32_t epoch, int need_table, SweepArgs& A) {
+  if (!tabs || n_tabs < 1 || n_tabs > kMaxOptTables) {
+    set_error("sparse row optimizer: 1..%d tables per call", kMaxOptTables);
     return KGREC_ERR_INVALID;
   }
+  A = SweepArgs{};
+  A.n_tabs = n_tabs;
+  A.epoch = epoch;
+  for (int t = 0; t < n_tabs; ++t) {
+    kgrec_opt_table T = tabs[t];
+    if (!T.acc || T.rows <= 0 || T.dim <= 0 || (need_table && !T.table)) {
+      set_error("sparse row optimizer: table %d has no accumulator / parameter / shape", t);
+      return KGREC_ERR_INVALID;
+    }
+    T.vec = (T.dim % 4 == 0) && (reinterpret_cast<uintptr_t>(T.acc) % 16 == 0) &&
+            (!T.table || reinterpret_cast<uintptr_t>(T.table) % 16 == 0) &&
+            (!T.state1 || reinterpret_cast<uintptr_t>(T.state1) % 16 == 0) &&
+            (!T.state2 || reinterpret_cast<uintptr_t>(T.state2) % 16 == 0);
+    A.tab[t] = T;
+    A.chunk_begin[t + 1] = A.chunk_begin[t] + (T.rows + 31) / 32;
+  }
+  for (int t = n_tabs; t < kMaxOptTables; ++t) A.chunk_begin[t + 1] = A.chunk_begin[n_tabs];
   return KGREC_OK;
 }
 
-static int opt_grid(int64_t n) {
-  const int64_t ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta, cap = static_cast<int64_t>(sm_count()) * 8;
+static int sweep_grid(const SweepArgs& A) {
+  const int64_t warps = A.chunk_begin[A.n_tabs], ctas = (warps + 7) / 8, cap = static_cast<int64_t>(sm_count()) * 8;
   return static_cast<int>(ctas < 1 ? 1 : (ctas < cap ? ctas : cap));
 }
 
-extern "C" int kgrec_rows_sqnorm(const float* acc, int32_t* flags, const void* idx, int idx_bytes, int64_t n,
-                                 int64_t rows, int32_t dim, float* sqnorm, kgrec_stream_t stream) {
-  int rc = opt_check(acc, flags, idx, idx_bytes, n, rows, dim);
-  if (rc) return rc;
-  if (!sqnorm) { set_error("sqnorm is NULL"); return KGREC_ERR_INVALID; }
-  if (n == 0) return KGREC_OK;
-  OptArgs A{};
-  A.acc = const_cast<float*>(acc); A.flags = flags; A.idx = idx; A.is64 = idx_bytes == 8; A.n = n; A.rows = rows; A.d = dim;
-  k_rows_sqnorm<<<opt_grid(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(A, sqnorm);
+extern "C" int kgrec_rows_mark(const kgrec_mark_seg* segs, int n_segs, int32_t epoch, int32_t* status,
+                               kgrec_stream_t stream) {
+  if (!segs || n_segs < 1 || n_segs > kMaxMarkSegs) {
+    set_error("kgrec_rows_mark: 1..%d id segments per call", kMaxMarkSegs);
+    return KGREC_ERR_INVALID;
+  }
+  MarkArgs A{};
+  A.n_segs = n_segs;
+  A.epoch = epoch;
+  for (int s = 0; s < n_segs; ++s) {
+    const kgrec_mark_seg& S = segs[s];
+    if (S.n < 0 || (S.n > 0 && (!S.ids || !S.marks)) || (S.idx_bytes != 4 && S.idx_bytes != 8) || S.rows <= 0) {
+      set_error("kgrec_rows_mark: bad segment %d", s);
+      return KGREC_ERR_INVALID;
+    }
+    A.seg[s] = S;
+    A.begin[s + 1] = A.begin[s] + S.n;
+  }
+  for (int s = n_segs; s < kMaxMarkSegs; ++s) A.begin[s + 1] = A.begin[n_segs];
+  const int64_t total = A.begin[n_segs];
+  if (total == 0) return KGREC_OK;
+  const int64_t blocks = (total + 255) / 256, cap = static_cast<int64_t>(sm_count()) * 16;
+  k_rows_mark<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(A, status);
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;
 }
 
-extern "C" int kgrec_rows_step(float* table, float* acc, float* state1, float* state2, int32_t* flags, const void* idx,
-                               int idx_bytes, int64_t n, int64_t rows, int32_t dim, int kind, float lr, float eps,
-                               float beta1, float beta2, int64_t step, float weight_decay, const float* sqnorm,
-                               float max_norm, int norm_claimed, kgrec_stream_t stream) {
-  int rc = opt_check(acc, flags, idx, idx_bytes, n, rows, dim);
+extern "C" int kgrec_rows_sqnorm(const kgrec_opt_table* tabs, int n_tabs, int32_t epoch, float* sqnorm,
+                                 kgrec_stream_t stream) {
+  SweepArgs A;
+  int rc = sweep_args(tabs, n_tabs, epoch, 0, A);
   if (rc) return rc;
-  if (!table || kind < OPT_SGD || kind > OPT_ADAM || (kind != OPT_SGD && !state1) || (kind == OPT_ADAM && !state2)) {
-    set_error("sparse row optimizer: table / state missing for optimizer kind %d", kind);
-    return KGREC_ERR_INVALID;
-  }
-  if (n == 0) return KGREC_OK;
-  OptArgs A{};
-  A.table = table; A.acc = acc; A.s1 = state1; A.s2 = state2; A.flags = flags; A.idx = idx; A.is64 = idx_bytes == 8;
-  A.n = n; A.rows = rows; A.d = dim; A.kind = kind; A.lr = lr; A.eps = eps; A.beta1 = beta1; A.beta2 = beta2; A.wd = weight_decay;
-  A.bias1 = 1.f - powf(beta1, static_cast<float>(step));
-  A.bias2 = 1.f - powf(beta2, static_cast<float>(step));
-  A.sqnorm = sqnorm; A.max_norm = max_norm;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  k_rows_step<<<opt_grid(n), kThreads, 0, st>>>(A, norm_claimed ? 1 : 0);
+  if (!sqnorm) { set_error("sqnorm is NULL"); return KGREC_ERR_INVALID; }
+  k_rows_sqnorm<<<sweep_grid(A), 256, 0, static_cast<cudaStream_t>(stream)>>>(A, sqnorm);
   KGREC_CUDA_OK(cudaGetLastError());
-  const int64_t blocks = (n + 255) / 256, cap = static_cast<int64_t>(sm_count()) * 8;
-  k_rows_release<<<static_cast<int>(blocks < cap ? blocks : cap), 256, 0, st>>>(A);
+  return KGREC_OK;
+}
+
+extern "C" int kgrec_rows_update(const kgrec_opt_table* tabs, int n_tabs, int32_t epoch, int kind, float lr, float eps,
+                                 float beta1, float beta2, int64_t step, float weight_decay, const float* sqnorm,
+                                 float max_norm, kgrec_stream_t stream) {
+  SweepArgs A;
+  int rc = sweep_args(tabs, n_tabs, epoch, 1, A);
+  if (rc) return rc;
+  if (kind < OPT_SGD || kind > OPT_ADAM) { set_error("sparse row optimizer: unknown kind %d", kind); return KGREC_ERR_INVALID; }
+  for (int t = 0; t < n_tabs; ++t)
+    if ((kind != OPT_SGD && !tabs[t].state1) || (kind == OPT_ADAM && !tabs[t].state2)) {
+      set_error("sparse row optimizer: state missing for optimizer kind %d (table %d)", kind, t);
+      return KGREC_ERR_INVALID;
+    }
+  A.kind = kind; A.lr = lr; A.eps = eps; A.beta1 = beta1; A.beta2 = beta2; A.wd = weight_decay;
+  A.bias1 = 1.f - powf(beta1, static_cast<float>(step));
+  A.bias2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+  A.sqnorm = sqnorm; A.max_norm = max_norm;
+  k_rows_update<<<sweep_grid(A), 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;
 }

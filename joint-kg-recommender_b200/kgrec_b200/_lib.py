@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libkgrec_b200.so")
 TRANSE, TRANSH, TRANSR, TUP, KTUP = range(5)
 LOSS_MARGIN, LOSS_BPR = 0, 1
 SIDE_HEAD, SIDE_TAIL, SIDE_REC = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_f32p = C.c_void_p  # device pointers travel as integers
 
@@ -34,6 +34,21 @@ class Grads(C.Structure):
         ("mode", C.c_int32), ("reserved", C.c_int32),
         ("ent", C.c_void_p), ("rel", C.c_void_p), ("norm", C.c_void_p), ("proj", C.c_void_p),
         ("user", C.c_void_p), ("item", C.c_void_p), ("pref", C.c_void_p), ("pref_norm", C.c_void_p),
+    ]
+
+
+class OptTable(C.Structure):          # struct kgrec_opt_table
+    _fields_ = [
+        ("table", C.c_void_p), ("acc", C.c_void_p), ("state1", C.c_void_p), ("state2", C.c_void_p),
+        ("marks", C.c_void_p), ("rows", C.c_int64), ("dim", C.c_int32), ("keep_acc", C.c_int32),
+        ("vec", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class MarkSeg(C.Structure):           # struct kgrec_mark_seg
+    _fields_ = [
+        ("ids", C.c_void_p), ("n", C.c_int64), ("idx_bytes", C.c_int32), ("compact", C.c_int32),
+        ("remap", C.c_void_p), ("n_remap", C.c_int64), ("marks", C.c_void_p), ("rows", C.c_int64),
     ]
 
 
@@ -76,11 +91,14 @@ _SIGNATURES = {
                                        C.c_int64, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "kgrec_sample_neg_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
-    "kgrec_rows_sqnorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int32,
-                                    C.c_void_p, C.c_void_p]),
-    "kgrec_rows_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                  C.c_int64, C.c_int64, C.c_int32, C.c_int, C.c_float, C.c_float, C.c_float,
-                                  C.c_float, C.c_int64, C.c_float, C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
+    "kgrec_rows_mark": (C.c_int, [C.POINTER(MarkSeg), C.c_int, C.c_int32, C.c_void_p, C.c_void_p]),
+    "kgrec_rows_sqnorm": (C.c_int, [C.POINTER(OptTable), C.c_int, C.c_int32, C.c_void_p, C.c_void_p]),
+    "kgrec_rows_update": (C.c_int, [C.POINTER(OptTable), C.c_int, C.c_int32, C.c_int, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, C.c_int64, C.c_float, C.c_void_p, C.c_float, C.c_void_p]),
+    "kgrec_reg_norm_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int, C.c_int64, C.c_float,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kgrec_reg_orth_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "kgrec_eval_scores": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p]),

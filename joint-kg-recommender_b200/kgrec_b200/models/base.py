@@ -14,6 +14,8 @@ Extensions over the reference (all optional, defaults reproduce the reference):
   * ``topk`` / ``rank_counts`` on-chip reductions of the evaluate* matrices;
   * explicit Gumbel noise (``gumbel_u=``) for bit-reproducible parity runs.
 """
+import contextlib
+import math
 import os
 
 import torch
@@ -39,6 +41,40 @@ def _embedding(weight, **kw):
     return emb
 
 
+_DEVICE_INIT = [None]
+
+
+@contextlib.contextmanager
+def device_init(device="cuda"):
+    """Construct models with their tables drawn directly on `device` (same distribution: xavier-uniform
+    bound, rows L2-normalised) instead of through the reference's CPU generator stream.  For large
+    catalogs (millions of rows: seconds on the host, milliseconds on the GPU) and benchmarks; the
+    tables are then NOT the ones the reference would draw for the same seed."""
+    prev = _DEVICE_INIT[0]
+    _DEVICE_INIT[0] = torch.device(device)
+    try:
+        yield
+    finally:
+        _DEVICE_INIT[0] = prev
+
+
+def _make_tables_on_device(module, specs, dev):
+    for s in specs:
+        attr, rows, dim, normalize = s[:4]
+        pad_rows = s[4] if len(s) > 4 else 0
+        kw = s[5] if len(s) > 5 else {}
+        bound = math.sqrt(6.0 / (rows + dim))
+        w = torch.empty(rows + pad_rows, dim, dtype=torch.float32, device=dev)
+        w[:rows].uniform_(-bound, bound)
+        if normalize:
+            w[:rows] = torch.nn.functional.normalize(w[:rows], p=2, dim=1)
+        if pad_rows:
+            w[rows:].zero_()
+        emb = nn.Embedding(rows + pad_rows, dim, device="meta", **kw)
+        emb.weight = nn.Parameter(w)
+        setattr(module, attr, emb)
+
+
 def _make_tables(module, specs):
     """Create the attribute ``nn.Embedding``s of a model the way the reference constructors
     consume torch's global generator: every ``xavier_uniform`` draw of the group first, in the
@@ -48,6 +84,8 @@ def _make_tables(module, specs):
     reference's, which is what lets a driver run be compared step for step.
 
     specs: (attribute, rows, dim, normalize[, extra zero rows, Embedding kwargs])."""
+    if _DEVICE_INIT[0] is not None:
+        return _make_tables_on_device(module, specs, _DEVICE_INIT[0])
     raw = [_init_table(s[1], s[2], normalize=False) for s in specs]
     for s, w in zip(specs, raw):
         attr, rows, dim, normalize = s[:4]

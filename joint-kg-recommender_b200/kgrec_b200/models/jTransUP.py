@@ -17,6 +17,27 @@ def build_model(FLAGS, user_total, item_total, entity_total, relation_total, i_m
                          use_st_gumbel=FLAGS.use_st_gumbel)
 
 
+def build_item2ent(item_total, pad, i_map, new_map):
+    """paddingItems (jTransUP.py:114-120) for every item at once: item -> new_map[i_map[item]][0], unaligned
+    (-1) or unmapped items -> the padding row.  Vectorised: the dicts are walked once by numpy.fromiter, not
+    once per item per forward call."""
+    import numpy as np
+    table = np.full(item_total, pad, dtype=np.int32)
+    if i_map is None or new_map is None or item_total == 0:
+        return torch.from_numpy(table)
+    n_i, n_m = len(i_map), len(new_map)
+    items = np.fromiter(i_map.keys(), dtype=np.int64, count=n_i)
+    idx = np.fromiter(i_map.values(), dtype=np.int64, count=n_i)
+    mkeys = np.fromiter(new_map.keys(), dtype=np.int64, count=n_m)
+    ments = np.fromiter((v[0] for v in new_map.values()), dtype=np.int64, count=n_m)
+    ent_of = np.full(int(max(mkeys.max(initial=-1), idx.max(initial=-1))) + 1, -1, dtype=np.int64)
+    ent_of[mkeys] = ments
+    ok = (items >= 0) & (items < item_total)
+    e = ent_of[idx[ok]]
+    table[items[ok]] = np.where(e >= 0, e, pad).astype(np.int32)
+    return torch.from_numpy(table)
+
+
 class jTransUPModel(RecModelBase):
     MODEL = _lib.KTUP
     TABLES = {"user": "user_embeddings", "item": "item_embeddings", "ent": "ent_embeddings",
@@ -45,14 +66,7 @@ class jTransUPModel(RecModelBase):
                             ("rel_embeddings", relation_total, d, True), ("norm_embeddings", relation_total, d, True)])
         # paddingItems (jTransUP.py:114-120) as a device lookup table built once:
         # item -> aligned entity row, unaligned -> the padding row
-        pad = self.ent_total - 1
-        table = torch.full((item_total,), pad, dtype=torch.int32)
-        if i_map is not None and new_map is not None:
-            for it in range(item_total):
-                if it in i_map:
-                    ent_id = new_map[i_map[it]][0]
-                    table[it] = ent_id if ent_id != -1 else pad
-        self.register_buffer("item2ent", table, persistent=False)
+        self.register_buffer("item2ent", build_item2ent(item_total, self.ent_total - 1, i_map, new_map), persistent=False)
         self._finish_init()
 
     def _apply(self, fn, *a, **kw):
