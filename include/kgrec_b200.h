@@ -380,6 +380,32 @@ int kgrec_eval_rank_count(const kgrec_tables* tables, int model, int side,
                           const float* gold_scores, const int32_t* gold_ids,
                           int32_t* counts, kgrec_stream_t stream);
 
+/* TransR full-catalog evaluation (transR.py:80-128 + projection_transR_pytorch_batch, misc.py:29-33).
+ * The reference projects the whole entity table with every query's matrix; queries of one relation
+ * share it, so the caller passes the queries SORTED BY RELATION (q / r device arrays, nq of them) with
+ * the run boundaries on the host (run g = sorted queries [run_begin_host[g], run_begin_host[g+1]) of
+ * relation run_rel_host[g]); per run the catalog shard is projected once by a hand-written FP32 kernel
+ * into `workspace` (kgrec_transr_workspace_floats floats, 16-byte aligned) and the distance kernels of
+ * the three modes above run on the projected rows.  Outputs / filter CSR / gold arrays are indexed in
+ * the sorted query order.  embedding_size % 4 == 0 and <= 128. */
+int64_t kgrec_transr_workspace_floats(int64_t nq, int64_t n_cat, int32_t dim);
+int kgrec_transr_eval_scores(const kgrec_tables* tables, int side, const void* q, const void* r, int idx_bytes,
+                             int64_t nq, const int64_t* run_begin_host, const int64_t* run_rel_host, int32_t n_runs,
+                             const float* cat, int64_t cat_ld, int64_t n_cat, int64_t id_base,
+                             const int32_t* cat_ids, float* workspace, float* out, int64_t ld_out,
+                             int32_t* status, kgrec_stream_t stream);
+int kgrec_transr_eval_topk(const kgrec_tables* tables, int side, const void* q, const void* r, int idx_bytes,
+                           int64_t nq, const int64_t* run_begin_host, const int64_t* run_rel_host, int32_t n_runs,
+                           const float* cat, int64_t cat_ld, int64_t n_cat, int64_t id_base, float* workspace,
+                           int32_t k, const int64_t* filter_ptr, const int32_t* filter_ids, uint64_t* out_keys,
+                           void* topk_workspace, int64_t topk_workspace_bytes, int32_t* status,
+                           kgrec_stream_t stream);
+int kgrec_transr_eval_rank_count(const kgrec_tables* tables, int side, const void* q, const void* r, int idx_bytes,
+                                 int64_t nq, const int64_t* run_begin_host, const int64_t* run_rel_host, int32_t n_runs,
+                                 const float* cat, int64_t cat_ld, int64_t n_cat, int64_t id_base, float* workspace,
+                                 const float* gold_scores, const int32_t* gold_ids, int32_t* counts,
+                                 int32_t* status, kgrec_stream_t stream);
+
 /* Soft-preference rec-side evaluation (use_st_gumbel = 0) on augmented rows: with raw logits as
  * mixing weights (transUP.py:108-113) r and w are linear in the logits, so each table row is
  * augmented ONCE into [x | x +/- XA | -/+ XB | x . XB] (leading dimension kgrec_pref_aug_ld(d))

@@ -620,6 +620,179 @@ k_group_step_e(const GroupArgs G, const float up0, const float* __restrict__ up_
   if (bad && status) *status = 1;
 }
 
+// --- TransE, d <= 128: the step kernel with its gather STAGED THROUGH SHARED MEMORY BY TMA ----------------------
+// north_star: "128-bit vectorised coalesced HBM loads staged through TMA into shared memory".  Every row of a
+// group -- h, t, r and the K corrupted entities -- is fetched by ONE cp.async.bulk (400 B at d = 100) issued by the
+// lane that holds its id, into the warp's own ring of S stages; a stage carries an mbarrier armed with the group's
+// byte count, so the warp waits once per group and then reads its rows with conflict-free LDS.128 (lane = chunk).
+// The ring is warp-local (the same warp produces and consumes: no CTA barrier, no empty-slot barrier -- program
+// order plus a proxy fence orders the reads of a stage before the bulk copies that refill it), and it keeps
+// (S - 1) x (3 + K) x 400 B per warp in flight without holding a register: 125 KB per SM at 8 warps x 4 stages.
+// The arithmetic and the gradient stores are k_group_step_e's.  Whether this beats register loads + L1 prefetch
+// depends on where the table lives: profiles/r02_tma_gather_ab.json (L2-resident 100k entities vs 500k / 5M).
+template <bool L1, bool DENSE, bool MARGIN, int W>
+__global__ void __launch_bounds__(W * 32, 1)
+k_group_step_e_tma(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
+                   float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
+                   int64_t* __restrict__ slot_rel, int32_t* status, const int S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const kgrec_tables& T = G.T;
+  const LossCfg& L = G.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K = L.n_neg, n_rows = 3 + K;
+  const int n_pos = static_cast<int>(L.n_pos);
+  const uint32_t n_ent = static_cast<uint32_t>(T.n_ent);
+  const uint32_t ld4 = static_cast<uint32_t>(T.ld) * 4u, d4 = static_cast<uint32_t>(T.dim) * 4u;
+  const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
+  const uint64_t pol_stream = policy_evict_first();
+  const bool act = lane * 4 < T.dim;
+  // shared-memory map: [W][S] mbarriers | [W][S][32] int32 compact ids | [W][S][n_rows] rows of d4 bytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw) + wid * S;
+  int32_t* ids_ring = reinterpret_cast<int32_t*>(smem_raw + static_cast<size_t>(W) * S * 8) + wid * S * 32;
+  const uint32_t stage_bytes = static_cast<uint32_t>(n_rows) * d4;
+  unsigned char* rows_base = smem_raw + ((static_cast<size_t>(W) * S * (8 + 128) + 127) & ~static_cast<size_t>(127)) +
+                             static_cast<size_t>(wid) * S * stage_bytes;
+  if (lane == 0)
+    for (int s = 0; s < S; ++s) mbar_init(bars + s, 1);
+  mbar_fence_init();
+  __syncwarp();
+  char* gent_b = reinterpret_cast<char*>(Gr.ent) + lane * 16;
+  char* grel_b = reinterpret_cast<char*>(Gr.rel) + lane * 16;
+  const float prm = L.param;
+  const int stride = gridDim.x * W;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool bad = false;
+  const void* pcol = lane == 0 ? G.ph : (lane == 1 ? G.pt : G.pr);
+
+  // producer half: ids of group jj -> ring slot, one bulk copy per row
+  auto issue = [&](int jj, int s) {
+    // lane 0..2: h, t, r of the positive; lane 3..3+K-1: corrupted entity of negative lane-3 (sign = head replaced)
+    int32_t v = 0;
+    if (lane < 3) {
+      const int64_t pv = load_idx(pcol, jj, G.is64);
+      const int64_t lim = lane == 2 ? T.n_rel : T.n_ent;
+      if (static_cast<uint64_t>(pv) >= static_cast<uint64_t>(lim)) bad = true; else v = static_cast<int32_t>(pv);
+    } else if (lane < n_rows) {
+      v = __ldg(G.corrupt + static_cast<uint32_t>(jj) * K + (lane - 3));
+      const uint32_t id = static_cast<uint32_t>(v < 0 ? ~v : v);
+      if (id >= n_ent) { bad = true; v = 0; }
+    }
+    ids_ring[s * 32 + lane] = v;
+    if (lane == 0) mbar_arrive_expect_tx(bars + s, stage_bytes);
+    __syncwarp();
+    if (lane < n_rows) {
+      const uint32_t id = lane < 3 ? static_cast<uint32_t>(v) : static_cast<uint32_t>(v < 0 ? ~v : v);
+      const char* src = reinterpret_cast<const char*>(lane == 2 ? T.rel : T.ent) + static_cast<uint64_t>(id) * ld4;
+      bulk_g2s(rows_base + static_cast<size_t>(s) * stage_bytes + static_cast<size_t>(lane) * d4, src, d4, bars + s);
+    }
+  };
+
+  int j = blockIdx.x * W + wid;
+  for (int s = 0, jj = j; s < S - 1 && jj < n_pos; ++s, jj += stride) issue(jj, s);
+  for (int it = 0; j < n_pos; j += stride, ++it) {
+    const int s = it % S;
+    {   // keep S - 1 groups in flight: refill the stage consumed in the previous iteration
+      const int jn = j + (S - 1) * stride;
+      if (jn < n_pos) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        issue(jn, (it + S - 1) % S);
+      }
+    }
+    mbar_wait(bars + s, static_cast<uint32_t>(it / S) & 1u);
+    const int32_t myid = ids_ring[s * 32 + lane];
+    const uint32_t st_addr = smem_u32(rows_base + static_cast<size_t>(s) * stage_bytes) + lane * 16;
+    const uint32_t ih0 = static_cast<uint32_t>(__shfl_sync(FULL, myid, 0)), it0 = static_cast<uint32_t>(__shfl_sync(FULL, myid, 1)),
+                   ir0 = static_cast<uint32_t>(__shfl_sync(FULL, myid, 2));
+    if (slot_ent) {
+      const uint32_t s0 = static_cast<uint32_t>(j) * (2 + K);
+      if (lane < 2) slot_ent[s0 + lane] = myid;
+      if (lane == 2) slot_rel[j] = myid;
+      if (lane >= 3 && lane < n_rows) slot_ent[s0 + lane - 1] = myid < 0 ? ~myid : myid;
+    }
+    float4 h = z4, t = z4, r = z4;
+    if (act) { h = lds_f4(st_addr); t = lds_f4(st_addr + d4); r = lds_f4(st_addr + 2 * d4); }
+    float up = up0;
+    if (!MARGIN) {
+      const int b = j / bp;
+      up /= static_cast<float>(min(bp, n_pos - b * bp)) * static_cast<float>(K);
+    }
+    const float4 bh = make_float4(h.x + r.x, h.y + r.y, h.z + r.z, h.w + r.w);
+    const float4 bt = make_float4(t.x - r.x, t.y - r.y, t.z - r.z, t.w - r.w);
+    const float4 ep = make_float4(bh.x - t.x, bh.y - t.y, bh.z - t.z, bh.w - t.w);
+    const float sp = warp_sum(dist_term(ep.x, L1) + dist_term(ep.y, L1) + dist_term(ep.z, L1) + dist_term(ep.w, L1));
+    float lsum = 0.f, cpos = 0.f, mys = 0.f;
+    float4 accT = z4, accH = z4;
+    uint32_t goff = (static_cast<uint32_t>(j) * (2 + K) + 2) * d4;
+#pragma unroll 2
+    for (int k = 0; k < K; ++k) {
+      const int32_t c = __shfl_sync(FULL, myid, 3 + k);
+      const bool head = c < 0;
+      const uint32_t id = static_cast<uint32_t>(head ? ~c : c);
+      float4 x = z4;
+      if (act) x = lds_f4(st_addr + (3 + k) * d4);
+      const float4 B = head ? bt : bh;
+      const float4 e = make_float4(B.x - x.x, B.y - x.y, B.z - x.z, B.w - x.w);
+      const float sn = warp_sum(dist_term(e.x, L1) + dist_term(e.y, L1) + dist_term(e.z, L1) + dist_term(e.w, L1));
+      if (lane == k) mys = sn;
+      float coef;
+      if (MARGIN) {
+        const float tt = sp - sn + prm;
+        lsum += fmaxf(tt, 0.f);
+        coef = tt > 0.f ? up : 0.f;
+        cpos += tt > 0.f ? 1.f : 0.f;
+      } else {
+        const float xx = prm * (sp - sn);
+        lsum += fmaxf(-xx, 0.f) + log1pf(expf(-fabsf(xx)));
+        const float dp = -prm / (1.f + expf(xx));
+        cpos += dp;
+        coef = dp * up;
+      }
+      if (coef != 0.f) {
+        float4 gc;
+        if (L1) {
+          gc = make_float4(coef * ddist_term(e.x, 1), coef * ddist_term(e.y, 1), coef * ddist_term(e.z, 1), coef * ddist_term(e.w, 1));
+        } else {
+          const float c2 = 2.f * coef;
+          gc = make_float4(c2 * e.x, c2 * e.y, c2 * e.z, c2 * e.w);
+        }
+        if (head) { accH.x -= gc.x; accH.y -= gc.y; accH.z -= gc.z; accH.w -= gc.w; }
+        else { accT.x -= gc.x; accT.y -= gc.y; accT.z -= gc.z; accT.w -= gc.w; }
+        if (act) {
+          if (DENSE) red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(id) * d4), gc.x, gc.y, gc.z, gc.w);
+          else stg_f4_hint(reinterpret_cast<float4*>(gent_b + goff), gc.x, gc.y, gc.z, gc.w, pol_stream);
+        }
+      } else if (!DENSE) {
+        if (act) stg_f4_hint(reinterpret_cast<float4*>(gent_b + goff), 0.f, 0.f, 0.f, 0.f, pol_stream);
+      }
+      goff += d4;
+    }
+    const float cp = cpos * up;
+    const float4 eps = make_float4(cp * ddist_term(ep.x, L1), cp * ddist_term(ep.y, L1), cp * ddist_term(ep.z, L1), cp * ddist_term(ep.w, L1));
+    const float4 gh = make_float4(accT.x + eps.x, accT.y + eps.y, accT.z + eps.z, accT.w + eps.w);
+    const float4 gt = make_float4(accH.x - eps.x, accH.y - eps.y, accH.z - eps.z, accH.w - eps.w);
+    const float4 gr = make_float4(accT.x - accH.x + eps.x, accT.y - accH.y + eps.y, accT.z - accH.z + eps.z, accT.w - accH.w + eps.w);
+    if (lane == 0) {
+      pos_scores[j] = sp;
+      group_loss[j] = lsum;
+    }
+    if (lane < K) neg_scores[static_cast<uint32_t>(j) * K + lane] = mys;
+    if (act) {
+      if (DENSE) {
+        red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(ih0) * d4), gh.x, gh.y, gh.z, gh.w);
+        red_add_f4(reinterpret_cast<float*>(gent_b + static_cast<uint64_t>(it0) * d4), gt.x, gt.y, gt.z, gt.w);
+        red_add_f4(reinterpret_cast<float*>(grel_b + static_cast<uint64_t>(ir0) * d4), gr.x, gr.y, gr.z, gr.w);
+      } else {
+        const uint32_t g0 = static_cast<uint32_t>(j) * (2 + K) * d4;
+        stg_f4_hint(reinterpret_cast<float4*>(gent_b + g0), gh.x, gh.y, gh.z, gh.w, pol_stream);
+        stg_f4_hint(reinterpret_cast<float4*>(gent_b + g0 + d4), gt.x, gt.y, gt.z, gt.w, pol_stream);
+        stg_f4_hint(reinterpret_cast<float4*>(grel_b + static_cast<uint32_t>(j) * d4), gr.x, gr.y, gr.z, gr.w, pol_stream);
+      }
+    }
+  }
+  if (bad && status) *status = 1;
+}
+
 // --- TransH (and the KTUP KG branch), d <= 128: the same treatment ------------------------------
 // With proj(v) = v - (v.w) w the residual is e' = B - proj(x), B = proj(h) + r or proj(t) - r.  Writing
 // g = -eps' for the gradient arriving at proj(x), the group needs per negative only
@@ -1119,6 +1292,26 @@ k_group_slot_ids(const void* ph, const void* pt, const void* pr, const int is64,
 
 int make_plan(const kgrec_tables* T, int model, Plan* pl);
 
+// KGREC_GROUP_STEP is an A/B / test switch: read once, not on every call of the hot path.
+static const char* group_step_env() {
+  static const char* cached = [] { const char* e = getenv("KGREC_GROUP_STEP"); return e ? e : ""; }();
+  return cached[0] ? cached : nullptr;
+}
+
+// TMA-staged variant of the TransE step kernel: encoded as 16 * warps + stages, 0 = register-load kernel.
+// KGREC_GROUP_STEP=t<w><s> forces it (w: 8 -> 8 warps, c -> 12, g -> 16; s = stages 2..6), anything else the default.
+static int group_step_tma_mode(const kgrec_tables* T, int n_neg, int reg_flags) {
+  const char* env = group_step_env();
+  if (reg_flags) return 0;
+  if (env && env[0] == 't' && env[1] && env[2]) {
+    const int W = env[1] == '8' ? 8 : (env[1] == 'c' ? 12 : 16), S = env[2] - '0';
+    if (S < 2 || S > 6) return 0;
+    const size_t smem = static_cast<size_t>(W) * S * (136 + static_cast<size_t>(3 + n_neg) * T->dim * 4) + 128;
+    return smem <= 225 * 1024 ? 16 * W + S : 0;
+  }
+  return 0;
+}
+
 static int group_check(const kgrec_tables* T, int model, Plan* pl, const void* ph, const void* pt, const void* pr,
                        int idx_bytes, int64_t n_pos, const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,
                        int loss_kind, bool allow_r = false) {
@@ -1162,7 +1355,7 @@ extern "C" int kgrec_corrupt_loss_fwd(const kgrec_tables* tables, int model, con
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   float* group_loss = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* env = getenv("KGREC_GROUP_STEP");
+  const char* env = group_step_env();
   const bool small32 = n_neg <= 32 && static_cast<double>(n_pos) * (2 + n_neg) * tables->dim * 4 < 4.0e9 &&
                        static_cast<double>(n_pos) * n_neg < 2.0e9;
   if (pl.fam == FAM_E && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
@@ -1211,7 +1404,7 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
   const GroupArgs G{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos},
                     l2_keep_fraction(static_cast<double>(tables->n_ent) * tables->ld * sizeof(float))};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const char* env = getenv("KGREC_GROUP_STEP");
+  const char* env = group_step_env();
   const bool small32 = n_neg <= 32 && static_cast<double>(n_pos) * (2 + n_neg) * tables->dim * 4 < 4.0e9 &&
                        static_cast<double>(n_pos) * n_neg < 2.0e9;
   if ((pl.fam == FAM_E || pl.fam == FAM_H) && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
@@ -1298,10 +1491,29 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
   if (reg_flags && loss_kind != KGREC_LOSS_MARGIN) { set_error("fused regularisers go with the margin loss (the KG drivers' loss)"); return KGREC_ERR_UNSUPPORTED; }
   // KGREC_GROUP_STEP (A/B runs, tests): 0 = the general kernel for every shape; n = no row prefetch;
   // 3 (TransE) / 2 (TransH) = fewer CTAs per SM, no prefetch
-  const char* env = getenv("KGREC_GROUP_STEP");
+  const char* env = group_step_env();
   const bool small32 = n_neg <= 32 && static_cast<double>(n_pos) * (2 + n_neg) * tables->dim * 4 < 4.0e9 &&
                        static_cast<double>(n_pos) * n_neg < 2.0e9;          // 32-bit slot offsets, scores kept in lanes
-  if (pl.fam == FAM_E && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
+  const int tma_mode = group_step_tma_mode(tables, n_neg, reg_flags);   // TMA-staged gather (A/B switch or the size rule)
+  if (pl.fam == FAM_E && pl.nch == 1 && small32 && tma_mode && n_neg <= 29 && tables->ld == tables->dim) {
+    const int W = tma_mode / 16, S = tma_mode % 16;
+    const size_t smem = ((static_cast<size_t>(W) * S * (8 + 128) + 127) & ~static_cast<size_t>(127)) +
+                        static_cast<size_t>(W) * S * (3 + n_neg) * tables->dim * 4;
+    int64_t ctas = (n_pos + W - 1) / W;
+    if (ctas > sm_count()) ctas = sm_count();
+#define CALL_T(L1V, DV, MV, WV)                                                                                         \
+  {                                                                                                                     \
+    auto kern = k_group_step_e_tma<L1V, DV, MV, WV>;                                                                    \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));      \
+    kern<<<static_cast<int>(ctas), WV * 32, smem, st>>>(G, grad_loss, pos_scores, neg_scores, group_loss, *grads, slot_ent_ids, slot_rel_ids, status, S); \
+  }
+#define CALL_TW(L1V, DV, MV) { if (W == 8) CALL_T(L1V, DV, MV, 8) else if (W == 12) CALL_T(L1V, DV, MV, 12) else CALL_T(L1V, DV, MV, 16) }
+    const bool dn = grads->mode == 1, mg = loss_kind == KGREC_LOSS_MARGIN;
+    if (tables->l1) { if (dn) { if (mg) CALL_TW(true, true, true) else CALL_TW(true, true, false) } else { if (mg) CALL_TW(true, false, true) else CALL_TW(true, false, false) } }
+    else { if (dn) { if (mg) CALL_TW(false, true, true) else CALL_TW(false, true, false) } else { if (mg) CALL_TW(false, false, true) else CALL_TW(false, false, false) } }
+#undef CALL_TW
+#undef CALL_T
+  } else if (pl.fam == FAM_E && pl.nch == 1 && small32 && !(env && env[0] == '0')) {
 #define CALL_E(L1V, DV, MV)                                                                                      \
   {                                                                                                              \
     if (env && env[0] == 'n')                                                                                    \
