@@ -246,16 +246,19 @@ int kgrec_hashset_build(const uint64_t* keys, int64_t n, uint64_t* table, int64_
 /* getTrainTripleBatch + corrupt_head/tail_filter (data.py:12-56): n_neg negatives per positive,
  * head or tail with probability 1/2, uniform entity, redrawn while equal to the original or a
  * known triple (table == NULL: unfiltered).  Output: the group-compact int32 format of
- * kgrec_corrupt_loss_* (>= 0 tail replaced, < 0 head replaced by ~value). */
+ * kgrec_corrupt_loss_* (>= 0 tail replaced, < 0 head replaced by ~value).  After 64 rejected draws
+ * the kernel scans on from the last draw for the first valid id (the reference would keep drawing);
+ * if a key has NO valid negative (where the reference never returns) the last draw is emitted and
+ * *status (optional int32[1]) is set to 2. */
 int kgrec_sample_corrupt(const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
                          int32_t n_neg, int64_t n_ent, int64_t n_rel,
                          const uint64_t* table, int64_t capacity, uint64_t seed,
-                         int32_t* corrupt, kgrec_stream_t stream);
+                         int32_t* corrupt, int32_t* status, kgrec_stream_t stream);
 /* getNegRatings (data.py:64-85): n_neg negative items per (user, positive item), uniform,
  * redrawn while equal to the positive or a known item of the user. */
 int kgrec_sample_neg_items(const void* u, const void* pi, int idx_bytes, int64_t n, int32_t n_neg,
                            int64_t n_item, const uint64_t* table, int64_t capacity, uint64_t seed,
-                           int32_t* neg_items, kgrec_stream_t stream);
+                           int32_t* neg_items, int32_t* status, kgrec_stream_t stream);
 
 /* ---- sparse-row optimizer -----------------------------------------
  * Replaces the reference's dense optimizer step and clip_grad_norm (utils/trainer.py:63-81,

@@ -543,8 +543,9 @@ __device__ __noinline__ uint32_t topk_insert_candidates(unsigned mask, uint32_t 
 // (pair, dim) for L1 / L2, 4 for the hyperplane form -- the issue-rate bound of the path.
 // Query vectors sit in shared memory and are read as warp-wide broadcasts; catalog rows are
 // read as one 128-bit load per lane.  Rows whose length in 16-byte units is even (d = 128)
-// would put a quarter-warp on one bank group, so the lanes then walk the dimensions in a
-// skewed order (chunk k + lane % 8): conflict-free on dense rows, no padding needed.
+// would put a quarter-warp on one bank group, so such tiles are stored with a row pitch of d + 4
+// floats (tile_pitch(): one bulk copy per row): conflict-free, and every lane walks the dimensions in
+// the same order, which keeps the query loads warp broadcasts.
 //
 // Work distribution: the (query tile x catalog tile) units are laid out query-tile-major and
 // cut into gridDim.x equal contiguous ranges (one resident CTA per SM each), so every CTA
@@ -556,6 +557,13 @@ constexpr int RQ = 8;                         // queries per warp
 struct TiledSmem {
   size_t bars, q, w, gold, tiles, lists, total;
 };
+// Row pitch of a catalog tile in shared memory (floats).  A lane reads one 16-byte chunk of "its" row per step, so
+// 8 consecutive rows must land on 8 different bank groups: true when the row is an odd number of 16-byte units long
+// (d = 100); rows an even number of units long (d = 128, 64, 32) are stored one unit apart (pitch d + 4, one bulk copy
+// per row instead of one per tile).  Every lane then walks the dimensions in the same order, so the query vectors stay
+// warp broadcasts at immediate offsets.  (Round 1 walked such rows in a lane-skewed order instead; with the chunk-major
+// query tile that turned every query load into an 8-way bank conflict: 0.23 of the FP32 bound at d = 128.)
+__host__ __device__ inline int tile_pitch(int d) { return ((d >> 2) & 1) ? d : d + 4; }
 __host__ __device__ inline TiledSmem tiled_smem_layout(int kind, int mode, int d, int tn, int stages, int k, int warps) {
   TiledSmem s{};
   const int TQT = RQ * warps;
@@ -566,7 +574,7 @@ __host__ __device__ inline TiledSmem tiled_smem_layout(int kind, int mode, int d
   if (kind == KIND_HYPER) { s.w = off; off += static_cast<size_t>(TQT) * d * sizeof(float); }
   if (mode == MODE_RANK) { s.gold = off; off += static_cast<size_t>(TQT) * 2 * sizeof(uint32_t); }
   off = (off + 127) & ~static_cast<size_t>(127);
-  s.tiles = off; off += static_cast<size_t>(stages) * tn * d * sizeof(float);
+  s.tiles = off; off += static_cast<size_t>(stages) * tn * tile_pitch(d) * sizeof(float);
   if (mode == MODE_TOPK) { s.lists = off; off += static_cast<size_t>(TQT) * k * sizeof(uint64_t); }
   s.total = off;
   return s;
@@ -589,7 +597,8 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
   [[maybe_unused]] float* sW = reinterpret_cast<float*>(smem_raw + L.w);
   [[maybe_unused]] uint32_t* sGold = reinterpret_cast<uint32_t*>(smem_raw + L.gold);
   float* tiles = reinterpret_cast<float*>(smem_raw + L.tiles);
-  const bool dense = A.cat_ld == d;           // strided catalogs need one copy per row
+  const int pitch = tile_pitch(d);
+  const bool dense = A.cat_ld == d && pitch == d;   // strided catalogs / padded tiles need one copy per row
 
   const int64_t n_tiles = (A.n_cat + TN - 1) / TN;
   const int64_t n_qtiles = (A.nq + TQT - 1) / TQT;
@@ -610,7 +619,7 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     const int s = static_cast<int>(g % stages);
     const int64_t row0 = ((u_begin + g) % n_tiles) * TN;
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
-    float* dst = tiles + static_cast<size_t>(s) * TN * d;
+    float* dst = tiles + static_cast<size_t>(s) * TN * pitch;
     if (lane == 0) {
       if (g >= stages) mbar_wait(empty + s, static_cast<uint32_t>(((g / stages) - 1) & 1));
       mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(rows) * d * sizeof(float));
@@ -620,7 +629,7 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       if (lane == 0) bulk_g2s(dst, A.cat + row0 * A.cat_ld, static_cast<uint32_t>(rows) * d * sizeof(float), full + s);
     } else {
       for (int r = lane; r < rows; r += 32)
-        bulk_g2s(dst + r * d, A.cat + (row0 + r) * A.cat_ld, d * sizeof(float), full + s);
+        bulk_g2s(dst + r * pitch, A.cat + (row0 + r) * A.cat_ld, d * sizeof(float), full + s);
     }
   };
   const int prefetch = stages - 1;
@@ -636,13 +645,10 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
   [[maybe_unused]] const float* wq = sW + wid * RQ * d;
   [[maybe_unused]] const uint32_t* gq = sGold + wid * RQ * 2;
   const int nk4 = d >> 2;
-  // Dimension walk of row n starts at chunk (n & 7) when rows are an even number of 16-byte
-  // units long: conflict-free (8 consecutive rows -> 8 bank groups) AND a function of the row's
-  // global id only, so a (query, row) score is bit-identical wherever the row sits (tile, lane,
-  // shard, gathered sub-catalog).  Tiles start at multiples of 32 rows, so for contiguous
-  // catalogs the start chunk is a per-lane constant.
-  const bool use_skew = (nk4 & 1) == 0;
-  const int skew0 = use_skew ? static_cast<int>((A.id_base + lane) & 7) : 0;
+  // Every row is walked in the same dimension order, so a (query, row) score is bit-identical wherever the row
+  // sits (tile, lane, shard, gathered sub-catalog).
+  constexpr bool use_skew = false;            // see tile_pitch(): padded tiles replaced the skewed dimension walk
+  const int skew0 = 0;
   int64_t cur_qt = -1, q0 = 0;
 
   // (re)load this warp's 8 query vectors and reset its per-query state
@@ -731,7 +737,7 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     }
     const int s = static_cast<int>(g % stages);
     if (wid == 0 && g + prefetch < my_units) issue_tile(g + prefetch);
-    const float* tile = tiles + static_cast<size_t>(s) * TN * d;
+    const float* tile = tiles + static_cast<size_t>(s) * TN * pitch;
     const int64_t row0 = ti * TN;
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
     mbar_wait(full + s, static_cast<uint32_t>((g / stages) & 1));
@@ -742,7 +748,7 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     for (int qi = 0; qi < RQ; ++qi)
 #pragma unroll
       for (int j = 0; j < RN; ++j) acc2[qi][j] = 0ull;
-    const float* xrow = tile + lane * d;
+    const float* xrow = tile + lane * pitch;
     [[maybe_unused]] int skj[RN];
 #pragma unroll
     for (int j = 0; j < RN; ++j) {
@@ -761,7 +767,7 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     for (int j = 0; j < RN; ++j) {                                                          \
       kj[j] = kk;                                                                           \
       if constexpr (IDS) { kj[j] = (k4) + skj[j]; if (kj[j] >= nk4) kj[j] -= nk4; }         \
-      xv[j] = *reinterpret_cast<const ulonglong2*>(xrow + j * 32 * d + 4 * kj[j]);          \
+      xv[j] = *reinterpret_cast<const ulonglong2*>(xrow + j * 32 * pitch + 4 * kj[j]);      \
     }
 #define KGREC_QVEC(base, qi, j) (reinterpret_cast<const ulonglong2*>(base)[(IDS ? kj[j] : kk) * RQ + (qi)])
 

@@ -41,11 +41,13 @@ __global__ void __launch_bounds__(256) k_rows_mark(const MarkArgs A, int32_t* st
     const kgrec_mark_seg& S = A.seg[s];
     int64_t v = load_idx(S.ids, i - A.begin[s], S.idx_bytes == 8);
     if (S.compact && v < 0) v = ~v;
+    // out-of-range ids: the training kernels clamp them to row 0 (and raise the status word), so that is where
+    // their gradient went -- mark the same row, or its accumulator would never be cleared
     if (S.remap) {
-      if (static_cast<uint64_t>(v) >= static_cast<uint64_t>(S.n_remap)) { if (status) *status = 1; continue; }
+      if (static_cast<uint64_t>(v) >= static_cast<uint64_t>(S.n_remap)) { if (status) *status = 1; v = 0; }
       v = __ldg(S.remap + v);
     }
-    if (static_cast<uint64_t>(v) >= static_cast<uint64_t>(S.rows)) { if (status) *status = 1; continue; }
+    if (static_cast<uint64_t>(v) >= static_cast<uint64_t>(S.rows)) { if (status) *status = 1; v = 0; }
     S.marks[v] = A.epoch;
   }
 }

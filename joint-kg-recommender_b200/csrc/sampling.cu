@@ -59,6 +59,7 @@ struct SampleArgs {
   const uint64_t* table; uint64_t mask;   // table == nullptr: unfiltered
   uint64_t seed;
   int32_t* out;
+  int32_t* status;           // optional: set to 2 when a key has no valid negative at all
 };
 
 constexpr int kMaxAttempts = 64;
@@ -71,16 +72,28 @@ __global__ void __launch_bounds__(256) k_sample_corrupt(const SampleArgs A) {
     const uint64_t r = static_cast<uint64_t>(load_idx(A.c, j, A.is64));
     const bool head = philox_uniform_bits(A.seed, static_cast<uint64_t>(m), 0xffffffffu) & 1u;      // random.random() < 0.5
     uint32_t ent = 0;
-    for (int attempt = 0; attempt < kMaxAttempts; ++attempt) {
+    auto valid = [&](uint32_t e) {
+      if (e == (head ? h : t)) return false;
+      if (A.table) {
+        const uint64_t key = head ? triple_key(e, r, t, A.n_cat, A.n_rel) : triple_key(h, r, e, A.n_cat, A.n_rel);
+        if (hashset_contains(A.table, A.mask, key)) return false;
+      }
+      return true;
+    };
+    bool found = false;
+    for (int attempt = 0; attempt < kMaxAttempts && !found; ++attempt) {
       const uint32_t bits = philox_uniform_bits(A.seed, static_cast<uint64_t>(m), static_cast<uint32_t>(attempt));
       ent = static_cast<uint32_t>((static_cast<uint64_t>(bits) * static_cast<uint64_t>(A.n_cat)) >> 32);   // randrange(entityTotal)
-      if (ent == (head ? h : t)) continue;
-      if (A.table) {
-        const uint64_t key = head ? triple_key(ent, r, t, A.n_cat, A.n_rel) : triple_key(h, r, ent, A.n_cat, A.n_rel);
-        if (hashset_contains(A.table, A.mask, key)) continue;
-      }
-      break;
+      found = valid(ent);
     }
+    // The reference loops until a draw is valid (data.py:23-56).  After kMaxAttempts rejections (a key whose valid set
+    // is a tiny share of the catalog) fall back to a scan from the last draw for the first valid id; if there is none
+    // at all -- where the reference would never return -- the last draw is emitted and A.status is raised.
+    for (int64_t s = 1; s < A.n_cat && !found; ++s) {
+      const uint32_t e = static_cast<uint32_t>((static_cast<uint64_t>(ent) + s) % static_cast<uint64_t>(A.n_cat));
+      if (valid(e)) { ent = e; found = true; }
+    }
+    if (!found && A.status) *A.status = 2;
     A.out[m] = head ? ~static_cast<int32_t>(ent) : static_cast<int32_t>(ent);
   }
 }
@@ -91,13 +104,20 @@ __global__ void __launch_bounds__(256) k_sample_items(const SampleArgs A) {
     const int64_t j = m / A.n_neg;
     const uint64_t u = static_cast<uint64_t>(load_idx(A.a, j, A.is64)), pi = static_cast<uint64_t>(load_idx(A.b, j, A.is64));
     uint32_t it = 0;
-    for (int attempt = 0; attempt < kMaxAttempts; ++attempt) {
+    auto valid = [&](uint32_t e) {
+      return e != pi && !(A.table && hashset_contains(A.table, A.mask, u * static_cast<uint64_t>(A.n_cat) + e));
+    };
+    bool found = false;
+    for (int attempt = 0; attempt < kMaxAttempts && !found; ++attempt) {
       const uint32_t bits = philox_uniform_bits(A.seed, static_cast<uint64_t>(m), static_cast<uint32_t>(attempt));
       it = static_cast<uint32_t>((static_cast<uint64_t>(bits) * static_cast<uint64_t>(A.n_cat)) >> 32);
-      if (it == pi) continue;
-      if (A.table && hashset_contains(A.table, A.mask, u * static_cast<uint64_t>(A.n_cat) + it)) continue;
-      break;
+      found = valid(it);
     }
+    for (int64_t s = 1; s < A.n_cat && !found; ++s) {      // dense users: scan on from the last draw (see k_sample_corrupt)
+      const uint32_t e = static_cast<uint32_t>((static_cast<uint64_t>(it) + s) % static_cast<uint64_t>(A.n_cat));
+      if (valid(e)) { it = e; found = true; }
+    }
+    if (!found && A.status) *A.status = 2;
     A.out[m] = static_cast<int32_t>(it);
   }
 }
@@ -141,12 +161,12 @@ static int sample_check(const void* a, const void* b, int idx_bytes, int64_t n_p
 
 extern "C" int kgrec_sample_corrupt(const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
                                     int32_t n_neg, int64_t n_ent, int64_t n_rel, const uint64_t* table,
-                                    int64_t capacity, uint64_t seed, int32_t* corrupt, kgrec_stream_t stream) {
+                                    int64_t capacity, uint64_t seed, int32_t* corrupt, int32_t* status, kgrec_stream_t stream) {
   int rc = sample_check(ph, pt, idx_bytes, n_pos, n_neg, n_ent, table, capacity, corrupt);
   if (rc) return rc;
   if (!pr || n_rel < 1) { set_error("negative sampler: relations missing"); return KGREC_ERR_INVALID; }
   if (n_pos == 0) return KGREC_OK;
-  const SampleArgs A{ph, pt, pr, idx_bytes == 8, n_pos, n_neg, n_ent, n_rel, table, table ? static_cast<uint64_t>(capacity - 1) : 0, seed, corrupt};
+  const SampleArgs A{ph, pt, pr, idx_bytes == 8, n_pos, n_neg, n_ent, n_rel, table, table ? static_cast<uint64_t>(capacity - 1) : 0, seed, corrupt, status};
   k_sample_corrupt<<<grid1d(n_pos * n_neg), 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;
@@ -154,11 +174,11 @@ extern "C" int kgrec_sample_corrupt(const void* ph, const void* pt, const void* 
 
 extern "C" int kgrec_sample_neg_items(const void* u, const void* pi, int idx_bytes, int64_t n, int32_t n_neg, int64_t n_item,
                                       const uint64_t* table, int64_t capacity, uint64_t seed, int32_t* neg_items,
-                                      kgrec_stream_t stream) {
+                                      int32_t* status, kgrec_stream_t stream) {
   int rc = sample_check(u, pi, idx_bytes, n, n_neg, n_item, table, capacity, neg_items);
   if (rc) return rc;
   if (n == 0) return KGREC_OK;
-  const SampleArgs A{u, pi, nullptr, idx_bytes == 8, n, n_neg, n_item, 1, table, table ? static_cast<uint64_t>(capacity - 1) : 0, seed, neg_items};
+  const SampleArgs A{u, pi, nullptr, idx_bytes == 8, n, n_neg, n_item, 1, table, table ? static_cast<uint64_t>(capacity - 1) : 0, seed, neg_items, status};
   k_sample_items<<<grid1d(n * n_neg), 256, 0, static_cast<cudaStream_t>(stream)>>>(A);
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;

@@ -88,9 +88,9 @@ _SIGNATURES = {
     "kgrec_hashset_capacity": (C.c_int64, [C.c_int64]),
     "kgrec_hashset_build": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "kgrec_sample_corrupt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64,
-                                       C.c_int64, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
+                                       C.c_int64, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kgrec_sample_neg_items": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64,
-                                         C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
+                                         C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kgrec_rows_mark": (C.c_int, [C.POINTER(MarkSeg), C.c_int, C.c_int32, C.c_void_p, C.c_void_p]),
     "kgrec_rows_sqnorm": (C.c_int, [C.POINTER(OptTable), C.c_int, C.c_int32, C.c_void_p, C.c_void_p]),
     "kgrec_rows_update": (C.c_int, [C.POINTER(OptTable), C.c_int, C.c_int32, C.c_int, C.c_float, C.c_float, C.c_float,

@@ -127,3 +127,91 @@ def load_checkpoint(path, model, optimizer=None):
     if optimizer is not None and ck.get("optimizer_state_dict"):
         optimizer.load_state_dict(ck["optimizer_state_dict"])
     return ck.get("step", 0), ck.get("best_step", 0), ck.get("best_dev_performance", 0.0)
+
+
+# ---- vocabularies and the item <-> entity alignment of the joint models -------------------------------------
+def load_vocab(path):
+    """`u_map.dat` / `i_map.dat` / `e_map.dat` / `r_map.dat`: lines `mapped_id \\t original_id`;
+    returns {original_id (str): mapped_id (int)} as loadVocab does (load_rating_data.py:6-16,
+    load_triple_data.py:32-43); lines without exactly two fields are skipped."""
+    vocab = {}
+    with open(path, "r", encoding="utf-8") as fin:
+        for line in fin:
+            parts = line.strip().split("\t")
+            if len(parts) != 2:
+                continue
+            vocab[parts[1]] = int(parts[0])
+    return vocab
+
+
+def load_item_kg_map(path):
+    """`i2kg_map.tsv`: lines `original item id \\t title \\t entity uri` -> (i2kg, kg2i) as loadR2KgMap
+    (load_kg_rating_data.py:5-18)."""
+    i2kg, kg2i = {}, {}
+    with open(path, "r", encoding="utf-8") as fin:
+        for line in fin:
+            parts = line.strip().split("\t")
+            if len(parts) != 3:
+                continue
+            i2kg[parts[0]] = parts[2]
+            kg2i[parts[2]] = parts[0]
+    return i2kg, kg2i
+
+
+def rebuild_entity_item_vocab(map1, map2, links):
+    """rebuildEntityItemVocab (load_kg_rating_data.py:21-48): the joint vocabulary of entities (map1: uri -> id)
+    and items (map2: original id -> id) linked by `links` (uri -> original item id).  Returns
+    (new_map {joint index: (entity id | -1, item id | -1)}, remap1 {entity id: joint index},
+    remap2 {item id: joint index}, number of aligned pairs) -- the reference's return values, built with the
+    same iteration order (dict order of map1, then of map2)."""
+    new_map, remap1, remap2, has_map2 = {}, {}, {}, {}
+    index = 0
+    for org1, id1 in map1.items():
+        mapped2 = -1
+        org2 = links.get(org1)
+        if org2 is not None and org2 in map2:
+            mapped2 = map2[org2]
+            has_map2[org2] = index
+        new_map[index] = (id1, mapped2)
+        remap1[id1] = index
+        index += 1
+    for org2, id2 in map2.items():
+        if org2 in has_map2:
+            remap2[id2] = has_map2[org2]
+            continue
+        new_map[index] = (-1, id2)
+        remap2[id2] = index
+        index += 1
+    return new_map, remap1, remap2, len(has_map2)
+
+
+def item_to_entity_table(item_total, pad, i_remap, ikg_map):
+    """The device lookup jTransUPModel needs (item -> aligned entity row, unaligned -> the padding row):
+    paddingItems (jTransUP.py:114-120) over every item, vectorised (models/jTransUP.build_item2ent)."""
+    from .models.jTransUP import build_item2ent
+    return build_item2ent(item_total, pad, i_remap, ikg_map)
+
+
+class JointDataset:
+    """Everything `load_kg_rating_data.load_data` (load_kg_rating_data.py:51-65) returns, parsed once:
+    rating / triple files as int32 arrays (with the reference's list / dict views on demand), the four
+    vocabularies, and the item <-> entity alignment."""
+
+    def __init__(self, data_path, rec_eval_files=(), kg_eval_files=(), use_cache=True):
+        kg = os.path.join(data_path, "kg")
+        self.rating_train = RatingFile(os.path.join(data_path, "train.dat"), use_cache)
+        self.rating_eval = [RatingFile(os.path.join(data_path, f), use_cache) for f in rec_eval_files]
+        self.triple_train = TripleFile(os.path.join(kg, "train.dat"), use_cache)
+        self.triple_eval = [TripleFile(os.path.join(kg, f), use_cache) for f in kg_eval_files]
+        self.u_map = load_vocab(os.path.join(data_path, "u_map.dat"))
+        self.i_map = load_vocab(os.path.join(data_path, "i_map.dat"))
+        self.e_map = load_vocab(os.path.join(kg, "e_map.dat"))
+        self.r_map = load_vocab(os.path.join(kg, "r_map.dat"))
+        self.i2kg, self.kg2i = load_item_kg_map(os.path.join(data_path, "i2kg_map.tsv"))
+        self.ikg_map, self.e_remap, self.i_remap, self.aligned = rebuild_entity_item_vocab(self.e_map, self.i_map, self.kg2i)
+
+    def totals(self):
+        """(user_total, item_total, entity_total, relation_total) as knowledgable_recommendation.run computes
+        them for -noshare_embeddings (knowledgable_recommendation.py:455-458)."""
+        return (max(len(self.u_map), max(self.u_map.values())), max(len(self.i_remap), max(self.i_remap.keys())),
+                max(len(self.e_remap), max(self.e_remap.keys())), max(len(self.r_map), max(self.r_map.values())))

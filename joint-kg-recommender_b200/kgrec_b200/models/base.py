@@ -130,10 +130,32 @@ class KGRecModule(nn.Module):
             param.requires_grad = True
 
     # -- plumbing -------------------------------------------------------------
+    # full-catalog evaluation kernels: embedding_size % 4 == 0 and <= 256 (TransR: <= 128); the training
+    # kernels take any embedding_size <= 512
+    EVAL_MAX_DIM = 256
+
     def _finish_init(self):
         """The reference moves every table to the GPU when one is visible (misc.py:11-16)."""
+        d = self.embedding_size
+        if d % 4 or d > self.EVAL_MAX_DIM:
+            # the reference's drivers call evaluate* eval_interval_steps into a run: say so now, not there
+            import warnings
+            warnings.warn("kgrec_b200: %s with embedding_size %d can be trained but not evaluated: evaluate* / topk need a "
+                          "multiple of 4, <= %d (the call will raise)" % (type(self).__name__, d, self.EVAL_MAX_DIM),
+                          stacklevel=3)
+        self._check_every = int(os.environ.get("KGREC_CHECK_EVERY", "0"))
+        self._calls = 0
         if torch.cuda.is_available():
             self.cuda()
+
+    def _maybe_check(self):
+        """Out-of-range ids: the kernels clamp them to row 0 and raise a device status word (the reference's
+        nn.Embedding would assert).  It is read back -- a device sync -- at the evaluate* calls, which the
+        drivers follow with a .cpu() anyway, and every KGREC_CHECK_EVERY-th scoring call when that is set."""
+        if self._check_every:
+            self._calls += 1
+            if self._calls % self._check_every == 0:
+                self.check_indices()
 
     def _weights(self):
         return {k: getattr(self, attr).weight for k, attr in self.TABLES.items()}
@@ -182,8 +204,10 @@ class KGRecModule(nn.Module):
         if gumbel_u is not None:
             gumbel_u = gumbel_u.to(dev, torch.float32).contiguous()
         seed = self._next_seed() if (self.use_st_gumbel and gumbel_u is None) else 0
-        return KF.ScoreFunction.apply(self._cfg(model, seed), a, b, c, gumbel_u, self._status_buf(dev),
-                                      *self._tables_for(model))
+        out = KF.ScoreFunction.apply(self._cfg(model, seed), a, b, c, gumbel_u, self._status_buf(dev),
+                                     *self._tables_for(model))
+        self._maybe_check()
+        return out
 
     def _rank_loss(self, model, pos, neg, loss, param, batch_pos=None, gumbel_u=None):
         dev = self._require_cuda()
@@ -268,4 +292,7 @@ class KGRecModule(nn.Module):
                 return torch.zeros((0, kw.get("k", 10)), dtype=torch.int64, device=dev)
             return torch.zeros(0, dtype=torch.int32, device=dev)
         T = KF.make_tables(self._weights(), self.embedding_size, self.L1_flag, self.use_st_gumbel, self._item2ent)
-        return KE.run(T, model, side, q, r, mode, **kw)
+        out = KE.run(T, model, side, q, r, mode, **kw)
+        if mode == "scores":                     # the drivers' full-matrix path: its caller copies to the host next
+            self.check_indices()
+        return out

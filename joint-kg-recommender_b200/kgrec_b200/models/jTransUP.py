@@ -123,16 +123,26 @@ class jTransUPModel(RecModelBase):
         KF.count_launches(1)
         return out
 
+    def _sub_catalog_unsupported(self, ids):
+        # The reference honours all_i_ids / all_e_ids only when is_share (jTransUP.py:166-181, 196-199); -model_type
+        # jtransup forces share_embeddings False (base.py:122-123), so the stock drivers never get here.
+        if self.is_share and ids is not None:
+            raise NotImplementedError("jTransUPModel(isShare=True): evaluation on a sub-catalog (all_i_ids / all_e_ids) "
+                                      "is not built; the reference's drivers always run jtransup with isShare=False")
+
     def evaluateRec(self, u_ids, all_i_ids=None, gumbel_u=None):
+        self._sub_catalog_unsupported(all_i_ids)
         return self._rec_scores(u_ids, gumbel_u)
 
     def _ent_catalog(self):
         return self.ent_embeddings.weight.detach()      # includes the padding row (jTransUP.py:195)
 
     def evaluateHead(self, t, r, all_e_ids=None):
+        self._sub_catalog_unsupported(all_e_ids)
         return self._eval(_lib.TRANSH, _lib.SIDE_HEAD, t, r, "scores", catalog=self._ent_catalog())
 
     def evaluateTail(self, h, r, all_e_ids=None):
+        self._sub_catalog_unsupported(all_e_ids)
         return self._eval(_lib.TRANSH, _lib.SIDE_TAIL, h, r, "scores", catalog=self._ent_catalog())
 
     def topk(self, side, q, r, k=10, filter_csr=None, catalog=None, id_base=0):

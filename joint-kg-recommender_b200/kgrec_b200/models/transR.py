@@ -14,6 +14,7 @@ def build_model(FLAGS, user_total, item_total, entity_total, relation_total, i_m
 
 class TransRModel(KGModelBase):
     MODEL = _lib.TRANSR
+    EVAL_MAX_DIM = 128          # k_transr_project keeps M_r^T (d x d) and a 128-row tile in shared memory
     TABLES = {"ent": "ent_embeddings", "rel": "rel_embeddings", "proj": "proj_embeddings"}
 
     def __init__(self, L1_flag, embedding_size, ent_total, rel_total):
@@ -65,6 +66,7 @@ class TransRModel(KGModelBase):
                                                 KF._ptr(self._status_buf(dev)), KF._stream()))
         out = torch.empty_like(res)
         out[order] = res
+        self.check_indices()
         return out
 
     def evaluateHead(self, t, r, all_e_ids=None):

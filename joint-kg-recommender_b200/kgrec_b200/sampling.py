@@ -20,7 +20,24 @@ class _KnownSet:
         KF.count_launches(1)
 
 
-class TripleNegativeSampler:
+class _Checked:
+    """status word shared by both samplers: 2 = some key had no valid negative at all (the reference's
+    rejection loop would never have returned there, utils/data.py:23-56, 64-85)."""
+
+    def _status(self):
+        if getattr(self, "status", None) is None:
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self.status
+
+    def check(self):
+        """Raise if a sample() since the last check found a key without any valid negative (device sync)."""
+        if getattr(self, "status", None) is not None and int(self.status.item()) != 0:
+            self.status.zero_()
+            raise RuntimeError("kgrec_b200: a negative sampler key has no valid negative (every candidate is the "
+                               "positive or a known triple / rating)")
+
+
+class TripleNegativeSampler(_Checked):
     """known_triples: [n, 3] (h, t, r) integer tensor of every triple negatives must avoid (the
     drivers pass train + valid + test dicts when -filter_wrong_corrupted, the default), or None."""
 
@@ -40,12 +57,12 @@ class TripleNegativeSampler:
         _lib.check(_lib.load().kgrec_sample_corrupt(
             KF._ptr(h), KF._ptr(t), KF._ptr(r), h.element_size(), h.numel(), n_neg, self.n_ent, self.n_rel,
             KF._ptr(tab.table) if tab else None, tab.capacity if tab else 0, int(seed) & 0xFFFFFFFFFFFFFFFF,
-            KF._ptr(out), KF._stream()))
+            KF._ptr(out), KF._ptr(self._status()), KF._stream()))
         KF.count_launches(1)
         return out
 
 
-class RatingNegativeSampler:
+class RatingNegativeSampler(_Checked):
     """known_ratings: [n, 2] (u, i) pairs negatives must avoid (train + eval dicts), or None."""
 
     def __init__(self, n_item, known_ratings=None, device="cuda"):
@@ -62,6 +79,6 @@ class RatingNegativeSampler:
         _lib.check(_lib.load().kgrec_sample_neg_items(
             KF._ptr(u), KF._ptr(pi), u.element_size(), u.numel(), n_neg, self.n_item,
             KF._ptr(tab.table) if tab else None, tab.capacity if tab else 0, int(seed) & 0xFFFFFFFFFFFFFFFF,
-            KF._ptr(out), KF._stream()))
+            KF._ptr(out), KF._ptr(self._status()), KF._stream()))
         KF.count_launches(1)
         return out

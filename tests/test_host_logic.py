@@ -254,3 +254,44 @@ def test_corrupt_format_encoding_round_trip():
     # the slot row ids the step kernels emit are [h, t, corrupted_1..K] per group
     want = torch.cat([h.view(-1, 1), t.view(-1, 1), ce.view(n_pos, K)], dim=1).reshape(-1)
     assert want.numel() == n_pos * (2 + K)
+
+
+def test_vocab_and_alignment_loaders_match_the_reference(tmp_path):
+    """loadVocab / loadR2KgMap / rebuildEntityItemVocab (load_rating_data.py:6-16,
+    load_kg_rating_data.py:5-48) and the item -> entity table against the reference's own loaders on a
+    synthetic dataset in its on-disk layout."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import make_ref
+    import synth_dataset
+    if not make_ref.available():
+        pytest.skip("baseline/_ref not built")
+    for p in reversed(make_ref.env_paths()):
+        sys.path.insert(0, p)
+    import gflags  # noqa: F401
+    from jTransUP.data import load_kg_rating_data as ref_joint, load_rating_data as ref_rec, load_triple_data as ref_kg
+    from jTransUP.models.jTransUP import jTransUPModel as RefKTUP
+    from kgrec_b200 import dataio
+    from kgrec_b200.models.jTransUP import build_item2ent
+    info = synth_dataset.write_dataset(str(tmp_path), users=40, items=90, ratings=900, entities=70, relations=5,
+                                       triples=800, aligned_frac=0.6)
+    base = info["path"]
+    ds = dataio.JointDataset(base, ["valid.dat"], ["valid.dat"], use_cache=False)
+    assert ds.u_map == ref_rec.loadVocab(os.path.join(base, "u_map.dat"))
+    assert ds.e_map == ref_kg.loadVocab(os.path.join(base, "kg", "e_map.dat"))
+    i2kg, kg2i = ref_joint.loadR2KgMap(os.path.join(base, "i2kg_map.tsv"))
+    assert (ds.i2kg, ds.kg2i) == (i2kg, kg2i)
+    want = ref_joint.rebuildEntityItemVocab(ds.e_map, ds.i_map, kg2i)
+    assert (ds.ikg_map, ds.e_remap, ds.i_remap, ds.aligned) == want
+    out = ref_joint.load_data(base, ["valid.dat"], ["valid.dat"], 32)
+    assert out[3] == ds.i_remap and out[6] == ds.e_remap and out[8] == ds.ikg_map
+    assert out[0][2] == ds.rating_train.as_list() and out[4][2] == ds.triple_train.as_list()
+    assert out[0][3] == ds.rating_train.rating_dict() and out[4][4] == ds.triple_train.tail_dict()
+    # the item -> entity table == the reference's per-call paddingItems over every item
+    _, item_total, entity_total, rel_total = ds.totals()
+    ref_model = RefKTUP(False, 4, 3, item_total, entity_total, rel_total, ds.i_remap, ds.ikg_map, False, False)
+    pad = entity_total
+    want_table = ref_model.paddingItems(list(range(item_total)), pad)
+    got = build_item2ent(item_total, pad, ds.i_remap, ds.ikg_map).tolist()
+    assert got == want_table
+    assert sum(1 for e in got if e != pad) == ds.aligned == info["aligned"]
