@@ -439,6 +439,12 @@ def run_ours(args):
             model.zero_grad(set_to_none=True)
             model.loss_step_corrupt(tuple(small[:3]), small[3], margin=1.0)
         out["single_batch_latency_us"] = timeit(one_batch, reps=50, warm=5) * 1e3
+        gs = model.graphed_loss_step(BATCH, K_NEG, margin=1.0)
+        for buf, src in ((gs.h, small[0]), (gs.t, small[1]), (gs.r, small[2]), (gs.corrupt, small[3])):
+            buf.copy_(src)
+        out["single_batch_latency_graph_us"] = timeit(gs.replay, reps=200, warm=10) * 1e3
+        out["single_batch_note"] = ("one 1024 pos + 10 neg/pos batch, forward + margin loss + backward: module API call vs the same two "
+                                    "kernels replayed from a CUDA graph over static id buffers (TransEModel.graphed_loss_step)")
 
     # ---- full-catalog evaluation at configs[4] shapes, catalog row-sharded over the N GPUs ----------------------------
     if not args.no_eval:

@@ -1,6 +1,7 @@
 """TransE on the CUDA engine.  Mirrors jTransUP/models/transE.py (constructor 18-49,
 forward 51-63, evaluateHead/Tail 65-105) with every method one kernel call."""
 from .. import _lib
+from .. import functional as KF
 from .base import KGRecModule, _make_tables
 
 
@@ -53,6 +54,11 @@ class KGModelBase(KGRecModule):
         normLoss over the gathered entity / relation rows (and orthogonalLoss for TransH) -- values
         and gradients from the same kernel pass."""
         return self._loss_step_corrupt(self.MODEL, pos, corrupt, loss, margin, batch_pos, grad_loss, reg)
+
+    def graphed_loss_step(self, n_pos, n_neg, margin=1.0, loss="margin", batch_pos=None, grad_loss=1.0, reg=False):
+        """loss_step_corrupt for a fixed batch shape as a CUDA graph over static id buffers (the single-batch
+        latency path): fill `.h / .t / .r / .corrupt` of the returned object, call `.replay()`."""
+        return KF.GraphedCorruptStep(self, n_pos, n_neg, margin, loss, batch_pos, grad_loss, reg)
 
     # -- evaluation: [B, ent_total] matrices for the unchanged drivers ---------------------
     def _catalog(self):
