@@ -1333,3 +1333,79 @@ def test_graphed_loss_step_matches_module_call(cls_name, grad_mode):
         want = want.to_dense() if want.is_sparse else want
         close(got, want.cpu().numpy(), rtol=1e-5, atol=1e-6)
     m.check_indices()
+
+
+@pytest.mark.parametrize("name", ["transe_l2", "transe_l1", "transh_l2"])
+@pytest.mark.parametrize("path", ["step", "autograd"])
+def test_golden_config_shape_cfg2(golden, name, path):
+    """BASELINE configs[1] shape (d=100, |E|=100k, |R|=500, 1024 positives x 10 negatives) against vectors recorded
+    from the unmodified reference classes with the reference's own call pattern for K negatives per positive
+    (model(pos.repeat_interleave(10)), model(neg), marginLoss, backward): tests/golden/make_golden_cfg2.py.
+    The tables are rebuilt from the seed (same generator consumption as the reference constructors)."""
+    import kgrec_b200 as K
+    g = golden("cfg2_" + name)
+    l1 = name.endswith("l1")
+    torch.manual_seed(int(g["seed"]))
+    m = (K.TransHModel if name.startswith("transh") else K.TransEModel)(l1, 100, 100_000, 500)
+    np.testing.assert_array_equal(m.ent_embeddings.weight.detach()[:4].cpu().numpy(), g["ent_rows_check"])
+    np.testing.assert_array_equal(m.rel_embeddings.weight.detach()[-4:].cpu().numpy(), g["rel_rows_check"])
+    m.grad_mode = "dense"
+    pos = (lt(g["ph"]), lt(g["pt"]), lt(g["pr"]))
+    corrupt = torch.from_numpy(g["corrupt"]).cuda()
+    if path == "step":          # one kernel: forward + margin loss + backward
+        loss, ps, ns = m.loss_step_corrupt(pos, corrupt, margin=1.0)
+    else:                       # fused forward, autograd backward
+        loss, ps, ns = m.rank_loss_corrupt(pos, corrupt, margin=1.0)
+        loss.sum().backward()
+    close(ps, g["pos_scores"], rtol=1e-4)
+    close(ns, g["neg_scores"], rtol=1e-4)
+    close(loss.sum(), g["loss"], rtol=1e-4)
+    eg = m.ent_embeddings.weight.grad
+    close(eg[torch.from_numpy(g["ent_grad_ids"]).cuda()], g["ent_grad_rows"], rtol=1e-3, atol=2e-5, max_outliers=8 if l1 else 0)
+    close((eg.double() ** 2).sum(), g["ent_grad_sqnorm"], rtol=1e-3)
+    close(m.rel_embeddings.weight.grad, g["rel_grad"], rtol=1e-3, atol=5e-5, max_outliers=8 if l1 else 0)
+    if "norm_grad" in g:
+        close(m.norm_embeddings.weight.grad, g["norm_grad"], rtol=1e-3, atol=5e-5)
+    m.check_indices()
+
+
+@pytest.mark.parametrize("cls_name", ["TransEModel", "TransHModel"])
+@pytest.mark.parametrize("l1", [False, True])
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+def test_step_kernels_vs_oracle_k10_d100(cls_name, l1, mode):
+    """The step kernels (k_group_step_e / _h) at the benchmark's group shape (10 negatives per positive, d=100)
+    directly against the numpy oracle: scores, per-batch margin losses and the gradient of every table."""
+    import kgrec_b200 as K
+    torch.manual_seed(23)
+    rng = np.random.RandomState(23)
+    d, E, R, B, KN, bp = 100, 4000, 17, 700, 10, 256
+    m = getattr(K, cls_name)(l1, d, E, R)
+    m.grad_mode = mode
+    W = np_tables(m)
+    h, t, r = rng.randint(0, E, B), rng.randint(0, E, B), rng.randint(0, R, B)
+    cid = rng.randint(0, E, B * KN)
+    head = rng.rand(B * KN) < 0.5
+    nh = np.where(head, cid, np.repeat(h, KN))
+    nt = np.where(head, np.repeat(t, KN), cid)
+    nr = np.repeat(r, KN)
+    corrupt = torch.from_numpy(np.where(head, ~cid, cid).astype(np.int32)).cuda()
+    loss, ps, ns = m.loss_step_corrupt((lt(h), lt(t), lt(r)), corrupt, margin=1.0, batch_pos=bp)
+    if cls_name == "TransEModel":
+        score = lambda a, b, c: O.transe_score(W["ent"], W["rel"], a, b, c, l1)                       # noqa: E731
+        grads = lambda a, b, c, g: O.transe_grads(W["ent"], W["rel"], a, b, c, l1, g)                  # noqa: E731
+    else:
+        score = lambda a, b, c: O.transh_score(W["ent"], W["rel"], W["norm"], a, b, c, l1)            # noqa: E731
+        grads = lambda a, b, c, g: O.transh_grads(W["ent"], W["rel"], W["norm"], a, b, c, l1, g)       # noqa: E731
+    op, on = score(h, t, r), score(nh, nt, nr)
+    close(ps, op, rtol=1e-4)
+    close(ns, on, rtol=1e-4)
+    opr = np.repeat(op, KN)
+    nb = (B + bp - 1) // bp
+    close(loss, np.array([O.margin_loss(opr[b * bp * KN:(b + 1) * bp * KN], on[b * bp * KN:(b + 1) * bp * KN], 1.0) for b in range(nb)]), rtol=1e-4)
+    gp, gn = O.margin_loss_grads(opr, on, 1.0)
+    a = grads(np.repeat(h, KN), np.repeat(t, KN), nr, gp)
+    b = grads(nh, nt, nr, gn)
+    got = grads_by_name(m)
+    for k in a:
+        close(got[k + "_embeddings"], a[k] + b[k], rtol=2e-3, atol=2e-4, max_outliers=6 if l1 else 0)
+    m.check_indices()

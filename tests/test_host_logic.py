@@ -35,6 +35,9 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Tables) == 16 + 32 + 8 + 9 * 8
     assert C.sizeof(_lib.Grads) == 8 + 8 * 8
     assert _lib.Tables.ent.offset == 56 and _lib.Tables.item2ent.offset == 56 + 64
+    # kgrec_opt_table: 5 pointers, int64, 4 x int32; kgrec_mark_seg: pointer, int64, 2 x int32, pointer, int64, pointer, int64
+    assert C.sizeof(_lib.OptTable) == 5 * 8 + 8 + 4 * 4 and _lib.OptTable.rows.offset == 40 and _lib.OptTable.keep_acc.offset == 52
+    assert C.sizeof(_lib.MarkSeg) == 56 and _lib.MarkSeg.remap.offset == 24 and _lib.MarkSeg.marks.offset == 40
 
 
 def test_module_surface_matches_reference_protocol():
