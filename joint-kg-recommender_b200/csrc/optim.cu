@@ -63,7 +63,11 @@ struct SweepArgs {
   float max_norm;
 };
 
-// Visit every marked row of every table: f(table, row, chunk index of this lane, active).
+// A warp owns 32 consecutive rows of one table: one coalesced load of their marks, a ballot, and the marked rows are
+// handed out kRowsInFlight at a time -- f gets the batch so that it can issue the loads of all its rows before the
+// first use (the sweeps are latency-bound: a row is three dependent-free loads, a few flops, three stores).
+constexpr int kRowsInFlight = 4;
+
 template <typename F>
 __device__ __forceinline__ void sweep_rows(const SweepArgs& A, F&& f) {
   const int lane = threadIdx.x & 31;
@@ -80,25 +84,36 @@ __device__ __forceinline__ void sweep_rows(const SweepArgs& A, F&& f) {
     bool mine = row < T.rows;
     if (mine && T.marks) mine = __ldg(T.marks + row) == A.epoch;
     unsigned m = __ballot_sync(FULL, mine);
-    const int nch = (T.dim + 3) >> 2;                     // 16-byte chunks per row
     while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      const int64_t r = row0 + b;
-      for (int ch = lane; ch < nch; ch += 32) f(T, r, ch);
+      int64_t rows[kRowsInFlight];
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < kRowsInFlight; ++i) {
+        rows[i] = row0;
+        if (m) { rows[i] = row0 + (__ffs(m) - 1); m &= m - 1; n = i + 1; }
+      }
+      f(T, rows, n, lane);
     }
   }
 }
 
 __global__ void __launch_bounds__(256) k_rows_sqnorm(const SweepArgs A, float* out) {
   float local = 0.f;
-  sweep_rows(A, [&](const kgrec_opt_table& T, int64_t r, int ch) {
-    const float* g = T.acc + r * T.dim + ch * 4;
-    if (T.vec) {
-      const float4 v = *reinterpret_cast<const float4*>(g);
-      local = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, local))));
-    } else {
-      for (int e = 0; e < 4 && ch * 4 + e < T.dim; ++e) local = fmaf(g[e], g[e], local);
+  sweep_rows(A, [&](const kgrec_opt_table& T, const int64_t (&rows)[kRowsInFlight], int n, int lane) {
+    const int nch = (T.dim + 3) >> 2;
+    for (int ch = lane; ch < nch; ch += 32) {
+      if (T.vec) {
+        float4 v[kRowsInFlight];
+#pragma unroll
+        for (int i = 0; i < kRowsInFlight; ++i)
+          v[i] = i < n ? *reinterpret_cast<const float4*>(T.acc + rows[i] * T.dim + ch * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < kRowsInFlight; ++i)
+          local = fmaf(v[i].x, v[i].x, fmaf(v[i].y, v[i].y, fmaf(v[i].z, v[i].z, fmaf(v[i].w, v[i].w, local))));
+      } else {
+        for (int i = 0; i < n; ++i)
+          for (int e = 0; e < 4 && ch * 4 + e < T.dim; ++e) { const float g = T.acc[rows[i] * T.dim + ch * 4 + e]; local = fmaf(g, g, local); }
+      }
     }
   });
   local = warp_sum(local);
@@ -131,30 +146,47 @@ __device__ __forceinline__ float opt_elem(const SweepArgs& A, float pv, float gv
 __global__ void __launch_bounds__(256) k_rows_update(const SweepArgs A) {
   float scale = 1.f;
   if (A.sqnorm) scale = fminf(1.f, A.max_norm / (sqrtf(__ldg(A.sqnorm)) + 1e-6f));   // clip_grad_norm's coefficient
-  sweep_rows(A, [&](const kgrec_opt_table& T, int64_t r, int ch) {
-    const int64_t o = r * T.dim + ch * 4;
-    if (T.vec) {
-      float4 g = *reinterpret_cast<float4*>(T.acc + o);
-      if (!T.keep_acc) *reinterpret_cast<float4*>(T.acc + o) = make_float4(0.f, 0.f, 0.f, 0.f);   // zero again after the step
-      float4 p = *reinterpret_cast<float4*>(T.table + o);
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-      if (A.kind != OPT_SGD) a = *reinterpret_cast<float4*>(T.state1 + o);
-      if (A.kind == OPT_ADAM) b = *reinterpret_cast<float4*>(T.state2 + o);
-      p.x = opt_elem(A, p.x, g.x * scale, &a.x, &b.x);
-      p.y = opt_elem(A, p.y, g.y * scale, &a.y, &b.y);
-      p.z = opt_elem(A, p.z, g.z * scale, &a.z, &b.z);
-      p.w = opt_elem(A, p.w, g.w * scale, &a.w, &b.w);
-      *reinterpret_cast<float4*>(T.table + o) = p;
-      if (A.kind != OPT_SGD) *reinterpret_cast<float4*>(T.state1 + o) = a;
-      if (A.kind == OPT_ADAM) *reinterpret_cast<float4*>(T.state2 + o) = b;
-    } else {
-      for (int e = 0; e < 4 && ch * 4 + e < T.dim; ++e) {
-        const float g = T.acc[o + e];
-        if (!T.keep_acc) T.acc[o + e] = 0.f;
-        float a = A.kind != OPT_SGD ? T.state1[o + e] : 0.f, b = A.kind == OPT_ADAM ? T.state2[o + e] : 0.f;
-        T.table[o + e] = opt_elem(A, T.table[o + e], g * scale, &a, &b);
-        if (A.kind != OPT_SGD) T.state1[o + e] = a;
-        if (A.kind == OPT_ADAM) T.state2[o + e] = b;
+  sweep_rows(A, [&](const kgrec_opt_table& T, const int64_t (&rows)[kRowsInFlight], int n, int lane) {
+    const int nch = (T.dim + 3) >> 2;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ch = lane; ch < nch; ch += 32) {
+      if (T.vec) {
+        float4 g[kRowsInFlight], p[kRowsInFlight], a[kRowsInFlight], b[kRowsInFlight];
+#pragma unroll
+        for (int i = 0; i < kRowsInFlight; ++i) {            // every load of the batch leaves before the first use
+          const int64_t o = rows[i] * T.dim + ch * 4;
+          g[i] = p[i] = a[i] = b[i] = z4;
+          if (i < n) {
+            g[i] = *reinterpret_cast<const float4*>(T.acc + o);
+            p[i] = *reinterpret_cast<const float4*>(T.table + o);
+            if (A.kind != OPT_SGD) a[i] = *reinterpret_cast<const float4*>(T.state1 + o);
+            if (A.kind == OPT_ADAM) b[i] = *reinterpret_cast<const float4*>(T.state2 + o);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kRowsInFlight; ++i) {
+          if (i >= n) continue;
+          const int64_t o = rows[i] * T.dim + ch * 4;
+          p[i].x = opt_elem(A, p[i].x, g[i].x * scale, &a[i].x, &b[i].x);
+          p[i].y = opt_elem(A, p[i].y, g[i].y * scale, &a[i].y, &b[i].y);
+          p[i].z = opt_elem(A, p[i].z, g[i].z * scale, &a[i].z, &b[i].z);
+          p[i].w = opt_elem(A, p[i].w, g[i].w * scale, &a[i].w, &b[i].w);
+          if (!T.keep_acc) *reinterpret_cast<float4*>(T.acc + o) = z4;                   // zero again after the step
+          *reinterpret_cast<float4*>(T.table + o) = p[i];
+          if (A.kind != OPT_SGD) *reinterpret_cast<float4*>(T.state1 + o) = a[i];
+          if (A.kind == OPT_ADAM) *reinterpret_cast<float4*>(T.state2 + o) = b[i];
+        }
+      } else {
+        for (int i = 0; i < n; ++i)
+          for (int e = 0; e < 4 && ch * 4 + e < T.dim; ++e) {
+            const int64_t o = rows[i] * T.dim + ch * 4 + e;
+            const float g = T.acc[o];
+            if (!T.keep_acc) T.acc[o] = 0.f;
+            float a = A.kind != OPT_SGD ? T.state1[o] : 0.f, b = A.kind == OPT_ADAM ? T.state2[o] : 0.f;
+            T.table[o] = opt_elem(A, T.table[o], g * scale, &a, &b);
+            if (A.kind != OPT_SGD) T.state1[o] = a;
+            if (A.kind == OPT_ADAM) T.state2[o] = b;
+          }
       }
     }
   });
