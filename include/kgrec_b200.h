@@ -421,6 +421,22 @@ int kgrec_pref_aug_rows(const kgrec_tables* tables, int model, int is_query,
                         const void* ids, int idx_bytes, const float* rows, int64_t row_ld, int64_t n,
                         float* out, int64_t ld_out, kgrec_stream_t stream);
 
+/* ST-Gumbel rec-side evaluation (use_st_gumbel = 1, squared-L2 score) on augmented rows.  The pair's preference is
+ * k* = arg-max_k (u + i).P'_k / 2 + g_k with fresh Gumbel noise per (pair, k) (transUP.py:84-102, 143-170); with
+ * r = hf P'_k*, w = hf N'_k*, a = u - i, s = a.w the score |a + r - s w|^2 equals
+ * |a|^2 + |r|^2 + 2 a.r + s^2 (|w|^2 - 2) - 2 s r.w, so each table row is augmented ONCE into
+ * [x | A_k = x.P'_k / 2 | C_k = x.(hf N'_k) | pad] (leading dimension kgrec_gumbel_aug_ld(d, P)) and a pair costs the
+ * distance |u - i|^2 plus a P-step arg-max: no per-pair [P x d] contraction.  Build the catalog rows (ids = NULL, rows
+ * = the item table or the kgrec_ktup_item_table output) and the query rows (ids gathers user rows; gconst = the [3 P]
+ * constants, which MUST be stored right behind the query rows: qvec + nq * ld), then call kgrec_eval_scores /
+ * kgrec_eval_topk with side = KGREC_SIDE_REC, qvec = the query rows, cat = the augmented catalog. */
+int32_t kgrec_gumbel_aug_ld(int32_t dim, int32_t n_pref);
+/* 1 when the augmented ST-Gumbel kernel fits this (embedding_size, preference_total, top-k [0 = score matrix]) */
+int32_t kgrec_gumbel_aug_supported(int32_t dim, int32_t n_pref, int32_t k);
+int kgrec_gumbel_aug_rows(const kgrec_tables* tables, int model, const void* ids, int idx_bytes, const float* rows,
+                          int64_t row_ld, int64_t n, float* out, int64_t ld_out, float* gconst,
+                          kgrec_stream_t stream);
+
 /* KTUP rec-side catalog: out[i] = Item[item_begin + i] + Ent[item2ent[item_begin + i]]
  * (jTransUP.py:177-181), n_items rows with leading dimension ld_out. */
 int kgrec_ktup_item_table(const kgrec_tables* tables, int64_t item_begin, int64_t n_items,

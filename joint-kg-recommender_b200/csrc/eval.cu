@@ -24,7 +24,7 @@
 
 namespace kgrec {
 
-enum { KIND_DIST = 0, KIND_HYPER = 1, KIND_PREF_HARD = 2, KIND_PREF_SOFT = 3 };
+enum { KIND_DIST = 0, KIND_HYPER = 1, KIND_PREF_HARD = 2, KIND_PREF_SOFT = 3, KIND_GUMBEL_L2 = 4 };
 enum { MODE_FULL = 0, MODE_TOPK = 1, MODE_RANK = 2 };
 
 constexpr int QW = 8;                       // queries per warp
@@ -98,6 +98,8 @@ struct EvalArgs {
   int tn;                   // catalog rows per tile
   const float* gumbel_u;    // explicit [nq, n_cat, P] (PREF_HARD parity mode)
   uint64_t seed;
+  int64_t qvec_ld;          // row stride of qvec (KG kinds: 2 dim; KIND_GUMBEL_L2: the augmented row length)
+  const float* gconst;      // KIND_GUMBEL_L2: [3 P] |R_k|^2, |W_k|^2, R_k . W_k of the mixing tables
   // outputs
   float* out; int64_t ld_out;               // FULL
   uint64_t* part_keys; int k;               // TOPK: [n_splits][nq][k]
@@ -564,7 +566,9 @@ struct TiledSmem {
 // warp broadcasts at immediate offsets.  (Round 1 walked such rows in a lane-skewed order instead; with the chunk-major
 // query tile that turned every query load into an 8-way bank conflict: 0.23 of the FP32 bound at d = 128.)
 __host__ __device__ inline int tile_pitch(int d) { return ((d >> 2) & 1) ? d : d + 4; }
-__host__ __device__ inline TiledSmem tiled_smem_layout(int kind, int mode, int d, int tn, int stages, int k, int warps) {
+// ST-Gumbel rec rows: [x (d) | A_k = x . P'_k / 2 (P) | C_k = x . W_k (P) | pad to a multiple of 4]
+__host__ __device__ inline int gumbel_aug_ld(int d, int P) { return (d + 2 * P + 3) & ~3; }
+__host__ __device__ inline TiledSmem tiled_smem_layout(int kind, int mode, int d, int tn, int stages, int k, int warps, int P = 0) {
   TiledSmem s{};
   const int TQT = RQ * warps;
   size_t off = 0;
@@ -572,9 +576,13 @@ __host__ __device__ inline TiledSmem tiled_smem_layout(int kind, int mode, int d
   off = (off + 127) & ~static_cast<size_t>(127);
   s.q = off; off += static_cast<size_t>(TQT) * d * sizeof(float);
   if (kind == KIND_HYPER) { s.w = off; off += static_cast<size_t>(TQT) * d * sizeof(float); }
+  if (kind == KIND_GUMBEL_L2) {           // per-query logit halves / normal dots [TQT][2 P], then the [3 P] table constants
+    s.w = off; off += (static_cast<size_t>(TQT) * 2 * P + 3 * P) * sizeof(float);
+    off = (off + 15) & ~static_cast<size_t>(15);
+  }
   if (mode == MODE_RANK) { s.gold = off; off += static_cast<size_t>(TQT) * 2 * sizeof(uint32_t); }
   off = (off + 127) & ~static_cast<size_t>(127);
-  s.tiles = off; off += static_cast<size_t>(stages) * tn * tile_pitch(d) * sizeof(float);
+  s.tiles = off; off += static_cast<size_t>(stages) * tn * tile_pitch(kind == KIND_GUMBEL_L2 ? gumbel_aug_ld(d, P) : d) * sizeof(float);
   if (mode == MODE_TOPK) { s.lists = off; off += static_cast<size_t>(TQT) * k * sizeof(uint64_t); }
   s.total = off;
   return s;
@@ -590,15 +598,16 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
   const kgrec_tables& T = A.T;
   const int d = T.dim;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const TiledSmem L = tiled_smem_layout(KIND, MODE, d, TN, stages, A.k, W);
+  const TiledSmem L = tiled_smem_layout(KIND, MODE, d, TN, stages, A.k, W, T.n_pref);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
   uint64_t* empty = full + 8;
   float* sQ = reinterpret_cast<float*>(smem_raw + L.q);
   [[maybe_unused]] float* sW = reinterpret_cast<float*>(smem_raw + L.w);
   [[maybe_unused]] uint32_t* sGold = reinterpret_cast<uint32_t*>(smem_raw + L.gold);
   float* tiles = reinterpret_cast<float*>(smem_raw + L.tiles);
-  const int pitch = tile_pitch(d);
-  const bool dense = A.cat_ld == d && pitch == d;   // strided catalogs / padded tiles need one copy per row
+  const int rf = (KIND == KIND_GUMBEL_L2) ? gumbel_aug_ld(d, T.n_pref) : d;   // floats of a catalog row that travel
+  const int pitch = tile_pitch(rf);
+  const bool dense = A.cat_ld == rf && pitch == rf;   // strided catalogs / padded tiles need one copy per row
 
   const int64_t n_tiles = (A.n_cat + TN - 1) / TN;
   const int64_t n_qtiles = (A.nq + TQT - 1) / TQT;
@@ -611,6 +620,8 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     for (int s = 0; s < stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kTiledWarps); }
     mbar_fence_init();
   }
+  if constexpr (KIND == KIND_GUMBEL_L2)
+    for (int i = threadIdx.x; i < 3 * T.n_pref; i += blockDim.x) sW[TQT * 2 * T.n_pref + i] = __ldg(A.gconst + i);
   __syncthreads();
   if (my_units <= 0) return;
 
@@ -622,14 +633,14 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     float* dst = tiles + static_cast<size_t>(s) * TN * pitch;
     if (lane == 0) {
       if (g >= stages) mbar_wait(empty + s, static_cast<uint32_t>(((g / stages) - 1) & 1));
-      mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(rows) * d * sizeof(float));
+      mbar_arrive_expect_tx(full + s, static_cast<uint32_t>(rows) * rf * sizeof(float));
     }
     __syncwarp();
     if (dense) {
-      if (lane == 0) bulk_g2s(dst, A.cat + row0 * A.cat_ld, static_cast<uint32_t>(rows) * d * sizeof(float), full + s);
+      if (lane == 0) bulk_g2s(dst, A.cat + row0 * A.cat_ld, static_cast<uint32_t>(rows) * rf * sizeof(float), full + s);
     } else {
       for (int r = lane; r < rows; r += 32)
-        bulk_g2s(dst + r * pitch, A.cat + (row0 + r) * A.cat_ld, d * sizeof(float), full + s);
+        bulk_g2s(dst + r * pitch, A.cat + (row0 + r) * A.cat_ld, rf * sizeof(float), full + s);
     }
   };
   const int prefetch = stages - 1;
@@ -664,8 +675,12 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       for (int e = 0; e < 8; ++e) { cv[e] = 0.f; wv[e] = 0.f; }
       if (q < A.nq) {
         if (A.qvec) {
-          R::load(cv, A.qvec + q * 2 * d, d, lane);
-          if (KIND == KIND_HYPER) R::load(wv, A.qvec + q * 2 * d + d, d, lane);
+          R::load(cv, A.qvec + q * A.qvec_ld, d, lane);
+          if (KIND == KIND_HYPER) R::load(wv, A.qvec + q * A.qvec_ld + d, d, lane);
+          if constexpr (KIND == KIND_GUMBEL_L2) {       // the query's logit halves and normal dots
+            const int P2 = 2 * T.n_pref;
+            for (int i = lane; i < P2; i += 32) sW[(wid * RQ + qi) * P2 + i] = __ldg(A.qvec + q * A.qvec_ld + d + i);
+          }
         } else {
           const int64_t ie = load_idx(A.q, q, A.is64), ir = load_idx(A.r, q, A.is64);
           float rv[8];
@@ -844,6 +859,46 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     for (int qi = 0; qi < RQ; ++qi)
 #pragma unroll
       for (int j = 0; j < RN; ++j) acc[qi][j] = sum2(acc2[qi][j]);
+    if constexpr (KIND == KIND_GUMBEL_L2) {
+      // ST-Gumbel preference of every (query, row) pair (transUP.py:143-170 in evaluate, 84-102): k* = arg-max of
+      // (u + i) . P'_k / 2 + g_k with fresh noise per (pair, k); then r = hf P'_k*, w = hf N'_k* and, for the squared L2
+      // distance,  |a + r - s w|^2 = |a|^2 + |r|^2 + 2 a.r + s^2 (|w|^2 - 2) - 2 s r.w   with a = u - i, s = a.w:
+      // |a|^2 is the accumulator, every other term comes from the rows' logit halves A = x.P'/2 and normal dots
+      // C = x.w (k_gumbel_aug) and three per-preference constants.  No per-pair [P x d] work, no table gather.
+      const int P = T.n_pref;
+      const float* gc = sW + TQT * 2 * P;
+      const float hf4 = A.ktup ? 2.f : 4.f;
+#pragma unroll
+      for (int j = 0; j < RN; ++j) {
+        const int r = lane + 32 * j;
+        const float* ia = tile + r * pitch + d;
+        const int64_t n_local = row0 + r;
+#pragma unroll 1
+        for (int qi = 0; qi < RQ; ++qi) {
+          const int64_t q = q0 + qi;
+          if (q >= A.nq) continue;
+          const float* ua = sW + (wid * RQ + qi) * 2 * P;
+          float best = -INFINITY;
+          int ks = 0;
+          uint32_t x = hash_bits(A.seed, static_cast<uint32_t>(q), static_cast<uint32_t>(A.id_base + n_local), 0u);
+          for (int k = 0; k < P; ++k) {
+            float nz;
+            if (A.gumbel_u) {
+              nz = gumbel_from_uniform(r < rows ? __ldg(A.gumbel_u + (q * A.n_cat + n_local) * P + k) : 0.5f);
+            } else {                                  // one hash per pair, then a PCG step per preference
+              x = x * 747796405u + 2891336453u;
+              uint32_t b = ((x >> ((x >> 28) + 4u)) ^ x) * 277803737u;
+              b ^= b >> 22;
+              nz = gumbel_fast(b);
+            }
+            const float v = ua[k] + ia[k] + nz;
+            if (v > best) { best = v; ks = k; }
+          }
+          const float sd = ua[P + ks] - ia[P + ks];
+          acc[qi][j] += gc[ks] + hf4 * (ua[ks] - ia[ks]) + sd * sd * (gc[P + ks] - 2.f) - 2.f * sd * gc[2 * P + ks];
+        }
+      }
+    }
     // the tile is consumed: release the stage before the (register-only) epilogue
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + s);
@@ -1174,6 +1229,61 @@ k_ktup_items(const kgrec_tables T, int64_t i0, int64_t n, float* __restrict__ ou
 // ===========================================================================================
 // host side
 // ===========================================================================================
+// ST-Gumbel rec rows (KIND_GUMBEL_L2): out[row] = [x | A_k = x . P'_k / 2 | C_k = x . (hf N'_k) | 0 pad], one warp per row;
+// P' = pref (+ rel for KTUP), N' = pref_norm (+ norm), hf = 1 (TUP) or 1/2 (KTUP): transUP.py:105-115, jTransUP.py:250-260.
+// Block 0 also writes the three per-preference constants |hf P'_k|^2, |hf N'_k|^2, (hf P'_k).(hf N'_k) to gconst [3 P].
+__global__ void __launch_bounds__(kThreads)
+k_gumbel_aug(const kgrec_tables T, const int ktup, const void* ids, const int is64, const float* __restrict__ rows,
+             const int64_t row_ld, const int64_t n, float* __restrict__ out, const int64_t lda, float* __restrict__ gconst) {
+  extern __shared__ __align__(16) float aug_smem[];
+  const int d = T.dim, P = T.n_pref, stride = (d + 3) & ~3;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* sP = aug_smem;
+  float* sN = sP + P * stride;
+  const float hf = ktup ? 0.5f : 1.f;
+  for (int idx = threadIdx.x; idx < P * stride; idx += blockDim.x) {
+    const int k = idx / stride, j = idx - k * stride;
+    float a = 0.f, b = 0.f;
+    if (j < d) {
+      a = __ldg(T.pref + static_cast<int64_t>(k) * T.ld + j);
+      b = __ldg(T.pref_norm + static_cast<int64_t>(k) * T.ld + j);
+      if (ktup) { a += __ldg(T.rel + static_cast<int64_t>(k) * T.ld + j); b += __ldg(T.norm + static_cast<int64_t>(k) * T.ld + j); }
+    }
+    sP[idx] = a;
+    sN[idx] = b;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && gconst) {
+    for (int k = wid; k < P; k += kWarpsPerCta) {
+      float pp = 0.f, nn = 0.f, pn = 0.f;
+      for (int j = lane; j < d; j += 32) {
+        const float a = hf * sP[k * stride + j], b = hf * sN[k * stride + j];
+        pp = fmaf(a, a, pp); nn = fmaf(b, b, nn); pn = fmaf(a, b, pn);
+      }
+      warp_sum2(pp, nn);
+      pn = warp_sum(pn);
+      if (lane == 0) { gconst[k] = pp; gconst[P + k] = nn; gconst[2 * P + k] = pn; }
+    }
+  }
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + wid; row < n; row += static_cast<int64_t>(gridDim.x) * kWarpsPerCta) {
+    const int64_t src = ids ? load_idx(ids, row, is64) : row;
+    const float* x = rows + src * row_ld;
+    float* o = out + row * lda;
+    for (int j = lane; j < d; j += 32) o[j] = __ldg(x + j);
+    for (int k = 0; k < P; ++k) {
+      float a = 0.f, c = 0.f;
+      for (int j = lane; j < d; j += 32) {
+        const float xv = __ldg(x + j);
+        a = fmaf(xv, sP[k * stride + j], a);
+        c = fmaf(xv, sN[k * stride + j], c);
+      }
+      warp_sum2(a, c);
+      if (lane == 0) { o[d + k] = 0.5f * a; o[d + P + k] = hf * c; }
+    }
+    for (int j = d + 2 * P + lane; j < lda; j += 32) o[j] = 0.f;
+  }
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 struct EvalPlan {
@@ -1211,6 +1321,37 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
   const bool rec = side == KGREC_SIDE_REC;
   if (rec != (pl->kind >= KIND_PREF_HARD)) { set_error("side %d does not fit model %d", side, model); return KGREC_ERR_INVALID; }
   pl->soft_aug = false;
+  if (rec && have_qvec && pl->kind == KIND_PREF_HARD) {
+    // ST-Gumbel on rows augmented by kgrec_gumbel_aug_rows: the register-tiled distance kernel + a per-pair epilogue
+    if (T->l1) { set_error("augmented ST-Gumbel rows are built for the squared-L2 score (L1_flag = 0)"); return KGREC_ERR_UNSUPPORTED; }
+    if (T->n_pref <= 0 || T->n_pref > 64) { set_error("augmented ST-Gumbel rows: preference_total must be <= 64"); return KGREC_ERR_UNSUPPORTED; }
+    if (cat_ld != gumbel_aug_ld(d, T->n_pref)) { set_error("augmented ST-Gumbel catalog must have leading dimension %d", gumbel_aug_ld(d, T->n_pref)); return KGREC_ERR_INVALID; }
+    if (mode == MODE_RANK) { set_error("rank counts are built for the KG sides"); return KGREC_ERR_UNSUPPORTED; }
+    if (mode == MODE_TOPK && (k <= 0 || k > 128)) { set_error("topn %d outside [1, 128]", k); return KGREC_ERR_UNSUPPORTED; }
+    pl->kind = KIND_GUMBEL_L2;
+    pl->tiled = true;
+    const bool wide = d > 128;
+    pl->warps = wide ? 8 : 16;
+    pl->rn = wide ? 1 : 2;
+    const int tn_t = 32 * pl->rn;
+    int stages = 4;
+    while (stages > 2 && tiled_smem_layout(pl->kind, mode, d, tn_t, stages, k, pl->warps, T->n_pref).total > 210 * 1024) --stages;
+    pl->stages = stages;
+    pl->tn = tn_t;
+    pl->smem = tiled_smem_layout(pl->kind, mode, d, tn_t, stages, k, pl->warps, T->n_pref).total;
+    if (pl->smem > 225 * 1024) { set_error("eval: shared-memory budget exceeded (%zu bytes)", pl->smem); return KGREC_ERR_UNSUPPORTED; }
+    const int64_t n_tiles_t = (n_cat + tn_t - 1) / tn_t;
+    pl->n_qtiles = (nq + RQ * pl->warps - 1) / (RQ * pl->warps);
+    const int64_t total_units = n_tiles_t * pl->n_qtiles;
+    int64_t ctas = sm_count();
+    if (ctas > total_units) ctas = total_units;
+    pl->units_per_cta = (total_units + ctas - 1) / ctas;
+    pl->grid = static_cast<int>((total_units + pl->units_per_cta - 1) / pl->units_per_cta);
+    pl->n_splits = static_cast<int>((n_tiles_t + pl->units_per_cta - 1) / pl->units_per_cta + 1);
+    A->T = *T; A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
+    A->n_splits = pl->n_splits; A->tn = tn_t; A->k = k;
+    return KGREC_OK;
+  }
   if (rec && have_qvec) {
     // augmented-row evaluation of the soft preference model (rows built by kgrec_pref_aug_rows)
     if (pl->kind != KIND_PREF_SOFT) { set_error("augmented rec rows are for use_st_gumbel = 0"); return KGREC_ERR_INVALID; }
@@ -1325,6 +1466,10 @@ static int launch_eval(const EvalArgs& A, const EvalPlan& pl, cudaStream_t st) {
     kern<<<pl.grid, WV * 32, pl.smem, st>>>(A, pl.stages, pl.units_per_cta);                                  \
   }
     if (pl.kind == KIND_DIST) { if (pl.warps == 16) KGREC_TILED_CASE(KIND_DIST, 4, 16) else KGREC_TILED_CASE(KIND_DIST, 2, 8) }
+    else if (pl.kind == KIND_GUMBEL_L2) {
+      if constexpr (MODE == MODE_RANK) { set_error("rank counts are built for the KG sides"); return KGREC_ERR_UNSUPPORTED; }
+      else { if (pl.warps == 16) KGREC_TILED_CASE(KIND_GUMBEL_L2, 2, 16) else KGREC_TILED_CASE(KIND_GUMBEL_L2, 1, 8) }
+    }
     else { if (pl.warps == 16) KGREC_TILED_CASE(KIND_HYPER, 2, 16) else KGREC_TILED_CASE(KIND_HYPER, 1, 8) }
 #undef KGREC_TILED_CASE
     KGREC_CUDA_OK(cudaGetLastError());
@@ -1368,6 +1513,8 @@ extern "C" int kgrec_eval_scores(const kgrec_tables* tables, int model, int side
   if (!out || ld_out < n_cat) { set_error("bad out / ld_out"); return KGREC_ERR_INVALID; }
   if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
   A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
+  A.qvec_ld = pl.kind == KIND_GUMBEL_L2 ? cat_ld : 2 * static_cast<int64_t>(tables->dim);
+  A.gconst = pl.kind == KIND_GUMBEL_L2 ? qvec + nq * cat_ld : nullptr;     // the constants follow the query rows
   A.gumbel_u = gumbel_u; A.seed = seed; A.id_base = id_base; A.cat_ids = cat_ids;
   if (cat_ids && !pl.tiled) { set_error("eval_scores: cat_ids is for the KG sides only"); return KGREC_ERR_INVALID; }
   A.out = out; A.ld_out = ld_out;
@@ -1389,6 +1536,8 @@ extern "C" int kgrec_eval_topk(const kgrec_tables* tables, int model, int side, 
   const int64_t need = static_cast<int64_t>(pl.n_splits) * nq * k * static_cast<int64_t>(sizeof(uint64_t));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
+  A.qvec_ld = pl.kind == KIND_GUMBEL_L2 ? cat_ld : 2 * static_cast<int64_t>(tables->dim);
+  A.gconst = pl.kind == KIND_GUMBEL_L2 ? qvec + nq * cat_ld : nullptr;
   A.gumbel_u = gumbel_u; A.seed = seed; A.id_base = id_base;
   A.filter_ptr = filter_ptr; A.filter_ids = filter_ids;
   if (pl.n_splits == 1 && !pl.tiled && !pl.soft_aug) {
@@ -1426,6 +1575,7 @@ extern "C" int kgrec_eval_rank_count(const kgrec_tables* tables, int model, int 
   if (!gold_scores || !gold_ids || !counts) { set_error("rank_count: NULL argument"); return KGREC_ERR_INVALID; }
   if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
   A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
+  A.qvec_ld = 2 * static_cast<int64_t>(tables->dim);
   A.id_base = id_base; A.seed = 0;
   A.gold_scores = gold_scores; A.gold_ids = gold_ids; A.counts = counts;
   return launch_eval<MODE_RANK>(A, pl, static_cast<cudaStream_t>(stream));
@@ -1441,6 +1591,37 @@ extern "C" int kgrec_ktup_item_table(const kgrec_tables* tables, int64_t item_be
   const int64_t total = n_items * tables->dim;
   const int grid = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
   k_ktup_items<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*tables, item_begin, n_items, out, ld_out);
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}
+
+extern "C" int32_t kgrec_gumbel_aug_ld(int32_t dim, int32_t n_pref) { return gumbel_aug_ld(dim, n_pref); }
+
+extern "C" int32_t kgrec_gumbel_aug_supported(int32_t dim, int32_t n_pref, int32_t k) {
+  if (dim <= 0 || dim > 256 || dim % 4 || n_pref <= 0 || n_pref > 64 || k < 0 || k > 128) return 0;
+  const bool wide = dim > 128;
+  return tiled_smem_layout(KIND_GUMBEL_L2, k > 0 ? MODE_TOPK : MODE_FULL, dim, wide ? 32 : 64, 2, k, wide ? 8 : 16, n_pref).total <= 225 * 1024;
+}
+
+extern "C" int kgrec_gumbel_aug_rows(const kgrec_tables* tables, int model, const void* ids, int idx_bytes, const float* rows,
+                                     int64_t row_ld, int64_t n, float* out, int64_t ld_out, float* gconst, kgrec_stream_t stream) {
+  if (!tables || !rows || !out || n < 0 || (model != KGREC_TUP && model != KGREC_KTUP)) { set_error("gumbel_aug_rows: bad arguments"); return KGREC_ERR_INVALID; }
+  const int d = tables->dim, P = tables->n_pref;
+  const bool ktup = model == KGREC_KTUP;
+  if (d <= 0 || d > 256 || d % 4 || P <= 0 || P > 64 || ld_out != gumbel_aug_ld(d, P)) {
+    set_error("gumbel_aug_rows: embedding_size must be a multiple of 4 (<= 256), preference_total <= 64, ld_out = %d", gumbel_aug_ld(d > 0 ? d : 4, P > 0 ? P : 1));
+    return KGREC_ERR_UNSUPPORTED;
+  }
+  if (!tables->pref || !tables->pref_norm || (ktup && (!tables->rel || !tables->norm))) { set_error("gumbel_aug_rows: preference tables missing"); return KGREC_ERR_INVALID; }
+  if (ids && idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 4 or 8"); return KGREC_ERR_INVALID; }
+  if (n == 0 && !gconst) return KGREC_OK;
+  const size_t smem = static_cast<size_t>(2) * P * ((d + 3) & ~3) * sizeof(float);
+  KGREC_CUDA_OK(cudaFuncSetAttribute(k_gumbel_aug, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int64_t ctas = (n + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 4;
+  ctas = ctas < 1 ? 1 : (ctas < cap ? ctas : cap);
+  k_gumbel_aug<<<static_cast<int>(ctas), kThreads, smem, static_cast<cudaStream_t>(stream)>>>(*tables, ktup ? 1 : 0, ids, idx_bytes == 8, rows,
+                                                                                         row_ld, n, out, ld_out, gconst);
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;
 }

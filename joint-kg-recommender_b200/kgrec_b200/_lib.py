@@ -122,6 +122,10 @@ _SIGNATURES = {
     "kgrec_transr_eval_rank_count": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int64,
                                                C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kgrec_gumbel_aug_ld": (C.c_int32, [C.c_int32, C.c_int32]),
+    "kgrec_gumbel_aug_supported": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "kgrec_gumbel_aug_rows": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64,
+                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "kgrec_pref_aug_ld": (C.c_int32, [C.c_int32]),
     "kgrec_pref_aug_rows": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
                                       C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),

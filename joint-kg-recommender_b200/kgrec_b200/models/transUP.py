@@ -41,8 +41,48 @@ class RecModelBase(KGRecModule):
         cat = self._rec_catalog() if catalog is None else catalog
         return self._aug_rows(cat.contiguous(), False)
 
+    def _gumbel_rows(self, rows, ids=None, with_consts=False):
+        """Augmented rows of the ST-Gumbel (squared-L2) evaluation: [x | x.P'_k / 2 | x.(hf N'_k) | pad]
+        (kgrec_gumbel_aug_rows); with_consts: the [3 P] table constants are stored right behind the rows,
+        where the evaluation kernels expect them for the QUERY rows."""
+        import ctypes as C
+        dev = self._require_cuda()
+        lib = _lib.load()
+        T = KF.make_tables(self._weights(), self.embedding_size, self.L1_flag, self.use_st_gumbel, self._item2ent)
+        n = ids.numel() if ids is not None else rows.shape[0]
+        P = self.pref_embeddings.weight.shape[0]
+        ld = int(lib.kgrec_gumbel_aug_ld(self.embedding_size, P))
+        buf = torch.empty(n * ld + (3 * P if with_consts else 0), dtype=torch.float32, device=dev)
+        out = buf[:n * ld].view(n, ld)
+        gconst = C.c_void_p(buf.data_ptr() + n * ld * 4) if with_consts else None
+        _lib.check(lib.kgrec_gumbel_aug_rows(C.byref(T), self.MODEL, KF._ptr(ids), ids.element_size() if ids is not None else 8,
+                                             KF._ptr(rows), rows.stride(0), n, KF._ptr(out), ld, gconst, KF._stream()))
+        KF.count_launches(1)
+        return out
+
+    def gumbel_catalog(self, catalog=None):
+        """Augmented item catalog for repeated ST-Gumbel evaluation calls (rebuild when the item or preference
+        tables change)."""
+        cat = self._rec_catalog() if catalog is None else catalog
+        return self._gumbel_rows(cat.contiguous())
+
+    def _gumbel_aug_ok(self, k=0):
+        if not self.use_st_gumbel or self.L1_flag:
+            return False
+        return bool(_lib.load().kgrec_gumbel_aug_supported(self.embedding_size, self.pref_embeddings.weight.shape[0], k))
+
     def _rec_call(self, mode, u_ids, gumbel_u, catalog, soft_catalog, **kw):
         dev = self._require_cuda()
+        if self._gumbel_aug_ok(kw.get("k", 10) if mode == "topk" else 0):
+            # ST-Gumbel, squared L2: the tiled distance kernel on augmented rows + a per-pair arg-max epilogue
+            u = KF.as_index(u_ids, dev)
+            if u.numel() == 0:
+                return self._eval(self.MODEL, _lib.SIDE_REC, u, None, mode, catalog=self._rec_catalog(), **kw)
+            aug_cat = soft_catalog if soft_catalog is not None else self.gumbel_catalog(catalog)
+            qrows = self._gumbel_rows(self.user_embeddings.weight.detach(), ids=u, with_consts=True)
+            seed = self._next_seed() if gumbel_u is None else 0
+            return self._eval(self.MODEL, _lib.SIDE_REC, None, None, mode, catalog=aug_cat, qvec=qrows, gumbel_u=gumbel_u,
+                              seed=seed, **kw)
         use_aug = (not self.use_st_gumbel) and self.embedding_size % 4 == 0 and self.embedding_size <= 256
         if use_aug:
             u = KF.as_index(u_ids, dev)
@@ -61,7 +101,8 @@ class RecModelBase(KGRecModule):
     def topk_items(self, u_ids, k=10, filter_csr=None, catalog=None, id_base=0, gumbel_u=None, soft_catalog=None):
         """K best items per user as uint64 keys (int64 storage): score bits << 32 | item id.
         catalog: a row shard of the item table (KTUP: of _rec_catalog()); soft_catalog: its
-        augmented form from soft_catalog(), reusable across calls while the tables are unchanged."""
+        augmented form from soft_catalog() (soft preferences) or gumbel_catalog() (ST-Gumbel, L2),
+        reusable across calls while the tables are unchanged."""
         return self._rec_call("topk", u_ids, gumbel_u, catalog, soft_catalog, id_base=id_base, k=k,
                               filter_csr=filter_csr)
 
