@@ -160,7 +160,12 @@ def test_rec_driver_unchanged(dataset, tmp_path, gumbel):
         # and in evaluate (transUP.py:161 draws it even under model.eval()): statistical agreement only
         _compare_logs(ref, new, ("train_loss", "rec"), loss_rel=0.05, frac_abs=0.06)
     else:
-        _compare_logs(ref, new, ("train_loss", "rec"))
+        # item_recommendation.py:177-180 adds normLoss over user / item / preference rows that start exactly on the unit
+        # sphere: which of them get its 2 x gradient on the first steps depends on the reduction order of the driver's own
+        # torch.sum on CPU vs GPU (see the TransR note in test_kg_driver_unchanged); with Adagrad's first steps being
+        # +-lr per element that seed is visible in the logged loss.  KTUP's rec branch has no such term and is held to
+        # the tight bounds (test_joint_driver_unchanged); here the exact check is the checkpoint interchange below.
+        _compare_logs(ref, new, ("train_loss", "rec"), loss_rel=0.05, frac_abs=0.01)
         a = _eval_only("rec", dataset, tmp_path, name + "_refckpt_on_b200", flags, ref_ckpt, dropin=True)
         _compare_logs({"rec": [ref["rec"][-1]]}, {"rec": [a["rec"][-1]]}, ("rec",), frac_abs=0.005)
 

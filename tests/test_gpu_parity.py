@@ -1407,5 +1407,6 @@ def test_step_kernels_vs_oracle_k10_d100(cls_name, l1, mode):
     b = grads(nh, nt, nr, gn)
     got = grads_by_name(m)
     for k in a:
-        close(got[k + "_embeddings"], a[k] + b[k], rtol=2e-3, atol=2e-4, max_outliers=6 if l1 else 0)
+        w = a[k] + b[k]                      # relation rows collect hundreds of +- terms: absolute tolerance scales with them
+        close(got[k + "_embeddings"], w, rtol=2e-3, atol=2e-4 * max(1.0, float(np.abs(w).max())), max_outliers=6 if l1 else 0)
     m.check_indices()
