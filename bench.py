@@ -159,8 +159,14 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_fd = 1
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version / debug banner on fd 1 from C, so fd 1 is pointed at
+        # stderr for the life of the process and the line is written to a duplicate of the real stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(0)
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -527,7 +533,7 @@ def run_ours(args):
         if extra and not args.no_regions:
             out["cpu_baseline"]["regions"] = ref_arm.regions(reps=1)
     if rank == 0:
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
