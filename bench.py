@@ -254,8 +254,11 @@ def run_ours(args):
             loss_host[i].copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()       # the caller reads the step's losses
         return float(loss_host[0, 0])
-    for k in range(max(2, args.warmup // 2)):
+    for k in range(max(3, args.warmup)):
         step_e2e(k)
+    import gc
+    gc.collect()
+    gc.disable()                                   # no collector pause inside the timed host loop
     barrier()
     e_evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     e_evs[0].record()
@@ -263,6 +266,7 @@ def run_ours(args):
         step_e2e(k)
         e_evs[k + 1].record()
     barrier()
+    gc.enable()
     e2e_total = max_over_ranks(e_evs[0].elapsed_time(e_evs[args.steps]))
     e2e_steps = sorted(e_evs[k].elapsed_time(e_evs[k + 1]) for k in range(args.steps))
     e2e_ms = e2e_total / args.steps
