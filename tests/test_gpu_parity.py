@@ -944,7 +944,7 @@ def test_full_scale_configs():
     m.check_indices()
     del m
     torch.cuda.empty_cache()
-    # ---- rec side at 1M x 1M, d=128, P=20, Gumbel: top-10 items of a few users is reproducible
+    # ---- rec side at 1M x 1M, d=128, P=20, soft preferences: eval scores == forward scores of the same pairs
     mu = K.TransUPModel(False, 128, 8, 8, 20, False)
     mu.user_embeddings.weight = _big_table(1_000_000, 128, 4)
     mu.item_embeddings.weight = _big_table(1_000_000, 128, 5)
@@ -955,6 +955,47 @@ def test_full_scale_configs():
     for b in (0, 63):
         close(mu(u[b].expand(10), ids1[b]), sc1[b].cpu().numpy(), rtol=2e-4)      # eval score == forward score
     assert (sc1[:, 1:] >= sc1[:, :-1]).all()
+
+
+@pytest.mark.parametrize("ktup", [False, True])
+@pytest.mark.parametrize("l1", [False, True])
+def test_st_gumbel_eval_large_catalog_vs_oracle(ktup, l1):
+    """ST-Gumbel full-catalog evaluation at a BASELINE-sized catalog (50k items, d=100, P=20; configs[2]) with
+    explicit noise on a query slice, against the oracle's per-pair statement of transUP.py:84-102 / jTransUP.py:163-191:
+    the squared-L2 case runs the tiled kernel on augmented rows (its arg-max must pick the oracle's preference for
+    every one of the 200k pairs), L1 the one-warp-per-row kernel; plus top-K == ranking walk on the kernel's scores."""
+    import kgrec_b200 as K
+    from kgrec_b200 import evaluation as KE
+    torch.manual_seed(77)
+    rng = np.random.RandomState(77)
+    d, U, I, E, P, Q = 100, 300, 50_000, 60_000, 20, 4
+    if ktup:
+        ents = rng.permutation(E)[:I]
+        new_map = {i: ((int(ents[i]) if i % 10 < 7 else -1), i) for i in range(I)}
+        m = K.jTransUPModel(l1, d, U, I, E, P, {i: i for i in range(I)}, new_map, False, True)
+    else:
+        m = K.TransUPModel(l1, d, U, I, P, True)
+    W = np_tables(m)
+    qu = rng.randint(0, U, Q)
+    noise = rng.rand(Q, I, P).astype(np.float32)
+    tn = torch.from_numpy(noise)
+    if ktup:
+        want = O.ktup_rec_eval(W["user"], W["item"], W["ent"], W["rel"], W["norm"], W["pref"], W["pref_norm"],
+                               m.item2ent.cpu().numpy().astype(np.int64), qu, l1, noise)
+        got = m.evaluateRec(lt(qu), gumbel_u=tn)
+    else:
+        want = O.tup_eval(W["user"], W["item"], W["pref"], W["pref_norm"], qu, l1, noise)
+        got = m.evaluate(lt(qu), gumbel_u=tn)
+    close(got, want, rtol=5e-4, atol=1e-4)
+    goth = got.cpu().numpy()
+    ids, sc = KE.keys_to_ids_scores(m.topk_items(lt(qu), k=10, gumbel_u=tn))
+    for b in range(Q):
+        assert ids[b].tolist() == O.rec_topk(goth[b], None, 10)
+        np.testing.assert_array_equal(sc[b].cpu().numpy(), goth[b][ids[b].cpu().numpy()])
+    # in-kernel noise: a different draw, same distribution -- scores stay in the support of the explicit-noise run
+    free = m.topk_items(lt(qu), k=10)
+    assert free.shape == (Q, 10) and (KE.keys_to_ids_scores(free)[0] >= 0).all()
+    m.check_indices()
 
 
 def test_edge_cases():
