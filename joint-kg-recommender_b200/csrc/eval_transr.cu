@@ -11,7 +11,7 @@
 // so the filtered top-K and rank-count modes come for free and no library GEMM is involved.  The path's one
 // dense contraction is a hand-written register-tiled FP32 kernel on the CUDA cores (north_star: no tensor
 // cores -- TF32 would not hold the 1e-4 score tolerance): a persistent CTA keeps M_r^T in shared memory and
-// walks 128-row catalog tiles, 8 x 8 accumulators per thread.
+// walks 128-row catalog tiles (cp.async, row-major), 8 x 8 accumulators per thread, two CTAs per SM at d <= 100.
 #include "common.cuh"
 
 namespace kgrec {
@@ -21,12 +21,18 @@ constexpr int kPLD = kPT + 4;         // shared-memory row pitch (floats): keeps
 constexpr int kProjThreads = 256;
 
 // out[n, a] = sum_b cat[n, b] * M[a, b]      (M = Proj[r].view(d, d), row-major: misc.py:25, 32-33)
-__global__ void __launch_bounds__(kProjThreads, 1)
+// Shared memory: Mt[b][a] = M[a][b] (a padded to 128 with zeros, pitch 132) and the catalog tile ROW-MAJOR, Es[n][b] with
+// pitch d + 4 floats (an odd number of 16-byte units for d = 100; for other d the few distinct rows a warp reads are
+// multicast), copied in with cp.async -- no transposing stores.  A thread owns rows {4 ty.., 64 + 4 ty..} and columns
+// {4 tx.., 64 + 4 tx..}: per 4 steps of b it issues 8 + 8 LDS.128 for 256 FMAs.  Sized by d, two CTAs fit an SM at
+// d <= 100, so one CTA's tile load overlaps the other's FMA loop.
+__global__ void __launch_bounds__(kProjThreads, 2)
 k_transr_project(const float* __restrict__ M, const float* __restrict__ cat, int64_t cat_ld, int64_t n_cat, int d,
                  float* __restrict__ out, int64_t out_ld) {
   extern __shared__ __align__(16) float smem[];
-  float* Mt = smem;                   // Mt[b][a] = M[a][b], a padded to 128 with zeros
-  float* Et = smem + kPT * kPLD;      // Et[b][n] = cat[n0 + n][b]
+  const int epitch = d + 4;
+  float* Mt = smem;                   // [d][kPLD]
+  float* Es = smem + d * kPLD;        // [kPT][epitch]
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int dq = d >> 2;              // 16-byte chunks per row
   for (int i = tid; i < d * kPLD; i += kProjThreads) Mt[i] = 0.f;
@@ -40,34 +46,47 @@ k_transr_project(const float* __restrict__ M, const float* __restrict__ cat, int
   const int64_t n_tiles = (n_cat + kPT - 1) / kPT;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t n0 = tile * kPT;
-    __syncthreads();                  // previous tile's Et is no longer read; Mt is complete
+    __syncthreads();                  // previous tile's Es is no longer read; Mt is complete
     for (int i = tid; i < kPT * dq; i += kProjThreads) {
       const int n = i / dq, c = i - n * dq;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + n < n_cat) v = ldg_f4(reinterpret_cast<const float4*>(cat + (n0 + n) * cat_ld) + c);
-      Et[(4 * c + 0) * kPLD + n] = v.x; Et[(4 * c + 1) * kPLD + n] = v.y;
-      Et[(4 * c + 2) * kPLD + n] = v.z; Et[(4 * c + 3) * kPLD + n] = v.w;
+      float* dst = Es + n * epitch + 4 * c;
+      if (n0 + n < n_cat) {
+        const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(cat + (n0 + n) * cat_ld + 4 * c) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    // thread tile: rows {4 ty .. 4 ty + 3} and {64 + 4 ty ..}, columns {4 tx ..} and {64 + 4 tx ..}
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     const bool hi_cols = 64 + 4 * tx < d;
-#pragma unroll 4
-    for (int k = 0; k < d; ++k) {
-      const float4 e0 = *reinterpret_cast<const float4*>(Et + k * kPLD + 4 * ty);
-      const float4 e1 = *reinterpret_cast<const float4*>(Et + k * kPLD + 64 + 4 * ty);
-      const float4 m0 = *reinterpret_cast<const float4*>(Mt + k * kPLD + 4 * tx);
-      const float4 m1 = *reinterpret_cast<const float4*>(Mt + k * kPLD + 64 + 4 * tx);
-      const float e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-      const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const float* e_lo = Es + (4 * ty) * epitch;
+    const float* e_hi = Es + (64 + 4 * ty) * epitch;
+#pragma unroll 1
+    for (int k = 0; k < d; k += 4) {
+      float4 e[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i) {
+        e[i] = *reinterpret_cast<const float4*>(e_lo + i * epitch + k);
+        e[4 + i] = *reinterpret_cast<const float4*>(e_hi + i * epitch + k);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(e[i], m[j], acc[i][j]);
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 m0 = *reinterpret_cast<const float4*>(Mt + (k + kk) * kPLD + 4 * tx);
+        const float4 m1 = *reinterpret_cast<const float4*>(Mt + (k + kk) * kPLD + 64 + 4 * tx);
+        const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ev = kk == 0 ? e[i].x : (kk == 1 ? e[i].y : (kk == 2 ? e[i].z : e[i].w));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ev, m[j], acc[i][j]);
+        }
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -151,15 +170,17 @@ int transr_check(const TransRCall& C) {
 // Project the shard and build the query vectors of run g.
 int transr_prepare(const TransRCall& C, int g) {
   static bool attr_done = false;
-  const size_t smem = 2u * kPT * kPLD * sizeof(float);
+  const int d = C.T->dim;
+  const size_t smem = (static_cast<size_t>(d) * kPLD + static_cast<size_t>(kPT) * (d + 4)) * sizeof(float);
   if (!attr_done) {
-    KGREC_CUDA_OK(cudaFuncSetAttribute(k_transr_project, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    KGREC_CUDA_OK(cudaFuncSetAttribute(k_transr_project, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>((2u * kPT * kPLD) * sizeof(float))));
     attr_done = true;
   }
-  const int d = C.T->dim;
   const int64_t rel = C.run_rel[g], i0 = C.run_begin[g], n = C.run_begin[g + 1] - i0;
   const int64_t tiles = (C.n_cat + kPT - 1) / kPT;
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  const int64_t slots = static_cast<int64_t>(sm_count()) * (smem <= 110 * 1024 ? 2 : 1);     // resident CTAs
+  const int grid = static_cast<int>(tiles < slots ? tiles : slots);
   k_transr_project<<<grid, kProjThreads, smem, C.st>>>(C.T->proj + rel * static_cast<int64_t>(d) * d, C.cat, C.cat_ld, C.n_cat, d,
                                                       C.proj_ws, d);
   KGREC_CUDA_OK(cudaGetLastError());
