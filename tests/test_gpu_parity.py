@@ -1451,3 +1451,21 @@ def test_step_kernels_vs_oracle_k10_d100(cls_name, l1, mode):
         w = a[k] + b[k]                      # relation rows collect hundreds of +- terms: absolute tolerance scales with them
         close(got[k + "_embeddings"], w, rtol=2e-3, atol=2e-4 * max(1.0, float(np.abs(w).max())), max_outliers=6 if l1 else 0)
     m.check_indices()
+
+
+def test_device_prefetcher_ring_reuse():
+    """Host batches staged through the fixed device ring arrive intact, in order, including a ragged last batch,
+    while the consumer's (slow) kernels on slot s are ordered before the copy that refills it."""
+    from kgrec_b200.data import DevicePrefetcher
+    g = torch.Generator().manual_seed(1)
+    host = [[torch.randint(0, 1 << 30, (50_000 if i < 6 else 777,), generator=g, dtype=torch.int32).pin_memory(),
+             torch.randint(0, 1 << 30, (123,), generator=g, dtype=torch.int64).pin_memory()] for i in range(7)]
+    sink = torch.zeros(4096, 4096, device="cuda")
+    sums = []
+    for dev_batch in DevicePrefetcher(iter(host), "cuda", depth=2):
+        sink = sink @ sink                                   # keep the compute stream busy past the next copies
+        sums.append((dev_batch[0].long().sum() + dev_batch[1].sum()))
+    want = [int(a.long().sum() + b.sum()) for a, b in host]
+    assert [int(s) for s in sums] == want
+    for a, b in zip(DevicePrefetcher(iter(host[:3]), "cuda"), host[:3]):     # a second pass reuses the ring
+        assert torch.equal(a[0].cpu(), b[0]) and torch.equal(a[1].cpu(), b[1])
