@@ -310,6 +310,24 @@ int kgrec_rows_update(const kgrec_opt_table* tabs_host, int n_tabs, int32_t epoc
                       float eps, float beta1, float beta2, int64_t step, float weight_decay,
                       const float* sqnorm, float max_norm, kgrec_stream_t stream);
 
+/* ---- row-factored training step of the soft-preference rec models (TUP / KTUP, use_st_gumbel = 0) --------------
+ * transUP.py:69-82, 105-115; jTransUP.py:122-161, 250-260.  With raw logits as mixing weights r = RA_u + RA_i and
+ * w = WB_u + WB_i with RA_x = hf (x P'^T / 2) P' (WB_x with N'): the [P x d] contractions are done once per DISTINCT
+ * row of the step (rows carrying the epoch mark: kgrec_rows_mark must have run on the step's user / item ids with
+ * this epoch) instead of once per pair; the pair kernel is O(d).  Positives (pu, pi), negatives ni [n_pos, n_neg]
+ * (the user is shared: getNegRatings, utils/data.py:64-85).  Gradients are ADDED to the dense accumulators in `acc`
+ * (grads->mode 1: user, item, pref, pref_norm [, ent]; the KTUP caller copies pref / pref_norm's to rel / norm);
+ * scores and per-batch losses as kgrec_rank_loss_step.  workspace: kgrec_rec_rows_workspace_floats floats, persistent
+ * across steps (first_use = 1 on the first call zero-fills its accumulators).  loss_workspace: n_pos floats.
+ * embedding_size % 4 == 0 and <= 128, preference_total <= 32, n_neg <= 31. */
+int64_t kgrec_rec_rows_workspace_floats(int64_t n_user, int64_t n_item, int32_t dim, int32_t n_pref, int ktup);
+int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const void* pu, const void* pi, const void* ni,
+                        int idx_bytes, int64_t n_pos, int32_t n_neg, int64_t batch_pos, int loss_kind,
+                        float margin_or_target, float grad_loss, const int32_t* marks_user,
+                        const int32_t* marks_item, int32_t epoch, float* workspace, int32_t first_use,
+                        const kgrec_grads* acc, float* pos_scores, float* neg_scores, float* loss,
+                        void* loss_workspace, int32_t* status, kgrec_stream_t stream);
+
 /* ---- the drivers' recommendation-side regularisers (utils/loss.py:18-23) -------------------------
  * item_recommendation.py:177-180: normLoss(user rows) + normLoss(item rows of cat[pos, neg]) +
  * normLoss(pref table) + orthogonalLoss(pref, pref_norm); knowledgable_recommendation.py:343-344:

@@ -1,0 +1,440 @@
+// Row-factored training step for TUP / KTUP with SOFT preferences (use_st_gumbel = 0: the mode of the reference's shipped
+// scripts, transup.sh / ktup.sh `-nouse_st_gumbel`; transUP.py:69-82, 105-115, jTransUP.py:122-161, 250-260).
+//
+// With raw logits as mixing weights everything the preference induction does is LINEAR in s = u + i':
+//     z = s P'^T / 2,   r = hf z P' = RA_u + RA_i,   w = hf z N' = WB_u + WB_i,     RA_x = hf (x P'^T / 2) P',  WB_x likewise with N'
+// so the nine [P x d] contractions the pair kernel (train_rec_tile.cu) spends per PAIR can be spent per DISTINCT ROW of a
+// step instead -- a step of 256 batches touches each of 50k users ~10 times, each of 6k users of an ml1m-sized rec side ~90
+// times (SURVEY 7.3-1 points at the same factorisation for evaluation):
+//   k_rows_compact     marked rows (the optimizer's epoch marks) -> a dense list per table
+//   k_soft_rows_fwd    per listed row: zx = x P'^T / 2 [P], RA_x, WB_x [d]   (KTUP items: x = item + ent[item2ent], also stored)
+//   k_soft_pairs       per group (positive + its negatives, one warp): r, w by two adds; a = u - i', s = a.w,
+//                      e = a + r - s w, score, ranking loss, then eps, gx = eps - (eps.w) w, gw = -((eps.w) a + s eps);
+//                      O(d) per pair; gradients leave as atomic row adds: gx -> the rows' direct gradient, eps -> G_RA, gw -> G_WB
+//   k_soft_rows_bwd    per listed row: g_z = hf (G_RA P'^T + G_WB N'^T), row gradient += g_z P' / 2, and the table gradients
+//                      dP' += hf zx^T G_RA + g_z^T x / 2, dN' += hf zx^T G_WB (register tiles over 32-row batches, one flush per CTA)
+// All of it accumulates into the dense accumulators of the sparse-row optimizer (csrc/optim.cu), which then clips and updates.
+// Same arithmetic as the pair kernel up to re-association; parity: tests/test_gpu_parity.py::test_sparse_row_optimizer_rec_models.
+#include "train_dev.cuh"
+
+namespace kgrec {
+namespace {
+
+constexpr int kRowThreads = 256;
+constexpr int kRowBatch = 32;         // rows per CTA batch in k_soft_rows_bwd (4 per warp)
+
+__global__ void __launch_bounds__(256)
+k_rows_compact(const int32_t* __restrict__ marks, int64_t rows, int32_t epoch, int32_t* __restrict__ list, int32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t c = warp; c * 32 < rows; c += n_warps) {
+    const int64_t row = c * 32 + lane;
+    const bool mine = row < rows && __ldg(marks + row) == epoch;
+    const unsigned m = __ballot_sync(FULL, mine);
+    if (!m) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (mine) list[base + __popc(m & ((1u << lane) - 1u))] = static_cast<int32_t>(row);
+  }
+}
+
+struct SoftRows {                 // one side (users or items) of the rec model
+  const float* table;             // [rows, d] parameter rows
+  const float* ent;               // KTUP items: entity table, else NULL
+  const int32_t* item2ent;
+  int64_t n_ent;
+  float* x;                       // KTUP items: effective rows item + ent [rows, d]; else NULL (x = table)
+  float *ra, *wb;                 // [rows, d]
+  float* zx;                      // [rows, P]
+  float *g_ra, *g_wb;             // [rows, d] accumulators, zeroed again by the backward
+  float* gx;                      // direct row gradient: the table's dense accumulator, or (KTUP items) a work buffer
+  float *acc_table, *acc_ent;     // KTUP items: where gx + logit path goes
+  const int32_t* list;
+  const int32_t* count;
+};
+
+__device__ __forceinline__ void stage_tables(const kgrec_tables& T, int ktup, float* sP, float* sN) {
+  const int d = T.dim, P = T.n_pref;
+  for (int idx = threadIdx.x; idx < P * d; idx += blockDim.x) {
+    const int k = idx / d, j = idx - k * d;
+    float a = __ldg(T.pref + static_cast<int64_t>(k) * T.ld + j), b = __ldg(T.pref_norm + static_cast<int64_t>(k) * T.ld + j);
+    if (ktup) { a += __ldg(T.rel + static_cast<int64_t>(k) * T.ld + j); b += __ldg(T.norm + static_cast<int64_t>(k) * T.ld + j); }
+    sP[idx] = a;
+    sN[idx] = b;
+  }
+}
+
+// P (<= 32) dots of length d between the lane-distributed vector(s) and the table rows in shared memory; lane k gets dot k.
+// v2 / t2 optional second pair (sum of both products).
+__device__ __forceinline__ float dots_to_lanes(const float4& v1, const float* t1, const float4* v2, const float* t2, int P, int d,
+                                               int lane, bool act) {
+  float mine = 0.f;
+  for (int g = 0; g < P; g += 8) {
+    float vals[8];
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      float s = 0.f;
+      if (g + kk < P && act) {
+        const float4 a = *reinterpret_cast<const float4*>(t1 + (g + kk) * d + 4 * lane);
+        s = fmaf(v1.x, a.x, fmaf(v1.y, a.y, fmaf(v1.z, a.z, v1.w * a.w)));
+        if (v2) {
+          const float4 b = *reinterpret_cast<const float4*>(t2 + (g + kk) * d + 4 * lane);
+          s = fmaf(v2->x, b.x, fmaf(v2->y, b.y, fmaf(v2->z, b.z, fmaf(v2->w, b.w, s))));
+        }
+      }
+      vals[kk] = s;
+    }
+    const float r = warp_reduce_scatter8(vals, lane);      // lane l holds dot g + ((l >> 2) & 7)
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      const float v = __shfl_sync(FULL, r, kk * 4);
+      if (lane == g + kk) mine = v;
+    }
+  }
+  return mine;
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+k_soft_rows_fwd(const kgrec_tables T, const int ktup, const SoftRows S) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = T.dim, P = T.n_pref, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* sP = sm;
+  float* sN = sP + P * d;
+  stage_tables(T, ktup, sP, sN);
+  __syncthreads();
+  const float hf = ktup ? 0.5f : 1.f;
+  const bool act = lane * 4 < d;
+  const int n = *S.count;
+  for (int i = blockIdx.x * (kRowThreads / 32) + wid; i < n; i += gridDim.x * (kRowThreads / 32)) {
+    const int64_t row = S.list[i];
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) {
+      x = ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + lane);
+      if (S.ent) {
+        const int64_t ia = __ldg(S.item2ent + row);
+        const float4 e = ldg_f4(reinterpret_cast<const float4*>(S.ent + ia * T.ld) + lane);
+        x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
+        reinterpret_cast<float4*>(S.x + row * d)[lane] = x;
+      }
+    }
+    const float zk = 0.5f * dots_to_lanes(x, sP, nullptr, nullptr, P, d, lane, act);     // lane k: zx_k
+    if (lane < P) S.zx[row * P + lane] = zk;
+    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), wb = ra;
+    for (int k = 0; k < P; ++k) {
+      const float z = hf * __shfl_sync(FULL, zk, k);
+      if (act) {
+        const float4 p = *reinterpret_cast<const float4*>(sP + k * d + 4 * lane), nn = *reinterpret_cast<const float4*>(sN + k * d + 4 * lane);
+        ra.x = fmaf(z, p.x, ra.x); ra.y = fmaf(z, p.y, ra.y); ra.z = fmaf(z, p.z, ra.z); ra.w = fmaf(z, p.w, ra.w);
+        wb.x = fmaf(z, nn.x, wb.x); wb.y = fmaf(z, nn.y, wb.y); wb.z = fmaf(z, nn.z, wb.z); wb.w = fmaf(z, nn.w, wb.w);
+      }
+    }
+    if (act) {
+      reinterpret_cast<float4*>(S.ra + row * d)[lane] = ra;
+      reinterpret_cast<float4*>(S.wb + row * d)[lane] = wb;
+    }
+  }
+}
+
+struct SoftPairs {
+  const void *pu, *pi, *ni;
+  int is64;
+  LossCfg L;
+  float grad_loss;
+  int64_t n_user, n_item;
+  const float *xu, *xi;           // effective rows [rows, d] (pitch ldu / ldi)
+  int64_t ldu, ldi;
+  const float *ra_u, *wb_u, *ra_i, *wb_i;
+  float *gx_u, *gx_i, *g_ra_u, *g_wb_u, *g_ra_i, *g_wb_i;
+  float *pos_scores, *neg_scores, *group_loss;
+  int32_t* status;
+  int d, l1;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ float4 axpy4(float s, const float4& x, const float4& y) {
+  return make_float4(fmaf(s, x.x, y.x), fmaf(s, x.y, y.y), fmaf(s, x.z, y.z), fmaf(s, x.w, y.w));
+}
+
+__global__ void __launch_bounds__(kThreads, 4)
+k_soft_pairs(const SoftPairs A) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int d = A.d, K = A.L.n_neg;
+  const bool act = lane * 4 < d;
+  const int64_t n_pos = A.L.n_pos;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool bad = false;
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + wid; j < n_pos; j += static_cast<int64_t>(gridDim.x) * kWarpsPerCta) {
+    int64_t iu = load_idx(A.pu, j, A.is64);
+    if (static_cast<uint64_t>(iu) >= static_cast<uint64_t>(A.n_user)) { bad = true; iu = 0; }
+    // lane m holds the item id of member m (0 = the positive)
+    int64_t idm = 0;
+    if (lane <= K) {
+      idm = lane == 0 ? load_idx(A.pi, j, A.is64) : load_idx(A.ni, j * K + lane - 1, A.is64);
+      if (static_cast<uint64_t>(idm) >= static_cast<uint64_t>(A.n_item)) { bad = true; idm = 0; }
+    }
+    float4 u = z4, rau = z4, wbu = z4;
+    if (act) {
+      u = ld4(A.xu + iu * A.ldu + 4 * lane);
+      rau = ld4(A.ra_u + iu * d + 4 * lane);
+      wbu = ld4(A.wb_u + iu * d + 4 * lane);
+    }
+    // pass 1: scores (lane m keeps member m's score and s = a.w)
+    float my_score = 0.f, my_s = 0.f;
+    for (int m = 0; m <= K; ++m) {
+      const int64_t id = __shfl_sync(FULL, idm, m);
+      float4 x = z4, r = z4, w = z4;
+      if (act) {
+        x = ld4(A.xi + id * A.ldi + 4 * lane);
+        r = add4(rau, ld4(A.ra_i + id * d + 4 * lane));
+        w = add4(wbu, ld4(A.wb_i + id * d + 4 * lane));
+      }
+      const float4 a = sub4(u, x);
+      const float s = warp_sum(dot4(a, w));
+      const float4 e = axpy4(-s, w, add4(a, r));
+      const float sc = warp_sum(dist_term(e.x, A.l1) + dist_term(e.y, A.l1) + dist_term(e.z, A.l1) + dist_term(e.w, A.l1));
+      if (lane == m) { my_score = sc; my_s = s; }
+    }
+    const float sp = __shfl_sync(FULL, my_score, 0);
+    // ranking loss of the group and its derivative (utils/loss.py:8-16, 29-31)
+    const float up = A.grad_loss * loss_batch_scale(A.L, j);
+    float term = 0.f, dp = 0.f;
+    if (lane >= 1 && lane <= K) { term = loss_term(A.L, sp, my_score); dp = loss_dpos(A.L, sp, my_score); }
+    const float lsum = warp_sum(term), dsum = warp_sum(dp);
+    const float my_g = lane == 0 ? dsum * up : -dp * up;          // dLoss / dscore of member `lane`
+    if (lane == 0) { A.pos_scores[j] = sp; A.group_loss[j] = lsum; }
+    if (lane >= 1 && lane <= K) A.neg_scores[j * K + lane - 1] = my_score;
+    // pass 2: gradients
+    float4 gu = z4, gra = z4, gwb = z4;
+    for (int m = 0; m <= K; ++m) {
+      const float g = __shfl_sync(FULL, my_g, m);
+      if (g == 0.f) continue;                                     // warp-uniform (inactive hinge)
+      const int64_t id = __shfl_sync(FULL, idm, m);
+      const float s = __shfl_sync(FULL, my_s, m);
+      float4 x = z4, r = z4, w = z4;
+      if (act) {
+        x = ld4(A.xi + id * A.ldi + 4 * lane);
+        r = add4(rau, ld4(A.ra_i + id * d + 4 * lane));
+        w = add4(wbu, ld4(A.wb_i + id * d + 4 * lane));
+      }
+      const float4 a = sub4(u, x);
+      const float4 e = axpy4(-s, w, add4(a, r));
+      const float4 eps = make_float4(g * ddist_term(e.x, A.l1), g * ddist_term(e.y, A.l1), g * ddist_term(e.z, A.l1), g * ddist_term(e.w, A.l1));
+      const float ew = warp_sum(dot4(eps, w));
+      const float4 gx = axpy4(-ew, w, eps);                                       // eps - (eps.w) w
+      const float4 gw = make_float4(-fmaf(ew, a.x, s * eps.x), -fmaf(ew, a.y, s * eps.y), -fmaf(ew, a.z, s * eps.z), -fmaf(ew, a.w, s * eps.w));
+      gu = add4(gu, gx); gra = add4(gra, eps); gwb = add4(gwb, gw);
+      if (act) {
+        red_add_f4(A.gx_i + id * d + 4 * lane, -gx.x, -gx.y, -gx.z, -gx.w);
+        red_add_f4(A.g_ra_i + id * d + 4 * lane, eps.x, eps.y, eps.z, eps.w);
+        red_add_f4(A.g_wb_i + id * d + 4 * lane, gw.x, gw.y, gw.z, gw.w);
+      }
+    }
+    if (act) {
+      red_add_f4(A.gx_u + iu * d + 4 * lane, gu.x, gu.y, gu.z, gu.w);
+      red_add_f4(A.g_ra_u + iu * d + 4 * lane, gra.x, gra.y, gra.z, gra.w);
+      red_add_f4(A.g_wb_u + iu * d + 4 * lane, gwb.x, gwb.y, gwb.z, gwb.w);
+    }
+  }
+  if (bad && A.status) *A.status = 1;
+}
+
+__global__ void __launch_bounds__(kRowThreads)
+k_soft_rows_bwd(const kgrec_tables T, const int ktup, const SoftRows S, float* __restrict__ acc_pref, float* __restrict__ acc_pref_norm) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = T.dim, P = T.n_pref, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* sP = sm;
+  float* sN = sP + P * d;
+  float* st = sN + P * d;                    // staging of a batch: per row [zx (P) | gz (P) | G_RA (d) | G_WB (d) | x (d)]
+  const int rs = 2 * P + 3 * d;
+  stage_tables(T, ktup, sP, sN);
+  const float hf = ktup ? 0.5f : 1.f;
+  const bool act = lane * 4 < d;
+  const int n = *S.count;
+  // phase-B ownership: column c, preferences [k0, k0 + KH)
+  const int c = threadIdx.x % 128, half = threadIdx.x / 128;
+  const int KH = (P + 1) / 2, k0 = half * KH;
+  float accP[16], accN[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { accP[k] = 0.f; accN[k] = 0.f; }
+  __syncthreads();
+  for (int b0 = blockIdx.x * kRowBatch; b0 < n; b0 += gridDim.x * kRowBatch) {
+    // phase A: a warp finishes the row gradients of 4 rows and stages what the table gradients need
+    for (int rr = wid; rr < kRowBatch; rr += kRowThreads / 32) {
+      const int i = b0 + rr;
+      float* srow = st + rr * rs;
+      if (i >= n) {                            // rows past the end contribute zeros
+        for (int t = lane; t < rs; t += 32) srow[t] = 0.f;
+        continue;
+      }
+      const int64_t row = S.list[i];
+      float4 gra = make_float4(0.f, 0.f, 0.f, 0.f), gwb = gra, x = gra;
+      if (act) {
+        gra = ld4(S.g_ra + row * d + 4 * lane);
+        gwb = ld4(S.g_wb + row * d + 4 * lane);
+        reinterpret_cast<float4*>(S.g_ra + row * d)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);      // clean for the next step
+        reinterpret_cast<float4*>(S.g_wb + row * d)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x = S.x ? ld4(S.x + row * d + 4 * lane) : ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + lane);
+      }
+      const float gz = hf * dots_to_lanes(gra, sP, &gwb, sN, P, d, lane, act);        // lane k: g_z[k]
+      float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < P; ++k) {
+        const float cz = 0.5f * __shfl_sync(FULL, gz, k);
+        if (act) {
+          const float4 p = *reinterpret_cast<const float4*>(sP + k * d + 4 * lane);
+          gs.x = fmaf(cz, p.x, gs.x); gs.y = fmaf(cz, p.y, gs.y); gs.z = fmaf(cz, p.z, gs.z); gs.w = fmaf(cz, p.w, gs.w);
+        }
+      }
+      if (act) {
+        if (S.acc_table) {                     // KTUP items: direct gradient sits in a work buffer; item and aligned entity both get the sum
+          float4 t = ld4(S.gx + row * d + 4 * lane);
+          reinterpret_cast<float4*>(S.gx + row * d)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+          t = add4(t, gs);
+          float4* ai = reinterpret_cast<float4*>(S.acc_table + row * d) + lane;
+          *ai = add4(*ai, t);
+          const int64_t ia = __ldg(S.item2ent + row);
+          if (ia != S.n_ent - 1) red_add_f4(S.acc_ent + ia * d + 4 * lane, t.x, t.y, t.z, t.w);    // padding row: no gradient (jTransUP.py:96)
+        } else {
+          float4* gp = reinterpret_cast<float4*>(S.gx + row * d) + lane;
+          *gp = add4(*gp, gs);
+        }
+        reinterpret_cast<float4*>(srow + 2 * P)[lane] = gra;
+        reinterpret_cast<float4*>(srow + 2 * P + d)[lane] = gwb;
+        reinterpret_cast<float4*>(srow + 2 * P + 2 * d)[lane] = x;
+      }
+      if (lane < P) { srow[lane] = hf * S.zx[row * P + lane]; srow[P + lane] = 0.5f * gz; }
+    }
+    __syncthreads();
+    // phase B: dP'[k][c] += hf zx_k G_RA[c] + (g_z[k] / 2) x[c];  dN'[k][c] += hf zx_k G_WB[c]
+    if (c < d) {
+      for (int rr = 0; rr < kRowBatch; ++rr) {
+        const float* srow = st + rr * rs;
+        const float gra = srow[2 * P + c], gwb = srow[2 * P + d + c], xv = srow[2 * P + 2 * d + c];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (k < KH && k0 + k < P) {
+            const float zk = srow[k0 + k], gk = srow[P + k0 + k];
+            accP[k] = fmaf(zk, gra, fmaf(gk, xv, accP[k]));
+            accN[k] = fmaf(zk, gwb, accN[k]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (c < d) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      if (k < KH && k0 + k < P) {
+        if (accP[k] != 0.f) atomicAdd(acc_pref + static_cast<int64_t>(k0 + k) * d + c, accP[k]);
+        if (accN[k] != 0.f) atomicAdd(acc_pref_norm + static_cast<int64_t>(k0 + k) * d + c, accN[k]);
+      }
+    }
+  }
+}
+
+}  // namespace
+}  // namespace kgrec
+
+using namespace kgrec;
+
+extern "C" int64_t kgrec_rec_rows_workspace_floats(int64_t n_user, int64_t n_item, int32_t dim, int32_t n_pref, int ktup) {
+  // per side: ra, wb, g_ra, g_wb [rows, d], zx [rows, P], list [rows] (+1 count); KTUP items: x, gx [rows, d]
+  const int64_t per = 4 * static_cast<int64_t>(dim) + n_pref + 1;
+  return n_user * per + n_item * (per + (ktup ? 2 * static_cast<int64_t>(dim) : 0)) + 16;
+}
+
+extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const void* pu, const void* pi, const void* ni, int idx_bytes,
+                                   int64_t n_pos, int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
+                                   float grad_loss, const int32_t* marks_user, const int32_t* marks_item, int32_t epoch,
+                                   float* workspace, int32_t first_use, const kgrec_grads* acc, float* pos_scores,
+                                   float* neg_scores, float* loss, void* loss_workspace, int32_t* status, kgrec_stream_t stream) {
+  if (!tables || (model != KGREC_TUP && model != KGREC_KTUP)) { set_error("rec_rows_step: TUP / KTUP"); return KGREC_ERR_INVALID; }
+  const kgrec_tables& T = *tables;
+  const int d = T.dim, P = T.n_pref;
+  const bool ktup = model == KGREC_KTUP;
+  if (T.use_gumbel) { set_error("rec_rows_step is the soft-preference path (use_st_gumbel = 0)"); return KGREC_ERR_UNSUPPORTED; }
+  if (d <= 0 || d > 128 || d % 4 || T.ld != d || P <= 0 || P > 32 || n_neg < 1 || n_neg > 31) {
+    set_error("rec_rows_step: embedding_size %% 4 == 0 and <= 128, contiguous tables, preference_total <= 32, 1..31 negatives per positive");
+    return KGREC_ERR_UNSUPPORTED;
+  }
+  if (!T.user || !T.item || !T.pref || !T.pref_norm || (ktup && (!T.ent || !T.rel || !T.norm || !T.item2ent))) { set_error("rec_rows_step: table missing"); return KGREC_ERR_INVALID; }
+  if (!pu || !pi || !ni || (idx_bytes != 4 && idx_bytes != 8) || n_pos < 0 || batch_pos < 1 || !marks_user || !marks_item || !workspace || !acc ||
+      acc->mode != 1 || !acc->user || !acc->item || !acc->pref || !acc->pref_norm || (ktup && !acc->ent) || !pos_scores || !neg_scores || !loss ||
+      !loss_workspace) {
+    set_error("rec_rows_step: NULL / bad argument (gradients go to dense accumulators, grads->mode 1)");
+    return KGREC_ERR_INVALID;
+  }
+  if (loss_kind != KGREC_LOSS_MARGIN && loss_kind != KGREC_LOSS_BPR) { set_error("unknown loss %d", loss_kind); return KGREC_ERR_INVALID; }
+  if (n_pos == 0) return KGREC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // carve the workspace
+  float* w = workspace;
+  auto take = [&](int64_t n) { float* p = w; w += (n + 3) & ~static_cast<int64_t>(3); return p; };
+  SoftRows U{}, I{};
+  U.table = T.user; I.table = T.item;
+  const int64_t nu = T.n_user, nit = T.n_item;
+  U.ra = take(nu * d); U.wb = take(nu * d); U.g_ra = take(nu * d); U.g_wb = take(nu * d); U.zx = take(nu * P);
+  I.ra = take(nit * d); I.wb = take(nit * d); I.g_ra = take(nit * d); I.g_wb = take(nit * d); I.zx = take(nit * P);
+  float* gx_i_buf = nullptr;
+  if (ktup) { I.x = take(nit * d); gx_i_buf = take(nit * d); }
+  int32_t* list_u = reinterpret_cast<int32_t*>(take(nu));
+  int32_t* list_i = reinterpret_cast<int32_t*>(take(nit));
+  int32_t* counts = reinterpret_cast<int32_t*>(take(4));
+  if (first_use) {        // accumulators start clean; afterwards the backward leaves them clean
+    KGREC_CUDA_OK(cudaMemsetAsync(U.g_ra, 0, sizeof(float) * 2 * nu * d, st));
+    KGREC_CUDA_OK(cudaMemsetAsync(I.g_ra, 0, sizeof(float) * 2 * nit * d, st));
+    if (ktup) KGREC_CUDA_OK(cudaMemsetAsync(gx_i_buf, 0, sizeof(float) * nit * d, st));
+  }
+  KGREC_CUDA_OK(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), st));
+  U.list = list_u; U.count = counts; I.list = list_i; I.count = counts + 1;
+  U.gx = acc->user;
+  if (ktup) {
+    I.ent = T.ent; I.item2ent = T.item2ent; I.n_ent = T.n_ent; I.gx = gx_i_buf; I.acc_table = acc->item; I.acc_ent = acc->ent;
+  } else {
+    I.gx = acc->item;
+  }
+  const int cap = sm_count() * 8;
+  auto grid1 = [&](int64_t units) { const int64_t g = units < 1 ? 1 : units; return static_cast<int>(g < cap ? g : cap); };
+  k_rows_compact<<<grid1((nu + 255) / 256), 256, 0, st>>>(marks_user, nu, epoch, list_u, counts);
+  k_rows_compact<<<grid1((nit + 255) / 256), 256, 0, st>>>(marks_item, nit, epoch, list_i, counts + 1);
+  KGREC_CUDA_OK(cudaGetLastError());
+  const size_t smem_f = static_cast<size_t>(2) * P * d * sizeof(float);
+  const size_t smem_b = (static_cast<size_t>(2) * P * d + static_cast<size_t>(kRowBatch) * (2 * P + 3 * d)) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    attr_done = true;
+  }
+  // rows touched: at most min(rows, ids) per side
+  const int64_t max_u = nu < n_pos ? nu : n_pos, max_i = nit < n_pos * (1 + n_neg) ? nit : n_pos * (1 + n_neg);
+  k_soft_rows_fwd<<<grid1((max_u + 7) / 8), kRowThreads, smem_f, st>>>(T, ktup ? 1 : 0, U);
+  k_soft_rows_fwd<<<grid1((max_i + 7) / 8), kRowThreads, smem_f, st>>>(T, ktup ? 1 : 0, I);
+  KGREC_CUDA_OK(cudaGetLastError());
+  SoftPairs A{};
+  A.pu = pu; A.pi = pi; A.ni = ni; A.is64 = idx_bytes == 8;
+  A.L = LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos};
+  A.grad_loss = grad_loss; A.n_user = nu; A.n_item = nit;
+  A.xu = T.user; A.ldu = T.ld;
+  A.xi = ktup ? I.x : T.item; A.ldi = ktup ? d : T.ld;
+  A.ra_u = U.ra; A.wb_u = U.wb; A.ra_i = I.ra; A.wb_i = I.wb;
+  A.gx_u = acc->user; A.gx_i = I.gx; A.g_ra_u = U.g_ra; A.g_wb_u = U.g_wb; A.g_ra_i = I.g_ra; A.g_wb_i = I.g_wb;
+  A.pos_scores = pos_scores; A.neg_scores = neg_scores; A.group_loss = static_cast<float*>(loss_workspace);
+  A.status = status; A.d = d; A.l1 = T.l1;
+  k_soft_pairs<<<grid_for(n_pos), kThreads, 0, st>>>(A);
+  KGREC_CUDA_OK(cudaGetLastError());
+  const int bcap = sm_count() * 2;
+  auto gridb = [&](int64_t rows) { const int64_t g = (rows + kRowBatch - 1) / kRowBatch; return static_cast<int>(g < 1 ? 1 : (g < bcap ? g : bcap)); };
+  k_soft_rows_bwd<<<gridb(max_u), kRowThreads, smem_b, st>>>(T, ktup ? 1 : 0, U, acc->pref, acc->pref_norm);
+  k_soft_rows_bwd<<<gridb(max_i), kRowThreads, smem_b, st>>>(T, ktup ? 1 : 0, I, acc->pref, acc->pref_norm);
+  KGREC_CUDA_OK(cudaGetLastError());
+  const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
+  k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(A.group_loss, A.L, loss);
+  KGREC_CUDA_OK(cudaGetLastError());
+  return KGREC_OK;
+}

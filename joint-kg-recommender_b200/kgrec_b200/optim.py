@@ -53,6 +53,7 @@ class SparseRowOptimizer:
         self.s2 = {k: torch.zeros_like(w[k]) for k in self.names} if self.kind == 2 else {k: None for k in self.names}
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.reg_loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._rows_ws = None          # work buffers of the row-factored soft rec step, allocated on first use
 
     # -- shared tail of every step: marks -> total norm -> update --------------------------------------
     def _seg(self, ids, table, compact=False, remap=None):
@@ -62,16 +63,20 @@ class SparseRowOptimizer:
                             n_remap=remap.numel() if remap is not None else 0,
                             marks=m.data_ptr(), rows=m.numel())
 
-    def _apply(self, segs, tables):
-        """segs: MarkSeg list of this step's id arrays; tables: names of the tables the step's loss reaches."""
+    def _mark(self, segs):
+        """Start a step: bump the epoch and mark the rows the step's id arrays name."""
         m = self.model
-        dev = m.device
+        self.t += 1
+        seg_arr = (_lib.MarkSeg * len(segs))(*segs)
+        _lib.check(_lib.load().kgrec_rows_mark(seg_arr, len(segs), self.t, KF._ptr(m._status_buf(m.device)), KF._stream()))
+        KF.count_launches(1)
+
+    def _update(self, tables):
+        """Finish a step: total norm (clip) and the optimizer update of the marked rows of `tables`."""
+        m = self.model
         lib = _lib.load()
         stream = KF._stream()
         w = m._weights()
-        self.t += 1
-        seg_arr = (_lib.MarkSeg * len(segs))(*segs)
-        _lib.check(lib.kgrec_rows_mark(seg_arr, len(segs), self.t, KF._ptr(m._status_buf(dev)), stream))
         entries = []
         for k in tables:
             mk = self.marks.get(k)
@@ -88,7 +93,12 @@ class SparseRowOptimizer:
         _lib.check(lib.kgrec_rows_update(tab_arr, len(entries), self.t, self.kind, self.lr, self.eps, self.betas[0],
                                          self.betas[1], self.t, self.wd, KF._ptr(self.sqnorm) if use_clip else None,
                                          float(self.clip or 0.0), stream))
-        KF.count_launches(2 + int(use_clip))
+        KF.count_launches(1 + int(use_clip))
+
+    def _apply(self, segs, tables):
+        """segs: MarkSeg list of this step's id arrays; tables: names of the tables the step's loss reaches."""
+        self._mark(segs)
+        self._update(tables)
 
     def _grads(self, names):
         g = _lib.Grads()
@@ -178,11 +188,30 @@ class SparseRowOptimizer:
         if gumbel_u is not None:
             gumbel_u = gumbel_u.to(dev, torch.float32).contiguous()
         seed = m._next_seed() if (m.use_st_gumbel and gumbel_u is None) else 0
-        _lib.check(lib.kgrec_rank_loss_step(
-            C.byref(T), m.MODEL, ptr(pu), ptr(pi), None, ptr(nu), ptr(ni), None, idx_bytes, n_pos, n_neg, bp, kind,
-            float(target), 1.0, ptr(gumbel_u), seed, ptr(pos_s), ptr(neg_s), ptr(out), C.byref(g),
-            None, None, None, ptr(ws), ptr(m._status_buf(dev)), stream))
-        KF.count_launches(2)
+        segs = [self._seg(pu, "user"), self._seg(pi, "item"), self._seg(ni, "item")]
+        if ktup:
+            segs += [self._seg(pi, "ent", remap=m._item2ent), self._seg(ni, "ent", remap=m._item2ent)]
+        self._mark(segs)
+        if self._use_rows_path(n_pos, n_neg, nu, pu):
+            # soft preferences: the [P x d] contractions once per distinct row of the step (csrc/train_rec_rows.cu)
+            if self._rows_ws is None:
+                n_fl = lib.kgrec_rec_rows_workspace_floats(w["user"].shape[0], w["item"].shape[0], m.embedding_size,
+                                                           w["pref"].shape[0], 1 if ktup else 0)
+                self._rows_ws = torch.empty(int(n_fl), dtype=torch.float32, device=dev)
+                first = 1
+            else:
+                first = 0
+            _lib.check(lib.kgrec_rec_rows_step(
+                C.byref(T), m.MODEL, ptr(pu), ptr(pi), ptr(ni), idx_bytes, n_pos, n_neg, bp, kind, float(target), 1.0,
+                ptr(self.marks["user"]), ptr(self.marks["item"]), self.t, ptr(self._rows_ws), first, C.byref(g),
+                ptr(pos_s), ptr(neg_s), ptr(out), ptr(ws), ptr(m._status_buf(dev)), stream))
+            KF.count_launches(8)
+        else:
+            _lib.check(lib.kgrec_rank_loss_step(
+                C.byref(T), m.MODEL, ptr(pu), ptr(pi), None, ptr(nu), ptr(ni), None, idx_bytes, n_pos, n_neg, bp, kind,
+                float(target), 1.0, ptr(gumbel_u), seed, ptr(pos_s), ptr(neg_s), ptr(out), C.byref(g),
+                None, None, None, ptr(ws), ptr(m._status_buf(dev)), stream))
+            KF.count_launches(2)
         if ktup:      # (pref + rel) and (pref_norm + norm) enter the score as sums (jTransUP.py:253-258): equal gradients
             self.acc["rel"].copy_(self.acc["pref"])
             self.acc["norm"].copy_(self.acc["pref_norm"])
@@ -200,8 +229,23 @@ class SparseRowOptimizer:
                 _lib.check(lib.kgrec_reg_norm_rows(ptr(pw), pw.shape[0], d, None, 8, pw.shape[0], 1.0, ptr(self.reg_loss),
                                                    ptr(self.acc["pref"]), None, stream))
                 KF.count_launches(4)
-        segs = [self._seg(pu, "user"), self._seg(pi, "item"), self._seg(ni, "item")]
-        if ktup:
-            segs += [self._seg(pi, "ent", remap=m._item2ent), self._seg(ni, "ent", remap=m._item2ent)]
-        self._apply(segs, names)
+        self._update(names)
         return out, self.reg_loss
+
+    def _use_rows_path(self, n_pos, n_neg, nu, pu):
+        """Row-factored soft step (train_rec_rows.cu) when the step re-uses rows: its per-row kernels cost about one
+        pair-kernel pair per DISTINCT row, its pair kernel about a third of one.  KGREC_REC_ROWS=0 | force overrides."""
+        import os
+        m = self.model
+        env = os.environ.get("KGREC_REC_ROWS", "")
+        d, P = m.embedding_size, m.pref_embeddings.weight.shape[0]
+        ok = (not m.use_st_gumbel) and d % 4 == 0 and d <= 128 and P <= 32 and 1 <= n_neg <= 31
+        if not ok or env == "0":
+            return False
+        # the row path scores negative k of positive j as (pu[j], ni[j, k]): the (u repeated, ni) contract of this
+        # method (what getNegRatings produces); nu itself is not read
+        if env == "force":
+            return True
+        pairs = n_pos * (1 + n_neg)
+        rows = min(m.user_embeddings.weight.shape[0], n_pos) + min(m.item_embeddings.weight.shape[0], pairs)
+        return rows <= 0.6 * pairs

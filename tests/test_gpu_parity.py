@@ -1086,9 +1086,10 @@ def test_sparse_row_optimizer_matches_torch(cls_name, opt_name, steps, clip):
     m1.check_indices()
 
 
-@pytest.mark.parametrize("ktup,gumbel", [(False, False), (False, True), (True, False)])
+@pytest.mark.parametrize("ktup,gumbel,rows_path", [(False, False, False), (False, True, False), (True, False, False),
+                                                   (False, False, True), (True, False, True)])
 @pytest.mark.parametrize("opt_name,steps", [("SGD", 2), ("Adagrad", 3), ("Adam", 1)])
-def test_sparse_row_optimizer_rec_models(ktup, gumbel, opt_name, steps):
+def test_sparse_row_optimizer_rec_models(ktup, gumbel, rows_path, opt_name, steps, monkeypatch):
     """The same for TUP / the rec branch of KTUP (tile kernel in dense-accumulate mode, KTUP's aligned
     entity rows marked through item2ent, rel / norm moved by the pref / pref_norm gradient), with the
     drivers' regularisers (item_recommendation.py:177-180, knowledgable_recommendation.py:343-344)
@@ -1096,9 +1097,13 @@ def test_sparse_row_optimizer_rec_models(ktup, gumbel, opt_name, steps):
     import copy
     import kgrec_b200 as K
     from kgrec_b200.optim import SparseRowOptimizer
+    # rows_path: the row-factored soft step (csrc/train_rec_rows.cu: [P x d] work per distinct row) instead of the pair kernel
+    monkeypatch.setenv("KGREC_REC_ROWS", "force" if rows_path else "0")
     torch.manual_seed(31)
     rng = np.random.RandomState(31)
     d, U, I, E, P, B, lr, clip = 64, 900, 700, 1100, 9, 600, 0.05, 1.5
+    if rows_path:
+        U, I, B = 90, 70, 2500          # heavy row re-use: every user / item many times per step
     if ktup:
         ents = rng.permutation(E)[:I]
         new_map = {i: ((int(ents[i]) if i % 10 < 7 else -1), i) for i in range(I)}
@@ -1145,6 +1150,44 @@ def test_sparse_row_optimizer_rec_models(ktup, gumbel, opt_name, steps):
         assert touched or ktup
         close(p1, p2[n1].detach().cpu().numpy(), rtol=3e-4, atol=5e-5)
     _assert_optimizer_clean(opt)
+    m1.check_indices()
+
+
+@pytest.mark.parametrize("ktup", [False, True])
+@pytest.mark.parametrize("l1", [False, True])
+@pytest.mark.parametrize("loss,n_neg", [("bpr", 1), ("margin", 3)])
+def test_rec_rows_step_matches_pair_kernel(ktup, l1, loss, n_neg, monkeypatch):
+    """The row-factored soft step against the pair (tile) kernel on the same step: scores, per-batch losses and
+    every table after one SGD step (i.e. every accumulated gradient), L1 and L2, BPR and margin, 1 and 3 negatives."""
+    import copy
+    import kgrec_b200 as K
+    from kgrec_b200.optim import SparseRowOptimizer
+    torch.manual_seed(51)
+    rng = np.random.RandomState(51)
+    d, U, I, E, P, B = 100, 120, 150, 400, 20, 3000
+    if ktup:
+        ents = rng.permutation(E)[:I]
+        new_map = {i: ((int(ents[i]) if i % 10 < 7 else -1), i) for i in range(I)}
+        m1 = K.jTransUPModel(l1, d, U, I, E, P, {i: i for i in range(I)}, new_map, False, False)
+    else:
+        m1 = K.TransUPModel(l1, d, U, I, P, False)
+    m2 = copy.deepcopy(m1)
+    g = torch.Generator().manual_seed(4)
+    u = torch.randint(0, U, (B,), generator=g).cuda()
+    pi = torch.randint(0, I, (B,), generator=g).cuda()
+    ni = torch.randint(0, I, (B * n_neg,), generator=g).cuda()
+    un = u.repeat_interleave(n_neg)
+    res = []
+    for m, env in ((m1, "force"), (m2, "0")):
+        monkeypatch.setenv("KGREC_REC_ROWS", env)
+        opt = SparseRowOptimizer(m, optimizer_type="SGD", lr=0.01, clip=None)
+        res.append(opt.step_pairs((u, pi), (un, ni), target=-1.0 if loss == "bpr" else 1.0, loss=loss, batch_pos=512))
+        _assert_optimizer_clean(opt)
+        if env == "force":
+            assert opt._rows_ws is not None
+    close(res[0][0], res[1][0].cpu().numpy(), rtol=2e-4)
+    for (n1, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        close(p1, p2.detach().cpu().numpy(), rtol=3e-4, atol=3e-6, max_outliers=12 if l1 else 0)
     m1.check_indices()
 
 
