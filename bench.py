@@ -367,10 +367,23 @@ def run_ours(args):
         qu4 = torch.arange(4096, device=dev) % 50_000
         ms = timeit(lambda: tm.topk_items(qu4, k=10, soft_catalog=soft_cat), reps=3)
         reg["cfg3_tup_soft_evaluate_top10_4096u_x_50k"] = 4096 * 50_000 / (ms * 1e-3)
-        del tm, soft_cat
+        # the same tables trained with soft preferences through the optimizer: row-factored step vs the pair kernel
+        topt = SparseRowOptimizer(tm, optimizer_type="Adagrad", lr=0.005, clip=5.0)
+
+        def tup_soft_step():
+            topt.step_pairs((tu, ti), (tu, tn), target=-1.0, batch_pos=BATCH, reg=True)
+        soft_rows_ms = timeit(tup_soft_step)
+        os.environ["KGREC_REC_ROWS"] = "0"
+        soft_pairs_ms = timeit(tup_soft_step)
+        os.environ.pop("KGREC_REC_ROWS")
+        del tm, soft_cat, topt
         out["regions"] = reg
         out["train_rec"] = {"tup_st_gumbel": {"ms": tup_ms, "pairs_per_s": 2 * n_pos / (tup_ms * 1e-3), "fma_per_pair": 14000,
-                                              "frac_of_fp32_bound": 2 * n_pos / (tup_ms * 1e-3) * 14000 / FP32_LANE_OPS}}
+                                              "frac_of_fp32_bound": 2 * n_pos / (tup_ms * 1e-3) * 14000 / FP32_LANE_OPS},
+                            "tup_soft_full_step": {"what": "forward + BPR + backward + regularisers + clip + sparse-row Adagrad, 50k users x 50k items, "
+                                                           "%d positives + 1 negative each" % n_pos,
+                                                   "row_factored_ms": soft_rows_ms, "pair_kernel_ms": soft_pairs_ms,
+                                                   "pairs_per_s": 2 * n_pos / (soft_rows_ms * 1e-3)}}
 
     # ---- complete training steps: fused step + global-norm clip + sparse-row optimizer --------------------------------
     if extra:
@@ -433,13 +446,16 @@ def run_ours(args):
             for _ in range(5):
                 kg_step()
         rec_ms, kg_ms = timeit(rec_step, reps=5), timeit(kg_step, reps=5)
+        os.environ["KGREC_REC_ROWS"] = "0"           # A/B: the pair (tile) kernel instead of the row-factored soft step
+        rec_pairs_ms = timeit(rec_step, reps=5)
+        os.environ.pop("KGREC_REC_ROWS")
         cyc_ms = timeit(joint_cycle, reps=3, warm=1)
         units = 5 * 2 * n_pos + 5 * 2 * n_pos            # scored pairs + scored triples per 10-step cycle
         out["joint_train_cfg4"] = {
             "what": "jtransup, joint_ratio 0.5: 5 rec steps (tile kernel + orthogonalLoss + clip + sparse-row Adagrad) then 5 KG steps "
                     "(TransH step kernel with fused regularisers + clip + update) per cycle; %d batches of 1024 positives + 1 negative per step; "
                     "6040 users x 3706 items, 500k entities, R = P = 20" % nb,
-            "rec_step_ms": rec_ms, "kg_step_ms": kg_ms, "cycle_ms": cyc_ms, "scored_pairs_plus_triples_per_s": units / (cyc_ms * 1e-3),
+            "rec_step_ms": rec_ms, "rec_step_pair_kernel_ms": rec_pairs_ms, "kg_step_ms": kg_ms, "cycle_ms": cyc_ms, "scored_pairs_plus_triples_per_s": units / (cyc_ms * 1e-3),
             "rec_pairs_per_s": 2 * n_pos / (rec_ms * 1e-3), "kg_triples_per_s": 2 * n_pos / (kg_ms * 1e-3)}
         del jm, jopt
 

@@ -249,8 +249,9 @@ k_soft_rows_bwd(const kgrec_tables T, const int ktup, const SoftRows S, float* _
   const int d = T.dim, P = T.n_pref, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float* sP = sm;
   float* sN = sP + P * d;
-  float* st = sN + P * d;                    // staging of a batch: per row [zx (P) | gz (P) | G_RA (d) | G_WB (d) | x (d)]
-  const int rs = 2 * P + 3 * d;
+  float* st = sN + P * d;                    // staging of a batch: per row [zx (Pp) | gz (Pp) | G_RA (d) | G_WB (d) | x (d)]
+  const int Pp = (P + 3) & ~3;               // keeps the three d-vectors 16-byte aligned
+  const int rs = 2 * Pp + 3 * d;
   stage_tables(T, ktup, sP, sN);
   const float hf = ktup ? 0.5f : 1.f;
   const bool act = lane * 4 < d;
@@ -302,22 +303,22 @@ k_soft_rows_bwd(const kgrec_tables T, const int ktup, const SoftRows S, float* _
           float4* gp = reinterpret_cast<float4*>(S.gx + row * d) + lane;
           *gp = add4(*gp, gs);
         }
-        reinterpret_cast<float4*>(srow + 2 * P)[lane] = gra;
-        reinterpret_cast<float4*>(srow + 2 * P + d)[lane] = gwb;
-        reinterpret_cast<float4*>(srow + 2 * P + 2 * d)[lane] = x;
+        reinterpret_cast<float4*>(srow + 2 * Pp)[lane] = gra;
+        reinterpret_cast<float4*>(srow + 2 * Pp + d)[lane] = gwb;
+        reinterpret_cast<float4*>(srow + 2 * Pp + 2 * d)[lane] = x;
       }
-      if (lane < P) { srow[lane] = hf * S.zx[row * P + lane]; srow[P + lane] = 0.5f * gz; }
+      if (lane < P) { srow[lane] = hf * S.zx[row * P + lane]; srow[Pp + lane] = 0.5f * gz; }
     }
     __syncthreads();
     // phase B: dP'[k][c] += hf zx_k G_RA[c] + (g_z[k] / 2) x[c];  dN'[k][c] += hf zx_k G_WB[c]
     if (c < d) {
       for (int rr = 0; rr < kRowBatch; ++rr) {
         const float* srow = st + rr * rs;
-        const float gra = srow[2 * P + c], gwb = srow[2 * P + d + c], xv = srow[2 * P + 2 * d + c];
+        const float gra = srow[2 * Pp + c], gwb = srow[2 * Pp + d + c], xv = srow[2 * Pp + 2 * d + c];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
           if (k < KH && k0 + k < P) {
-            const float zk = srow[k0 + k], gk = srow[P + k0 + k];
+            const float zk = srow[k0 + k], gk = srow[Pp + k0 + k];
             accP[k] = fmaf(zk, gra, fmaf(gk, xv, accP[k]));
             accN[k] = fmaf(zk, gwb, accN[k]);
           }
@@ -404,7 +405,7 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   k_rows_compact<<<grid1((nit + 255) / 256), 256, 0, st>>>(marks_item, nit, epoch, list_i, counts + 1);
   KGREC_CUDA_OK(cudaGetLastError());
   const size_t smem_f = static_cast<size_t>(2) * P * d * sizeof(float);
-  const size_t smem_b = (static_cast<size_t>(2) * P * d + static_cast<size_t>(kRowBatch) * (2 * P + 3 * d)) * sizeof(float);
+  const size_t smem_b = (static_cast<size_t>(2) * P * d + static_cast<size_t>(kRowBatch) * (2 * ((P + 3) & ~3) + 3 * d)) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
