@@ -33,13 +33,21 @@ class DevicePrefetcher:
         self.slot = 0
         self.ring = None
 
+    def _fresh(self, host):
+        """New staging buffers.  The caching allocator may hand out memory whose previous owner's kernels are still
+        queued on the CURRENT stream; the copy stream writes these buffers, so it must first catch up with it."""
+        bufs = [torch.empty(x.shape, dtype=x.dtype, device=self.device) for x in host]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.copy_stream.wait_event(ev)
+        return bufs
+
     def _ring_for(self, host):
         sig = (self.key, self.depth, tuple((tuple(x.shape), x.dtype) for x in host))
         ring = DevicePrefetcher._rings.get(sig)
         if ring is None:
             n = self.depth + 1
-            ring = {"bufs": [[torch.empty(x.shape, dtype=x.dtype, device=self.device) for x in host] for _ in range(n)],
-                    "done": [None] * n}
+            ring = {"bufs": [self._fresh(host) for _ in range(n)], "done": [None] * n}
             if len(DevicePrefetcher._rings) > 8:
                 DevicePrefetcher._rings.clear()
             DevicePrefetcher._rings[sig] = ring
@@ -56,7 +64,7 @@ class DevicePrefetcher:
         self.slot = (s + 1) % len(self.ring["bufs"])
         bufs = self.ring["bufs"][s]
         if len(bufs) != len(host) or any(b.shape != x.shape or b.dtype != x.dtype for b, x in zip(bufs, host)):
-            bufs = [torch.empty(x.shape, dtype=x.dtype, device=self.device) for x in host]     # ragged last batch
+            bufs = self._fresh(host)                                                           # ragged last batch
             self.ring["done"][s] = None
         with torch.cuda.stream(self.copy_stream):
             if self.ring["done"][s] is not None:
