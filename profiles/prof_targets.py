@@ -62,6 +62,25 @@ elif target == "tup_step":
     for i in range(reps):
         m.zero_grad(set_to_none=True)
         m.loss_step((u, pi), (u, ni), target=-1.0, batch_pos=B)
+elif target in ("tup_soft_opt", "ktup_soft_opt"):
+    from kgrec_b200.optim import SparseRowOptimizer
+    import numpy as np
+    n = NB * B
+    if target == "tup_soft_opt":
+        with device_init(dev):
+            m = K.TransUPModel(False, D, 50_000, 50_000, 20, False)
+        nu_, ni_ = 50_000, 50_000
+    else:
+        nu_, ni_, ne_ = 6040, 3706, 500_000
+        ents = np.random.RandomState(0).permutation(ne_)[:ni_]
+        new_map = {i: (int(ents[i]) if i % 10 < 7 else -1, i) for i in range(ni_)}
+        with device_init(dev):
+            m = K.jTransUPModel(False, D, nu_, ni_, ne_, 20, {i: i for i in range(ni_)}, new_map, False, False)
+    opt = SparseRowOptimizer(m, "Adagrad", lr=0.005, clip=5.0)
+    u = torch.randint(0, nu_, (n,), generator=g, dtype=torch.int32).to(dev)
+    pi, ni = (torch.randint(0, ni_, (n,), generator=g, dtype=torch.int32).to(dev) for _ in range(2))
+    for i in range(reps):
+        opt.step_pairs((u, pi), (u, ni), target=-1.0, batch_pos=B, reg=True)
 elif target in ("gumbel_eval", "soft_eval_d128"):
     gum = target == "gumbel_eval"
     d = 100 if gum else 128
