@@ -11,8 +11,9 @@
 //   k_soft_pairs       per group (positive + its negatives, one warp): r, w by two adds; a = u - i', s = a.w,
 //                      e = a + r - s w, score, ranking loss, then eps, gx = eps - (eps.w) w, gw = -((eps.w) a + s eps);
 //                      O(d) per pair; gradients leave as atomic row adds: gx -> the rows' direct gradient, eps -> G_RA, gw -> G_WB
-//   k_soft_rows_bwd    per listed row: g_z = hf (G_RA P'^T + G_WB N'^T), row gradient += g_z P' / 2, and the table gradients
-//                      dP' += hf zx^T G_RA + g_z^T x / 2, dN' += hf zx^T G_WB (register tiles over 32-row batches, one flush per CTA)
+//   k_soft_rows_bwd    per listed row: g_z = hf (G_RA P'^T + G_WB N'^T), row gradient += g_z P' / 2
+//   k_soft_rows_tables the table gradients dP' += hf zx^T G_RA + g_z^T x / 2, dN' += hf zx^T G_WB as a [P x n] . [n x d] product over the
+//                      listed rows (a thread owns a column chunk x half of the preferences in registers; one flush per CTA)
 // All of it accumulates into the dense accumulators of the sparse-row optimizer (csrc/optim.cu), which then clips and updates.
 // Same arithmetic as the pair kernel up to re-association; parity: tests/test_gpu_parity.py::test_sparse_row_optimizer_rec_models.
 #include "train_dev.cuh"
@@ -21,7 +22,6 @@ namespace kgrec {
 namespace {
 
 constexpr int kRowThreads = 256;
-constexpr int kRowBatch = 32;         // rows per CTA batch in k_soft_rows_bwd (4 per warp)
 
 __global__ void __launch_bounds__(256)
 k_rows_compact(const int32_t* __restrict__ marks, int64_t rows, int32_t epoch, int32_t* __restrict__ list, int32_t* __restrict__ count) {
@@ -55,84 +55,106 @@ struct SoftRows {                 // one side (users or items) of the rec model
   const int32_t* count;
 };
 
-__device__ __forceinline__ void stage_tables(const kgrec_tables& T, int ktup, float* sP, float* sN) {
-  const int d = T.dim, P = T.n_pref;
-  for (int idx = threadIdx.x; idx < P * d; idx += blockDim.x) {
-    const int k = idx / d, j = idx - k * d;
-    float a = __ldg(T.pref + static_cast<int64_t>(k) * T.ld + j), b = __ldg(T.pref_norm + static_cast<int64_t>(k) * T.ld + j);
-    if (ktup) { a += __ldg(T.rel + static_cast<int64_t>(k) * T.ld + j); b += __ldg(T.norm + static_cast<int64_t>(k) * T.ld + j); }
-    sP[idx] = a;
-    sN[idx] = b;
-  }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ float4 axpy4(float s, const float4& x, const float4& y) {
+  return make_float4(fmaf(s, x.x, y.x), fmaf(s, x.y, y.y), fmaf(s, x.z, y.z), fmaf(s, x.w, y.w));
 }
 
-// P (<= 32) dots of length d between the lane-distributed vector(s) and the table rows in shared memory; lane k gets dot k.
-// v2 / t2 optional second pair (sum of both products).
-__device__ __forceinline__ float dots_to_lanes(const float4& v1, const float* t1, const float4* v2, const float* t2, int P, int d,
-                                               int lane, bool act) {
-  float mine = 0.f;
-  for (int g = 0; g < P; g += 8) {
-    float vals[8];
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      float s = 0.f;
-      if (g + kk < P && act) {
-        const float4 a = *reinterpret_cast<const float4*>(t1 + (g + kk) * d + 4 * lane);
-        s = fmaf(v1.x, a.x, fmaf(v1.y, a.y, fmaf(v1.z, a.z, v1.w * a.w)));
-        if (v2) {
-          const float4 b = *reinterpret_cast<const float4*>(t2 + (g + kk) * d + 4 * lane);
-          s = fmaf(v2->x, b.x, fmaf(v2->y, b.y, fmaf(v2->z, b.z, fmaf(v2->w, b.w, s))));
-        }
+// ---- per-row kernels: a thread owns (row, slice) -- 8 rows x 4 slices of interleaved 16-byte chunks per warp, the tile
+// kernel's mapping: a table chunk is one broadcast LDS.128 feeding 4 FMAs per preference, a dot over d costs two
+// xor-shuffles, nothing is staged per row.  Tables chunk-major in shared memory: chunk c of preference k at [c * PT + k].
+template <int PT>
+__device__ __forceinline__ void stage_tables_cm(const kgrec_tables& T, int ktup, float4* sP, float4* sN) {
+  const int NC = T.dim >> 2, P = T.n_pref;
+  for (int idx = threadIdx.x; idx < PT * NC; idx += blockDim.x) {
+    const int k = idx / NC, c = idx - k * NC;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (k < P) {
+      a = ldg_f4(reinterpret_cast<const float4*>(T.pref + static_cast<int64_t>(k) * T.ld) + c);
+      b = ldg_f4(reinterpret_cast<const float4*>(T.pref_norm + static_cast<int64_t>(k) * T.ld) + c);
+      if (ktup) {
+        const float4 r = ldg_f4(reinterpret_cast<const float4*>(T.rel + static_cast<int64_t>(k) * T.ld) + c);
+        const float4 w = ldg_f4(reinterpret_cast<const float4*>(T.norm + static_cast<int64_t>(k) * T.ld) + c);
+        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+        b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
       }
-      vals[kk] = s;
     }
-    const float r = warp_reduce_scatter8(vals, lane);      // lane l holds dot g + ((l >> 2) & 7)
-#pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-      const float v = __shfl_sync(FULL, r, kk * 4);
-      if (lane == g + kk) mine = v;
-    }
+    sP[c * PT + k] = a;
+    sN[c * PT + k] = b;
   }
-  return mine;
 }
+__device__ __forceinline__ float qsum4(float v) {   // all-reduce over the 4 slices of a row
+  v += __shfl_xor_sync(FULL, v, 8);
+  v += __shfl_xor_sync(FULL, v, 16);
+  return v;
+}
+constexpr int kMaxChunks = 8;        // chunks per slice: d <= 128
 
+template <int PT>
 __global__ void __launch_bounds__(kRowThreads)
 k_soft_rows_fwd(const kgrec_tables T, const int ktup, const SoftRows S) {
   extern __shared__ __align__(16) float sm[];
-  const int d = T.dim, P = T.n_pref, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float* sP = sm;
-  float* sN = sP + P * d;
-  stage_tables(T, ktup, sP, sN);
+  const int d = T.dim, P = T.n_pref, NC = d >> 2, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float4* sP = reinterpret_cast<float4*>(sm);
+  float4* sN = sP + PT * NC;
+  stage_tables_cm<PT>(T, ktup, sP, sN);
   __syncthreads();
   const float hf = ktup ? 0.5f : 1.f;
-  const bool act = lane * 4 < d;
+  const int slot = lane & 7, q = lane >> 3;
   const int n = *S.count;
-  for (int i = blockIdx.x * (kRowThreads / 32) + wid; i < n; i += gridDim.x * (kRowThreads / 32)) {
-    const int64_t row = S.list[i];
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act) {
-      x = ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + lane);
-      if (S.ent) {
-        const int64_t ia = __ldg(S.item2ent + row);
-        const float4 e = ldg_f4(reinterpret_cast<const float4*>(S.ent + ia * T.ld) + lane);
-        x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
-        reinterpret_cast<float4*>(S.x + row * d)[lane] = x;
+  for (int base = blockIdx.x * 64; base < n; base += gridDim.x * 64) {
+    const int i = base + wid * 8 + slot;
+    const bool valid = i < n;
+    const int64_t row = valid ? S.list[i] : 0;
+    float4 x[kMaxChunks];
+    int64_t ia = 0;
+    if (S.ent && valid) ia = __ldg(S.item2ent + row);
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int c = q + 4 * j;
+      x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < NC && valid) {
+        x[j] = ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + c);
+        if (S.ent) {
+          const float4 e = ldg_f4(reinterpret_cast<const float4*>(S.ent + ia * T.ld) + c);
+          x[j].x += e.x; x[j].y += e.y; x[j].z += e.z; x[j].w += e.w;
+          reinterpret_cast<float4*>(S.x + row * d)[c] = x[j];
+        }
       }
     }
-    const float zk = 0.5f * dots_to_lanes(x, sP, nullptr, nullptr, P, d, lane, act);     // lane k: zx_k
-    if (lane < P) S.zx[row * P + lane] = zk;
-    float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), wb = ra;
-    for (int k = 0; k < P; ++k) {
-      const float z = hf * __shfl_sync(FULL, zk, k);
-      if (act) {
-        const float4 p = *reinterpret_cast<const float4*>(sP + k * d + 4 * lane), nn = *reinterpret_cast<const float4*>(sN + k * d + 4 * lane);
-        ra.x = fmaf(z, p.x, ra.x); ra.y = fmaf(z, p.y, ra.y); ra.z = fmaf(z, p.z, ra.z); ra.w = fmaf(z, p.w, ra.w);
-        wb.x = fmaf(z, nn.x, wb.x); wb.y = fmaf(z, nn.y, wb.y); wb.z = fmaf(z, nn.z, wb.z); wb.w = fmaf(z, nn.w, wb.w);
+    float z[PT];
+#pragma unroll
+    for (int k = 0; k < PT; ++k) z[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int c = q + 4 * j;
+      if (c < NC) {
+#pragma unroll
+        for (int k = 0; k < PT; ++k) z[k] += dot4(x[j], sP[c * PT + k]);
       }
     }
-    if (act) {
-      reinterpret_cast<float4*>(S.ra + row * d)[lane] = ra;
-      reinterpret_cast<float4*>(S.wb + row * d)[lane] = wb;
+#pragma unroll
+    for (int k = 0; k < PT; ++k) {
+      z[k] = 0.5f * qsum4(z[k]);
+      if (valid && k < P && (k & 3) == q) S.zx[row * P + k] = z[k];
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int c = q + 4 * j;
+      if (c < NC && valid) {
+        float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), wb = ra;
+#pragma unroll
+        for (int k = 0; k < PT; ++k) {
+          const float zz = hf * z[k];
+          ra = axpy4(zz, sP[c * PT + k], ra);
+          wb = axpy4(zz, sN[c * PT + k], wb);
+        }
+        reinterpret_cast<float4*>(S.ra + row * d)[c] = ra;
+        reinterpret_cast<float4*>(S.wb + row * d)[c] = wb;
+      }
     }
   }
 }
@@ -151,14 +173,6 @@ struct SoftPairs {
   int32_t* status;
   int d, l1;
 };
-
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
-__device__ __forceinline__ float4 axpy4(float s, const float4& x, const float4& y) {
-  return make_float4(fmaf(s, x.x, y.x), fmaf(s, x.y, y.y), fmaf(s, x.z, y.z), fmaf(s, x.w, y.w));
-}
 
 __global__ void __launch_bounds__(kThreads, 4)
 k_soft_pairs(const SoftPairs A) {
@@ -243,98 +257,115 @@ k_soft_pairs(const SoftPairs A) {
   if (bad && A.status) *A.status = 1;
 }
 
+// backward, part a: g_z = hf (G_RA P'^T + G_WB N'^T) -> cb[row] = g_z / 2, and the row gradient += (g_z / 2) P'
+template <int PT>
 __global__ void __launch_bounds__(kRowThreads)
-k_soft_rows_bwd(const kgrec_tables T, const int ktup, const SoftRows S, float* __restrict__ acc_pref, float* __restrict__ acc_pref_norm) {
+k_soft_rows_bwd(const kgrec_tables T, const int ktup, const SoftRows S, float* __restrict__ cb) {
   extern __shared__ __align__(16) float sm[];
-  const int d = T.dim, P = T.n_pref, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float* sP = sm;
-  float* sN = sP + P * d;
-  float* st = sN + P * d;                    // staging of a batch: per row [zx (Pp) | gz (Pp) | G_RA (d) | G_WB (d) | x (d)]
-  const int Pp = (P + 3) & ~3;               // keeps the three d-vectors 16-byte aligned
-  const int rs = 2 * Pp + 3 * d;
-  stage_tables(T, ktup, sP, sN);
-  const float hf = ktup ? 0.5f : 1.f;
-  const bool act = lane * 4 < d;
-  const int n = *S.count;
-  // phase-B ownership: column c, preferences [k0, k0 + KH)
-  const int c = threadIdx.x % 128, half = threadIdx.x / 128;
-  const int KH = (P + 1) / 2, k0 = half * KH;
-  float accP[16], accN[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) { accP[k] = 0.f; accN[k] = 0.f; }
+  const int d = T.dim, P = T.n_pref, NC = d >> 2, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float4* sP = reinterpret_cast<float4*>(sm);
+  float4* sN = sP + PT * NC;
+  stage_tables_cm<PT>(T, ktup, sP, sN);
   __syncthreads();
-  for (int b0 = blockIdx.x * kRowBatch; b0 < n; b0 += gridDim.x * kRowBatch) {
-    // phase A: a warp finishes the row gradients of 4 rows and stages what the table gradients need
-    for (int rr = wid; rr < kRowBatch; rr += kRowThreads / 32) {
-      const int i = b0 + rr;
-      float* srow = st + rr * rs;
-      if (i >= n) {                            // rows past the end contribute zeros
-        for (int t = lane; t < rs; t += 32) srow[t] = 0.f;
-        continue;
+  const float hf = ktup ? 0.5f : 1.f;
+  const int slot = lane & 7, q = lane >> 3;
+  const int n = *S.count;
+  for (int base = blockIdx.x * 64; base < n; base += gridDim.x * 64) {
+    const int i = base + wid * 8 + slot;
+    const bool valid = i < n;
+    const int64_t row = valid ? S.list[i] : 0;
+    float gz[PT];
+#pragma unroll
+    for (int k = 0; k < PT; ++k) gz[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int c = q + 4 * j;
+      if (c < NC && valid) {
+        const float4 gra = ld4(S.g_ra + row * d + 4 * c), gwb = ld4(S.g_wb + row * d + 4 * c);
+#pragma unroll
+        for (int k = 0; k < PT; ++k) gz[k] += dot4(gra, sP[c * PT + k]) + dot4(gwb, sN[c * PT + k]);
       }
-      const int64_t row = S.list[i];
-      float4 gra = make_float4(0.f, 0.f, 0.f, 0.f), gwb = gra, x = gra;
-      if (act) {
-        gra = ld4(S.g_ra + row * d + 4 * lane);
-        gwb = ld4(S.g_wb + row * d + 4 * lane);
-        reinterpret_cast<float4*>(S.g_ra + row * d)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);      // clean for the next step
-        reinterpret_cast<float4*>(S.g_wb + row * d)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        x = S.x ? ld4(S.x + row * d + 4 * lane) : ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + lane);
-      }
-      const float gz = hf * dots_to_lanes(gra, sP, &gwb, sN, P, d, lane, act);        // lane k: g_z[k]
-      float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = 0; k < P; ++k) {
-        const float cz = 0.5f * __shfl_sync(FULL, gz, k);
-        if (act) {
-          const float4 p = *reinterpret_cast<const float4*>(sP + k * d + 4 * lane);
-          gs.x = fmaf(cz, p.x, gs.x); gs.y = fmaf(cz, p.y, gs.y); gs.z = fmaf(cz, p.z, gs.z); gs.w = fmaf(cz, p.w, gs.w);
-        }
-      }
-      if (act) {
-        if (S.acc_table) {                     // KTUP items: direct gradient sits in a work buffer; item and aligned entity both get the sum
-          float4 t = ld4(S.gx + row * d + 4 * lane);
-          reinterpret_cast<float4*>(S.gx + row * d)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < PT; ++k) {
+      gz[k] = 0.5f * hf * qsum4(gz[k]);
+      if (valid && k < P && (k & 3) == q) cb[row * P + k] = gz[k];
+    }
+    int64_t ia = 0;
+    if (S.acc_table && valid) ia = __ldg(S.item2ent + row);
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int c = q + 4 * j;
+      if (c < NC && valid) {
+        float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < PT; ++k) gs = axpy4(gz[k], sP[c * PT + k], gs);
+        if (S.acc_table) {                   // KTUP items: direct gradient from the work buffer; item and aligned entity both get the sum
+          float4 t = ld4(S.gx + row * d + 4 * c);
+          reinterpret_cast<float4*>(S.gx + row * d)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
           t = add4(t, gs);
-          float4* ai = reinterpret_cast<float4*>(S.acc_table + row * d) + lane;
+          float4* ai = reinterpret_cast<float4*>(S.acc_table + row * d) + c;
           *ai = add4(*ai, t);
-          const int64_t ia = __ldg(S.item2ent + row);
-          if (ia != S.n_ent - 1) red_add_f4(S.acc_ent + ia * d + 4 * lane, t.x, t.y, t.z, t.w);    // padding row: no gradient (jTransUP.py:96)
+          if (ia != S.n_ent - 1) red_add_f4(S.acc_ent + ia * d + 4 * c, t.x, t.y, t.z, t.w);     // padding row: no gradient (jTransUP.py:96)
         } else {
-          float4* gp = reinterpret_cast<float4*>(S.gx + row * d) + lane;
+          float4* gp = reinterpret_cast<float4*>(S.gx + row * d) + c;
           *gp = add4(*gp, gs);
         }
-        reinterpret_cast<float4*>(srow + 2 * Pp)[lane] = gra;
-        reinterpret_cast<float4*>(srow + 2 * Pp + d)[lane] = gwb;
-        reinterpret_cast<float4*>(srow + 2 * Pp + 2 * d)[lane] = x;
-      }
-      if (lane < P) { srow[lane] = hf * S.zx[row * P + lane]; srow[Pp + lane] = 0.5f * gz; }
-    }
-    __syncthreads();
-    // phase B: dP'[k][c] += hf zx_k G_RA[c] + (g_z[k] / 2) x[c];  dN'[k][c] += hf zx_k G_WB[c]
-    if (c < d) {
-      for (int rr = 0; rr < kRowBatch; ++rr) {
-        const float* srow = st + rr * rs;
-        const float gra = srow[2 * Pp + c], gwb = srow[2 * Pp + d + c], xv = srow[2 * Pp + 2 * d + c];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          if (k < KH && k0 + k < P) {
-            const float zk = srow[k0 + k], gk = srow[Pp + k0 + k];
-            accP[k] = fmaf(zk, gra, fmaf(gk, xv, accP[k]));
-            accN[k] = fmaf(zk, gwb, accN[k]);
-          }
-        }
       }
     }
-    __syncthreads();
   }
-  if (c < d) {
+}
+
+// backward, part b: the [P, d] table gradients as a [P x n] . [n x d] product over the listed rows:
+//   dP'[k] += sum_rows hf zx[row][k] G_RA[row] + cb[row][k] x[row];   dN'[k] += sum_rows hf zx[row][k] G_WB[row]
+// A thread owns (16-byte column chunk, half of the preferences) in registers over all the rows of its row group.
+template <int PT>
+__global__ void __launch_bounds__(kRowThreads, (PT <= 20 ? 2 : 1))
+k_soft_rows_tables(const kgrec_tables T, const int ktup, const SoftRows S, const float* __restrict__ cb,
+                   float* __restrict__ acc_pref, float* __restrict__ acc_pref_norm) {
+  constexpr int KH = PT / 2;
+  const int d = T.dim, P = T.n_pref, NC = d >> 2;
+  const float hf = ktup ? 0.5f : 1.f;
+  const int items = NC * 2, ngrp = kRowThreads / items;
+  const int grp = threadIdx.x / items, item = threadIdx.x - grp * items;
+  const int jc = item % NC, k0 = (item / NC) * KH;
+  if (grp >= ngrp) return;
+  float4 accP[KH], accN[KH];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      if (k < KH && k0 + k < P) {
-        if (accP[k] != 0.f) atomicAdd(acc_pref + static_cast<int64_t>(k0 + k) * d + c, accP[k]);
-        if (accN[k] != 0.f) atomicAdd(acc_pref_norm + static_cast<int64_t>(k0 + k) * d + c, accN[k]);
+  for (int k = 0; k < KH; ++k) { accP[k] = make_float4(0.f, 0.f, 0.f, 0.f); accN[k] = accP[k]; }
+  const int n = *S.count;
+  for (int i = blockIdx.x * ngrp + grp; i < n; i += gridDim.x * ngrp) {
+    const int64_t row = S.list[i];
+    const float4 gra = ld4(S.g_ra + row * d + 4 * jc), gwb = ld4(S.g_wb + row * d + 4 * jc);
+    const float4 x = S.x ? ld4(S.x + row * d + 4 * jc) : ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + jc);
+#pragma unroll
+    for (int k = 0; k < KH; ++k) {
+      if (k0 + k < P) {
+        const float za = hf * __ldg(S.zx + row * P + k0 + k), zb = __ldg(cb + row * P + k0 + k);
+        accP[k] = axpy4(za, gra, axpy4(zb, x, accP[k]));
+        accN[k] = axpy4(za, gwb, accN[k]);
       }
     }
+  }
+#pragma unroll
+  for (int k = 0; k < KH; ++k) {
+    if (k0 + k < P) {
+      red_add_f4(acc_pref + static_cast<int64_t>(k0 + k) * d + 4 * jc, accP[k].x, accP[k].y, accP[k].z, accP[k].w);
+      red_add_f4(acc_pref_norm + static_cast<int64_t>(k0 + k) * d + 4 * jc, accN[k].x, accN[k].y, accN[k].z, accN[k].w);
+    }
+  }
+}
+
+// the per-row accumulators are clean again for the next step
+__global__ void __launch_bounds__(256)
+k_rows_zero2(const int32_t* __restrict__ list, const int32_t* __restrict__ count, float* __restrict__ a, float* __restrict__ b, int d) {
+  const int n = *count, NC = d >> 2;
+  const int64_t total = static_cast<int64_t>(n) * NC;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = list[t / NC];
+    const int c = static_cast<int>(t % NC);
+    reinterpret_cast<float4*>(a + row * d)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    reinterpret_cast<float4*>(b + row * d)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -345,7 +376,7 @@ using namespace kgrec;
 
 extern "C" int64_t kgrec_rec_rows_workspace_floats(int64_t n_user, int64_t n_item, int32_t dim, int32_t n_pref, int ktup) {
   // per side: ra, wb, g_ra, g_wb [rows, d], zx [rows, P], list [rows] (+1 count); KTUP items: x, gx [rows, d]
-  const int64_t per = 4 * static_cast<int64_t>(dim) + n_pref + 1;
+  const int64_t per = 4 * static_cast<int64_t>(dim) + 2 * n_pref + 2;
   return n_user * per + n_item * (per + (ktup ? 2 * static_cast<int64_t>(dim) : 0)) + 16;
 }
 
@@ -383,6 +414,8 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   I.ra = take(nit * d); I.wb = take(nit * d); I.g_ra = take(nit * d); I.g_wb = take(nit * d); I.zx = take(nit * P);
   float* gx_i_buf = nullptr;
   if (ktup) { I.x = take(nit * d); gx_i_buf = take(nit * d); }
+  float* cb_u = take(nu * P);
+  float* cb_i = take(nit * P);
   int32_t* list_u = reinterpret_cast<int32_t*>(take(nu));
   int32_t* list_i = reinterpret_cast<int32_t*>(take(nit));
   int32_t* counts = reinterpret_cast<int32_t*>(take(4));
@@ -404,18 +437,20 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   k_rows_compact<<<grid1((nu + 255) / 256), 256, 0, st>>>(marks_user, nu, epoch, list_u, counts);
   k_rows_compact<<<grid1((nit + 255) / 256), 256, 0, st>>>(marks_item, nit, epoch, list_i, counts + 1);
   KGREC_CUDA_OK(cudaGetLastError());
-  const size_t smem_f = static_cast<size_t>(2) * P * d * sizeof(float);
-  const size_t smem_b = (static_cast<size_t>(2) * P * d + static_cast<size_t>(kRowBatch) * (2 * ((P + 3) & ~3) + 3 * d)) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    attr_done = true;
-  }
   // rows touched: at most min(rows, ids) per side
   const int64_t max_u = nu < n_pos ? nu : n_pos, max_i = nit < n_pos * (1 + n_neg) ? nit : n_pos * (1 + n_neg);
-  k_soft_rows_fwd<<<grid1((max_u + 7) / 8), kRowThreads, smem_f, st>>>(T, ktup ? 1 : 0, U);
-  k_soft_rows_fwd<<<grid1((max_i + 7) / 8), kRowThreads, smem_f, st>>>(T, ktup ? 1 : 0, I);
+  const int PT = P <= 8 ? 8 : (P <= 20 ? 20 : 32);
+  const size_t smem_t = static_cast<size_t>(2) * PT * (d / 4) * sizeof(float4);
+  const int rcap = sm_count() * 4;
+  auto grid64 = [&](int64_t rows) { const int64_t g = (rows + 63) / 64; return static_cast<int>(g < 1 ? 1 : (g < rcap ? g : rcap)); };
+#define ROWS_FWD(PTV)                                                                                                    \
+  {                                                                                                                      \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_fwd<PTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t))); \
+    k_soft_rows_fwd<PTV><<<grid64(max_u), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, U);                                \
+    k_soft_rows_fwd<PTV><<<grid64(max_i), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, I);                                \
+  }
+  if (PT == 8) ROWS_FWD(8) else if (PT == 20) ROWS_FWD(20) else ROWS_FWD(32)
+#undef ROWS_FWD
   KGREC_CUDA_OK(cudaGetLastError());
   SoftPairs A{};
   A.pu = pu; A.pi = pi; A.ni = ni; A.is64 = idx_bytes == 8;
@@ -429,10 +464,20 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   A.status = status; A.d = d; A.l1 = T.l1;
   k_soft_pairs<<<grid_for(n_pos), kThreads, 0, st>>>(A);
   KGREC_CUDA_OK(cudaGetLastError());
-  const int bcap = sm_count() * 2;
-  auto gridb = [&](int64_t rows) { const int64_t g = (rows + kRowBatch - 1) / kRowBatch; return static_cast<int>(g < 1 ? 1 : (g < bcap ? g : bcap)); };
-  k_soft_rows_bwd<<<gridb(max_u), kRowThreads, smem_b, st>>>(T, ktup ? 1 : 0, U, acc->pref, acc->pref_norm);
-  k_soft_rows_bwd<<<gridb(max_i), kRowThreads, smem_b, st>>>(T, ktup ? 1 : 0, I, acc->pref, acc->pref_norm);
+  const int tcap = sm_count() * 2;
+  auto gridt = [&](int64_t rows) { const int64_t g = (rows + 31) / 32; return static_cast<int>(g < 1 ? 1 : (g < tcap ? g : tcap)); };
+#define ROWS_BWD(PTV)                                                                                                    \
+  {                                                                                                                      \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_bwd<PTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t))); \
+    k_soft_rows_bwd<PTV><<<grid64(max_u), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, U, cb_u);                          \
+    k_soft_rows_bwd<PTV><<<grid64(max_i), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, I, cb_i);                          \
+    k_soft_rows_tables<PTV><<<gridt(max_u), kRowThreads, 0, st>>>(T, ktup ? 1 : 0, U, cb_u, acc->pref, acc->pref_norm);   \
+    k_soft_rows_tables<PTV><<<gridt(max_i), kRowThreads, 0, st>>>(T, ktup ? 1 : 0, I, cb_i, acc->pref, acc->pref_norm);   \
+  }
+  if (PT == 8) ROWS_BWD(8) else if (PT == 20) ROWS_BWD(20) else ROWS_BWD(32)
+#undef ROWS_BWD
+  k_rows_zero2<<<grid1((max_u * (d / 4) + 255) / 256), 256, 0, st>>>(list_u, counts, U.g_ra, U.g_wb, d);
+  k_rows_zero2<<<grid1((max_i * (d / 4) + 255) / 256), 256, 0, st>>>(list_i, counts + 1, I.g_ra, I.g_wb, d);
   KGREC_CUDA_OK(cudaGetLastError());
   const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
   k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(A.group_loss, A.L, loss);
