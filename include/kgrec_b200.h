@@ -310,7 +310,7 @@ int kgrec_rows_update(const kgrec_opt_table* tabs_host, int n_tabs, int32_t epoc
                       float eps, float beta1, float beta2, int64_t step, float weight_decay,
                       const float* sqnorm, float max_norm, kgrec_stream_t stream);
 
-/* ---- row-factored training step of the soft-preference rec models (TUP / KTUP, use_st_gumbel = 0) --------------
+/* ---- row-factored training step of the rec models (TUP / KTUP): soft preferences, or ST-Gumbel with the L2 score ----
  * transUP.py:69-82, 105-115; jTransUP.py:122-161, 250-260.  With raw logits as mixing weights r = RA_u + RA_i and
  * w = WB_u + WB_i with RA_x = hf (x P'^T / 2) P' (WB_x with N'): the [P x d] contractions are done once per DISTINCT
  * row of the step (rows carrying the epoch mark: kgrec_rows_mark must have run on the step's user / item ids with
@@ -319,6 +319,11 @@ int kgrec_rows_update(const kgrec_opt_table* tabs_host, int n_tabs, int32_t epoc
  * (grads->mode 1: user, item, pref, pref_norm [, ent]; the KTUP caller copies pref / pref_norm's to rel / norm);
  * scores and per-batch losses as kgrec_rank_loss_step.  workspace: kgrec_rec_rows_workspace_floats floats, persistent
  * across steps (first_use = 1 on the first call zero-fills its accumulators).  loss_workspace: n_pos floats.
+ * norm_reg_loss (optional, TUP): adds the driver's normLoss over the batch's user rows and cat[pos, neg] item rows
+ * (item_recommendation.py:177-179) -- value to *norm_reg_loss, gradient into the same accumulators -- inside the pair kernel.
+ * tables->use_gumbel = 1 (squared-L2 score only): the arg-max preference per pair from per-row logit halves, dL/dp_k for
+ * every k in O(1) from [P, P] Gram tables, the logit path per distinct row (csrc/train_rec_rows.cu); gumbel_u: optional
+ * explicit uniforms [n_pos * (1 + n_neg), P] (positives first, then negatives), else Philox draws keyed by seed.
  * embedding_size % 4 == 0 and <= 128, preference_total <= 32, n_neg <= 31. */
 int64_t kgrec_rec_rows_workspace_floats(int64_t n_user, int64_t n_item, int32_t dim, int32_t n_pref, int ktup);
 int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const void* pu, const void* pi, const void* ni,
@@ -326,7 +331,8 @@ int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const void* pu, c
                         float margin_or_target, float grad_loss, const int32_t* marks_user,
                         const int32_t* marks_item, int32_t epoch, float* workspace, int32_t first_use,
                         const kgrec_grads* acc, float* pos_scores, float* neg_scores, float* loss,
-                        void* loss_workspace, int32_t* status, kgrec_stream_t stream);
+                        void* loss_workspace, float* norm_reg_loss, const float* gumbel_u, uint64_t seed,
+                        int32_t* status, kgrec_stream_t stream);
 
 /* ---- the drivers' recommendation-side regularisers (utils/loss.py:18-23) -------------------------
  * item_recommendation.py:177-180: normLoss(user rows) + normLoss(item rows of cat[pos, neg]) +

@@ -172,6 +172,10 @@ struct SoftPairs {
   float *pos_scores, *neg_scores, *group_loss;
   int32_t* status;
   int d, l1;
+  // optional: the driver's normLoss over the batch's user rows and cat[pos, neg] item rows (item_recommendation.py:177-179),
+  // value added to *reg_loss, gradient 2 x folded into the rows' direct gradient (TUP; the rows are in registers here)
+  float* reg_loss;
+  float reg_scale;
 };
 
 __global__ void __launch_bounds__(kThreads, 4)
@@ -197,6 +201,10 @@ k_soft_pairs(const SoftPairs A) {
       rau = ld4(A.ra_u + iu * d + 4 * lane);
       wbu = ld4(A.wb_u + iu * d + 4 * lane);
     }
+    float reg_sum = 0.f, my_n2 = 0.f;
+    const bool reg = A.reg_loss != nullptr;
+    const float n2u = reg ? warp_sum(dot4(u, u)) : 0.f;
+    if (reg && n2u > 1.f) reg_sum += n2u - 1.f;
     // pass 1: scores (lane m keeps member m's score and s = a.w)
     float my_score = 0.f, my_s = 0.f;
     for (int m = 0; m <= K; ++m) {
@@ -210,8 +218,11 @@ k_soft_pairs(const SoftPairs A) {
       const float4 a = sub4(u, x);
       const float s = warp_sum(dot4(a, w));
       const float4 e = axpy4(-s, w, add4(a, r));
-      const float sc = warp_sum(dist_term(e.x, A.l1) + dist_term(e.y, A.l1) + dist_term(e.z, A.l1) + dist_term(e.w, A.l1));
-      if (lane == m) { my_score = sc; my_s = s; }
+      float sc = dist_term(e.x, A.l1) + dist_term(e.y, A.l1) + dist_term(e.z, A.l1) + dist_term(e.w, A.l1);
+      float n2x = reg ? dot4(x, x) : 0.f;
+      if (reg) warp_sum2(sc, n2x); else sc = warp_sum(sc);
+      if (reg && n2x > 1.f) reg_sum += n2x - 1.f;
+      if (lane == m) { my_score = sc; my_s = s; my_n2 = n2x; }
     }
     const float sp = __shfl_sync(FULL, my_score, 0);
     // ranking loss of the group and its derivative (utils/loss.py:8-16, 29-31)
@@ -226,7 +237,8 @@ k_soft_pairs(const SoftPairs A) {
     float4 gu = z4, gra = z4, gwb = z4;
     for (int m = 0; m <= K; ++m) {
       const float g = __shfl_sync(FULL, my_g, m);
-      if (g == 0.f) continue;                                     // warp-uniform (inactive hinge)
+      const bool regx = reg && __shfl_sync(FULL, my_n2, m) > 1.f;
+      if (g == 0.f && !regx) continue;                            // warp-uniform (inactive hinge, row inside the unit ball)
       const int64_t id = __shfl_sync(FULL, idm, m);
       const float s = __shfl_sync(FULL, my_s, m);
       float4 x = z4, r = z4, w = z4;
@@ -242,12 +254,16 @@ k_soft_pairs(const SoftPairs A) {
       const float4 gx = axpy4(-ew, w, eps);                                       // eps - (eps.w) w
       const float4 gw = make_float4(-fmaf(ew, a.x, s * eps.x), -fmaf(ew, a.y, s * eps.y), -fmaf(ew, a.z, s * eps.z), -fmaf(ew, a.w, s * eps.w));
       gu = add4(gu, gx); gra = add4(gra, eps); gwb = add4(gwb, gw);
+      float4 gxi = make_float4(-gx.x, -gx.y, -gx.z, -gx.w);
+      if (regx) gxi = axpy4(2.f * A.reg_scale, x, gxi);
       if (act) {
-        red_add_f4(A.gx_i + id * d + 4 * lane, -gx.x, -gx.y, -gx.z, -gx.w);
+        red_add_f4(A.gx_i + id * d + 4 * lane, gxi.x, gxi.y, gxi.z, gxi.w);
         red_add_f4(A.g_ra_i + id * d + 4 * lane, eps.x, eps.y, eps.z, eps.w);
         red_add_f4(A.g_wb_i + id * d + 4 * lane, gw.x, gw.y, gw.z, gw.w);
       }
     }
+    if (reg && n2u > 1.f) gu = axpy4(2.f * A.reg_scale, u, gu);
+    if (reg && lane == 0 && reg_sum != 0.f) atomicAdd(A.reg_loss, A.reg_scale * reg_sum);
     if (act) {
       red_add_f4(A.gx_u + iu * d + 4 * lane, gu.x, gu.y, gu.z, gu.w);
       red_add_f4(A.g_ra_u + iu * d + 4 * lane, gra.x, gra.y, gra.z, gra.w);
@@ -369,6 +385,319 @@ k_rows_zero2(const int32_t* __restrict__ list, const int32_t* __restrict__ count
   }
 }
 
+// =====================================================================================================================
+// ST-Gumbel preferences, squared-L2 score (use_st_gumbel = 1, L1_flag = 0): transUP.py:143-170.
+// The forward picks ONE preference per pair, k* = arg-max_k z_k + g_k with z = (u + i') P'^T / 2 = A_u + A_i, so r = hf P'_k*,
+// w = hf N'_k* are table rows and s = a.w = hf (CN_u[k*] - CN_i[k*]) with CN_x = x N'^T.  The straight-through backward needs
+// dL/dp_k = hf (eps . P'_k + gw . N'_k) for EVERY k; with eps = 2 g e (L2) and e = a + r - s w these dots are O(1) from the
+// per-row A / CN and the [P, P] Gram tables PP = P' P'^T, NP = N' P'^T, NN = N' N'^T:
+//     eps . P'_k = 2 g (2 (A_u - A_i)[k] + hf PP[k*][k] - s hf NP[k*][k])
+//     eps . N'_k = 2 g ((CN_u - CN_i)[k] + hf NP[k][k*] - s hf NN[k*][k])
+//     gp_k = hf (eps . P'_k - ew (CN_u - CN_i)[k] - s eps . N'_k),      gz = y (gp - <y, gp>),  y = softmax(z + g)
+// (lane k of the warp handles preference k).  What is left per pair is O(d): e, gx = eps - ew w, gw, the one-hot table rows
+// dP'_k* += hf eps, dN'_k* += hf gw (shared-memory accumulators per CTA).  The logit path -- row gradient += (gz / 2) P',
+// dP' += (gz / 2)^T (u + i') -- is linear in the rows and done per DISTINCT row from GZ_x = sum of the row's gz.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256)
+k_gumbel_gram(const kgrec_tables T, const int ktup, float* __restrict__ gram) {      // gram: [3][P][P] = PP | NP | NN
+  const int d = T.dim, P = T.n_pref, lane = threadIdx.x & 31;
+  const int wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wq >= P * P) return;
+  const int j = wq / P, k = wq - j * P;
+  float pp = 0.f, np = 0.f, nn = 0.f;
+  for (int t = lane; t < d; t += 32) {
+    float pj = __ldg(T.pref + static_cast<int64_t>(j) * T.ld + t), pk = __ldg(T.pref + static_cast<int64_t>(k) * T.ld + t);
+    float nj = __ldg(T.pref_norm + static_cast<int64_t>(j) * T.ld + t), nk = __ldg(T.pref_norm + static_cast<int64_t>(k) * T.ld + t);
+    if (ktup) {
+      pj += __ldg(T.rel + static_cast<int64_t>(j) * T.ld + t); pk += __ldg(T.rel + static_cast<int64_t>(k) * T.ld + t);
+      nj += __ldg(T.norm + static_cast<int64_t>(j) * T.ld + t); nk += __ldg(T.norm + static_cast<int64_t>(k) * T.ld + t);
+    }
+    pp = fmaf(pj, pk, pp); np = fmaf(nj, pk, np); nn = fmaf(nj, nk, nn);
+  }
+  warp_sum2(pp, np);
+  nn = warp_sum(nn);
+  if (lane == 0) { gram[wq] = pp; gram[P * P + wq] = np; gram[2 * P * P + wq] = nn; }
+}
+
+struct GumbelRows {
+  const float* table; const float* ent; const int32_t* item2ent; int64_t n_ent;
+  float* x;                        // KTUP items: effective rows
+  float *a, *cn;                   // [rows, P] logit halves x.P'_k / 2 and normal dots x.N'_k
+  float *gz;                       // [rows, P] accumulated logit gradients, zeroed again by the backward
+  float *cb;                       // [rows, P] gz / 2 for the table-gradient product
+  float* gx; float *acc_table, *acc_ent;
+  const int32_t* list; const int32_t* count;
+};
+
+template <int PT>
+__global__ void __launch_bounds__(kRowThreads)
+k_gumbel_rows_fwd(const kgrec_tables T, const int ktup, const GumbelRows S) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = T.dim, P = T.n_pref, NC = d >> 2, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float4* sP = reinterpret_cast<float4*>(sm);
+  float4* sN = sP + PT * NC;
+  stage_tables_cm<PT>(T, ktup, sP, sN);
+  __syncthreads();
+  const int slot = lane & 7, q = lane >> 3;
+  const int n = *S.count;
+  for (int base = blockIdx.x * 64; base < n; base += gridDim.x * 64) {
+    const int i = base + wid * 8 + slot;
+    const bool valid = i < n;
+    const int64_t row = valid ? S.list[i] : 0;
+    int64_t ia = 0;
+    if (S.ent && valid) ia = __ldg(S.item2ent + row);
+    float za[PT], zc[PT];
+#pragma unroll
+    for (int k = 0; k < PT; ++k) { za[k] = 0.f; zc[k] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int c = q + 4 * j;
+      if (c < NC && valid) {
+        float4 x = ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + c);
+        if (S.ent) {
+          x = add4(x, ldg_f4(reinterpret_cast<const float4*>(S.ent + ia * T.ld) + c));
+          reinterpret_cast<float4*>(S.x + row * d)[c] = x;
+        }
+#pragma unroll
+        for (int k = 0; k < PT; ++k) { za[k] += dot4(x, sP[c * PT + k]); zc[k] += dot4(x, sN[c * PT + k]); }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PT; ++k) {
+      const float a = 0.5f * qsum4(za[k]), c = qsum4(zc[k]);
+      if (valid && k < P && (k & 3) == q) { S.a[row * P + k] = a; S.cn[row * P + k] = c; }
+    }
+  }
+}
+
+struct GumbelPairs {
+  const void *pu, *pi, *ni;
+  int is64;
+  LossCfg L;
+  float grad_loss;
+  int64_t n_user, n_item;
+  const float *xu, *xi; int64_t ldu, ldi;
+  const float *a_u, *cn_u, *a_i, *cn_i;
+  float *gx_u, *gx_i, *gz_u, *gz_i;
+  float *acc_pref, *acc_pref_norm;
+  const float* gram;                 // [3][P][P]
+  const float* gumbel_u; uint64_t seed;
+  float *pos_scores, *neg_scores, *group_loss;
+  int32_t* status;
+  kgrec_tables T; int ktup;
+};
+
+__global__ void __launch_bounds__(kThreads, 3)
+k_gumbel_pairs(const GumbelPairs A) {
+  extern __shared__ __align__(16) float sm[];
+  const kgrec_tables& T = A.T;
+  const int d = T.dim, P = T.n_pref, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float* sR = sm;                    // [P][d] hf P'
+  float* sW = sR + P * d;            // [P][d] hf N'
+  float* sDP = sW + P * d;           // [P][d] one-hot table gradients of this CTA
+  float* sDN = sDP + P * d;
+  float* sG = sDN + P * d;           // [3][P][P]
+  const float hf = A.ktup ? 0.5f : 1.f;
+  for (int idx = threadIdx.x; idx < P * d; idx += blockDim.x) {
+    const int k = idx / d, j = idx - k * d;
+    float a = __ldg(T.pref + static_cast<int64_t>(k) * T.ld + j), b = __ldg(T.pref_norm + static_cast<int64_t>(k) * T.ld + j);
+    if (A.ktup) { a += __ldg(T.rel + static_cast<int64_t>(k) * T.ld + j); b += __ldg(T.norm + static_cast<int64_t>(k) * T.ld + j); }
+    sR[idx] = hf * a; sW[idx] = hf * b; sDP[idx] = 0.f; sDN[idx] = 0.f;
+  }
+  for (int idx = threadIdx.x; idx < 3 * P * P; idx += blockDim.x) sG[idx] = __ldg(A.gram + idx);
+  __syncthreads();
+  const int K = A.L.n_neg;
+  const bool act = lane * 4 < d, kl = lane < P;
+  const int64_t n_pos = A.L.n_pos;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  bool bad = false;
+  // z + noise of member m of group j in lane k, and its arg-max (lowest index among equals, as torch.max)
+  auto logits = [&](int64_t pid, float au, float ax) {
+    float v = -INFINITY;
+    if (kl) {
+      const float nz = A.gumbel_u ? gumbel_from_uniform(__ldg(A.gumbel_u + pid * P + lane))
+                                  : gumbel_fast(philox_uniform_bits(A.seed, static_cast<uint64_t>(pid), static_cast<uint32_t>(lane)));
+      v = au + ax + nz;
+    }
+    return v;
+  };
+  auto argmax = [&](float v) {
+    float bv = v; int bk = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(FULL, bv, o);
+      const int ok = __shfl_xor_sync(FULL, bk, o);
+      if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
+    }
+    return bk;
+  };
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + wid; j < n_pos; j += static_cast<int64_t>(gridDim.x) * kWarpsPerCta) {
+    int64_t iu = load_idx(A.pu, j, A.is64);
+    if (static_cast<uint64_t>(iu) >= static_cast<uint64_t>(A.n_user)) { bad = true; iu = 0; }
+    int64_t idm = 0;
+    if (lane <= K) {
+      idm = lane == 0 ? load_idx(A.pi, j, A.is64) : load_idx(A.ni, j * K + lane - 1, A.is64);
+      if (static_cast<uint64_t>(idm) >= static_cast<uint64_t>(A.n_item)) { bad = true; idm = 0; }
+    }
+    float4 u = z4;
+    if (act) u = ld4(A.xu + iu * A.ldu + 4 * lane);
+    const float au = kl ? __ldg(A.a_u + iu * P + lane) : 0.f, cu = kl ? __ldg(A.cn_u + iu * P + lane) : 0.f;
+    // pass 1: scores; lane m keeps member m's score, k* and s
+    float my_score = 0.f, my_s = 0.f;
+    int my_k = 0;
+    for (int m = 0; m <= K; ++m) {
+      const int64_t id = __shfl_sync(FULL, idm, m);
+      const int64_t pid = m == 0 ? j : n_pos + j * K + (m - 1);
+      const float ax = kl ? __ldg(A.a_i + id * P + lane) : 0.f, cx = kl ? __ldg(A.cn_i + id * P + lane) : 0.f;
+      const int ks = argmax(logits(pid, au, ax));
+      const float s = hf * __shfl_sync(FULL, cu - cx, ks);
+      float4 x = z4, r = z4, w = z4;
+      if (act) { x = ld4(A.xi + id * A.ldi + 4 * lane); r = ld4(sR + ks * d + 4 * lane); w = ld4(sW + ks * d + 4 * lane); }
+      const float4 e = axpy4(-s, w, add4(sub4(u, x), r));
+      const float sc = warp_sum(dot4(e, e));
+      if (lane == m) { my_score = sc; my_s = s; my_k = ks; }
+    }
+    const float sp = __shfl_sync(FULL, my_score, 0);
+    const float up = A.grad_loss * loss_batch_scale(A.L, j);
+    float term = 0.f, dp = 0.f;
+    if (lane >= 1 && lane <= K) { term = loss_term(A.L, sp, my_score); dp = loss_dpos(A.L, sp, my_score); }
+    const float lsum = warp_sum(term), dsum = warp_sum(dp);
+    const float my_g = lane == 0 ? dsum * up : -dp * up;
+    if (lane == 0) { A.pos_scores[j] = sp; A.group_loss[j] = lsum; }
+    if (lane >= 1 && lane <= K) A.neg_scores[j * K + lane - 1] = my_score;
+    // pass 2: gradients
+    float4 gu = z4;
+    float gzu = 0.f;
+    for (int m = 0; m <= K; ++m) {
+      const float g = __shfl_sync(FULL, my_g, m);
+      if (g == 0.f) continue;
+      const int64_t id = __shfl_sync(FULL, idm, m);
+      const int64_t pid = m == 0 ? j : n_pos + j * K + (m - 1);
+      const int ks = __shfl_sync(FULL, my_k, m);
+      const float s = __shfl_sync(FULL, my_s, m);
+      const float ax = kl ? __ldg(A.a_i + id * P + lane) : 0.f, cx = kl ? __ldg(A.cn_i + id * P + lane) : 0.f;
+      const float v = logits(pid, au, ax);
+      const float mx = warp_max(v);
+      const float ex = kl ? __expf(v - mx) : 0.f;
+      const float y = ex / warp_sum(ex);
+      float4 x = z4, r = z4, w = z4;
+      if (act) { x = ld4(A.xi + id * A.ldi + 4 * lane); r = ld4(sR + ks * d + 4 * lane); w = ld4(sW + ks * d + 4 * lane); }
+      const float4 a = sub4(u, x);
+      const float4 e = axpy4(-s, w, add4(a, r));
+      const float g2 = 2.f * g;
+      const float4 eps = make_float4(g2 * e.x, g2 * e.y, g2 * e.z, g2 * e.w);
+      const float ew = warp_sum(dot4(eps, w));
+      const float4 gx = axpy4(-ew, w, eps);
+      const float4 gw = make_float4(-fmaf(ew, a.x, s * eps.x), -fmaf(ew, a.y, s * eps.y), -fmaf(ew, a.z, s * eps.z), -fmaf(ew, a.w, s * eps.w));
+      // dL/dp_k for every k (lane k), O(1) from the Gram tables
+      float gz = 0.f;
+      {
+        float gp = 0.f;
+        if (kl) {
+          const float da = au - ax, dc = cu - cx;
+          const float epk = g2 * (2.f * da + hf * sG[ks * P + lane] - s * hf * sG[P * P + ks * P + lane]);
+          const float enk = g2 * (dc + hf * sG[P * P + lane * P + ks] - s * hf * sG[2 * P * P + ks * P + lane]);
+          gp = hf * (epk - ew * dc - s * enk);
+        }
+        const float yg = warp_sum(y * gp);
+        gz = y * (gp - yg);
+      }
+      gu = add4(gu, gx);
+      gzu += gz;
+      if (act) {
+        red_add_f4(A.gx_i + id * d + 4 * lane, -gx.x, -gx.y, -gx.z, -gx.w);
+        float* dp_row = sDP + ks * d + 4 * lane;
+        float* dn_row = sDN + ks * d + 4 * lane;
+        atomicAdd(dp_row, hf * eps.x); atomicAdd(dp_row + 1, hf * eps.y); atomicAdd(dp_row + 2, hf * eps.z); atomicAdd(dp_row + 3, hf * eps.w);
+        atomicAdd(dn_row, hf * gw.x); atomicAdd(dn_row + 1, hf * gw.y); atomicAdd(dn_row + 2, hf * gw.z); atomicAdd(dn_row + 3, hf * gw.w);
+      }
+      if (kl) atomicAdd(A.gz_i + id * P + lane, gz);
+    }
+    if (act) red_add_f4(A.gx_u + iu * d + 4 * lane, gu.x, gu.y, gu.z, gu.w);
+    if (kl && gzu != 0.f) atomicAdd(A.gz_u + iu * P + lane, gzu);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < P * d; idx += blockDim.x) {
+    if (sDP[idx] != 0.f) atomicAdd(A.acc_pref + idx, sDP[idx]);
+    if (sDN[idx] != 0.f) atomicAdd(A.acc_pref_norm + idx, sDN[idx]);
+  }
+  if (bad && A.status) *A.status = 1;
+}
+
+// backward per row: cb = GZ / 2 (GZ cleared), row gradient += cb P'
+template <int PT>
+__global__ void __launch_bounds__(kRowThreads)
+k_gumbel_rows_bwd(const kgrec_tables T, const int ktup, const GumbelRows S) {
+  extern __shared__ __align__(16) float sm[];
+  const int d = T.dim, P = T.n_pref, NC = d >> 2, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float4* sP = reinterpret_cast<float4*>(sm);
+  float4* sN = sP + PT * NC;
+  stage_tables_cm<PT>(T, ktup, sP, sN);
+  __syncthreads();
+  const int slot = lane & 7, q = lane >> 3;
+  const int n = *S.count;
+  for (int base = blockIdx.x * 64; base < n; base += gridDim.x * 64) {
+    const int i = base + wid * 8 + slot;
+    const bool valid = i < n;
+    const int64_t row = valid ? S.list[i] : 0;
+    float gz[PT];
+#pragma unroll
+    for (int k = 0; k < PT; ++k) gz[k] = (valid && k < P) ? 0.5f * S.gz[row * P + k] : 0.f;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < PT; ++k)
+      if (valid && k < P && (k & 3) == q) { S.cb[row * P + k] = gz[k]; S.gz[row * P + k] = 0.f; }
+    int64_t ia = 0;
+    if (S.acc_table && valid) ia = __ldg(S.item2ent + row);
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+      const int c = q + 4 * j;
+      if (c < NC && valid) {
+        float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < PT; ++k) gs = axpy4(gz[k], sP[c * PT + k], gs);
+        if (S.acc_table) {
+          float4 t = ld4(S.gx + row * d + 4 * c);
+          reinterpret_cast<float4*>(S.gx + row * d)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          t = add4(t, gs);
+          float4* ai = reinterpret_cast<float4*>(S.acc_table + row * d) + c;
+          *ai = add4(*ai, t);
+          if (ia != S.n_ent - 1) red_add_f4(S.acc_ent + ia * d + 4 * c, t.x, t.y, t.z, t.w);
+        } else {
+          float4* gp = reinterpret_cast<float4*>(S.gx + row * d) + c;
+          *gp = add4(*gp, gs);
+        }
+      }
+    }
+  }
+}
+
+// dP'[k] += sum_rows cb[row][k] x[row]
+template <int PT>
+__global__ void __launch_bounds__(kRowThreads, 2)
+k_gumbel_rows_tables(const kgrec_tables T, const GumbelRows S, float* __restrict__ acc_pref) {
+  constexpr int KH = PT / 2;
+  const int d = T.dim, P = T.n_pref, NC = d >> 2;
+  const int items = NC * 2, ngrp = kRowThreads / items;
+  const int grp = threadIdx.x / items, item = threadIdx.x - grp * items;
+  const int jc = item % NC, k0 = (item / NC) * KH;
+  if (grp >= ngrp) return;
+  float4 accP[KH];
+#pragma unroll
+  for (int k = 0; k < KH; ++k) accP[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n = *S.count;
+  for (int i = blockIdx.x * ngrp + grp; i < n; i += gridDim.x * ngrp) {
+    const int64_t row = S.list[i];
+    const float4 x = S.x ? ld4(S.x + row * d + 4 * jc) : ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + jc);
+#pragma unroll
+    for (int k = 0; k < KH; ++k)
+      if (k0 + k < P) accP[k] = axpy4(__ldg(S.cb + row * P + k0 + k), x, accP[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < KH; ++k)
+    if (k0 + k < P) red_add_f4(acc_pref + static_cast<int64_t>(k0 + k) * d + 4 * jc, accP[k].x, accP[k].y, accP[k].z, accP[k].w);
+}
+
 }  // namespace
 }  // namespace kgrec
 
@@ -377,19 +706,20 @@ using namespace kgrec;
 extern "C" int64_t kgrec_rec_rows_workspace_floats(int64_t n_user, int64_t n_item, int32_t dim, int32_t n_pref, int ktup) {
   // per side: ra, wb, g_ra, g_wb [rows, d], zx [rows, P], list [rows] (+1 count); KTUP items: x, gx [rows, d]
   const int64_t per = 4 * static_cast<int64_t>(dim) + 2 * n_pref + 2;
-  return n_user * per + n_item * (per + (ktup ? 2 * static_cast<int64_t>(dim) : 0)) + 16;
+  return n_user * per + n_item * (per + (ktup ? 2 * static_cast<int64_t>(dim) : 0)) + 3 * static_cast<int64_t>(n_pref) * n_pref + 64;
 }
 
 extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const void* pu, const void* pi, const void* ni, int idx_bytes,
                                    int64_t n_pos, int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
                                    float grad_loss, const int32_t* marks_user, const int32_t* marks_item, int32_t epoch,
                                    float* workspace, int32_t first_use, const kgrec_grads* acc, float* pos_scores,
-                                   float* neg_scores, float* loss, void* loss_workspace, int32_t* status, kgrec_stream_t stream) {
+                                   float* neg_scores, float* loss, void* loss_workspace, float* norm_reg_loss,
+                                   const float* gumbel_u, uint64_t seed, int32_t* status, kgrec_stream_t stream) {
   if (!tables || (model != KGREC_TUP && model != KGREC_KTUP)) { set_error("rec_rows_step: TUP / KTUP"); return KGREC_ERR_INVALID; }
   const kgrec_tables& T = *tables;
   const int d = T.dim, P = T.n_pref;
   const bool ktup = model == KGREC_KTUP;
-  if (T.use_gumbel) { set_error("rec_rows_step is the soft-preference path (use_st_gumbel = 0)"); return KGREC_ERR_UNSUPPORTED; }
+  if (T.use_gumbel && T.l1) { set_error("rec_rows_step with use_st_gumbel is built for the squared-L2 score (L1_flag = 0)"); return KGREC_ERR_UNSUPPORTED; }
   if (d <= 0 || d > 128 || d % 4 || T.ld != d || P <= 0 || P > 32 || n_neg < 1 || n_neg > 31) {
     set_error("rec_rows_step: embedding_size %% 4 == 0 and <= 128, contiguous tables, preference_total <= 32, 1..31 negatives per positive");
     return KGREC_ERR_UNSUPPORTED;
@@ -407,9 +737,78 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   // carve the workspace
   float* w = workspace;
   auto take = [&](int64_t n) { float* p = w; w += (n + 3) & ~static_cast<int64_t>(3); return p; };
+  const int64_t nu = T.n_user, nit = T.n_item;
+  const int cap = sm_count() * 8;
+  auto grid1 = [&](int64_t units) { const int64_t g = units < 1 ? 1 : units; return static_cast<int>(g < cap ? g : cap); };
+  // rows touched: at most min(rows, ids) per side
+  const int64_t max_u = nu < n_pos ? nu : n_pos, max_i = nit < n_pos * (1 + n_neg) ? nit : n_pos * (1 + n_neg);
+  const int PT = P <= 8 ? 8 : (P <= 20 ? 20 : 32);
+  const size_t smem_t = static_cast<size_t>(2) * PT * (d / 4) * sizeof(float4);
+  const int rcap = sm_count() * 4;
+  auto grid64 = [&](int64_t rows) { const int64_t g = (rows + 63) / 64; return static_cast<int>(g < 1 ? 1 : (g < rcap ? g : rcap)); };
+  const int tcap = sm_count() * 2;
+  auto gridt = [&](int64_t rows) { const int64_t g = (rows + 31) / 32; return static_cast<int>(g < 1 ? 1 : (g < tcap ? g : tcap)); };
+  const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
+  if (T.use_gumbel) {
+    if (norm_reg_loss) { set_error("rec_rows_step: the fused row-norm regulariser goes with the soft path"); return KGREC_ERR_UNSUPPORTED; }
+    GumbelRows GU{}, GI{};
+    GU.table = T.user; GI.table = T.item;
+    GU.a = take(nu * P); GU.cn = take(nu * P); GU.gz = take(nu * P); GU.cb = take(nu * P);
+    GI.a = take(nit * P); GI.cn = take(nit * P); GI.gz = take(nit * P); GI.cb = take(nit * P);
+    float* gxb = nullptr;
+    if (ktup) { GI.x = take(nit * d); gxb = take(nit * d); }
+    int32_t* gl_u = reinterpret_cast<int32_t*>(take(nu));
+    int32_t* gl_i = reinterpret_cast<int32_t*>(take(nit));
+    int32_t* gcnt = reinterpret_cast<int32_t*>(take(4));
+    float* gram = take(3 * static_cast<int64_t>(P) * P);
+    if (first_use) {
+      KGREC_CUDA_OK(cudaMemsetAsync(GU.gz, 0, sizeof(float) * nu * P, st));
+      KGREC_CUDA_OK(cudaMemsetAsync(GI.gz, 0, sizeof(float) * nit * P, st));
+      if (ktup) KGREC_CUDA_OK(cudaMemsetAsync(gxb, 0, sizeof(float) * nit * d, st));
+    }
+    KGREC_CUDA_OK(cudaMemsetAsync(gcnt, 0, 4 * sizeof(int32_t), st));
+    GU.list = gl_u; GU.count = gcnt; GI.list = gl_i; GI.count = gcnt + 1;
+    GU.gx = acc->user;
+    if (ktup) { GI.ent = T.ent; GI.item2ent = T.item2ent; GI.n_ent = T.n_ent; GI.gx = gxb; GI.acc_table = acc->item; GI.acc_ent = acc->ent; }
+    else GI.gx = acc->item;
+    k_rows_compact<<<grid1((nu + 255) / 256), 256, 0, st>>>(marks_user, nu, epoch, gl_u, gcnt);
+    k_rows_compact<<<grid1((nit + 255) / 256), 256, 0, st>>>(marks_item, nit, epoch, gl_i, gcnt + 1);
+    k_gumbel_gram<<<(P * P * 32 + 255) / 256, 256, 0, st>>>(T, ktup ? 1 : 0, gram);
+    KGREC_CUDA_OK(cudaGetLastError());
+    GumbelPairs A{};
+    A.pu = pu; A.pi = pi; A.ni = ni; A.is64 = idx_bytes == 8;
+    A.L = LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos};
+    A.grad_loss = grad_loss; A.n_user = nu; A.n_item = nit;
+    A.xu = T.user; A.ldu = T.ld; A.xi = ktup ? GI.x : T.item; A.ldi = ktup ? d : T.ld;
+    A.a_u = GU.a; A.cn_u = GU.cn; A.a_i = GI.a; A.cn_i = GI.cn;
+    A.gx_u = acc->user; A.gx_i = GI.gx; A.gz_u = GU.gz; A.gz_i = GI.gz;
+    A.acc_pref = acc->pref; A.acc_pref_norm = acc->pref_norm; A.gram = gram; A.gumbel_u = gumbel_u; A.seed = seed;
+    A.pos_scores = pos_scores; A.neg_scores = neg_scores; A.group_loss = static_cast<float*>(loss_workspace);
+    A.status = status; A.T = T; A.ktup = ktup ? 1 : 0;
+    const size_t smem_p = (static_cast<size_t>(4) * P * d + 3 * static_cast<size_t>(P) * P) * sizeof(float);
+    KGREC_CUDA_OK(cudaFuncSetAttribute(k_gumbel_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_p)));
+    const int64_t pg = (n_pos + kWarpsPerCta - 1) / kWarpsPerCta, pcap = static_cast<int64_t>(sm_count()) * 3;
+#define GROWS(PTV)                                                                                                       \
+  {                                                                                                                      \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(k_gumbel_rows_fwd<PTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t))); \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(k_gumbel_rows_bwd<PTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t))); \
+    k_gumbel_rows_fwd<PTV><<<grid64(max_u), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, GU);                             \
+    k_gumbel_rows_fwd<PTV><<<grid64(max_i), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, GI);                             \
+    k_gumbel_pairs<<<static_cast<int>(pg < pcap ? pg : pcap), kThreads, smem_p, st>>>(A);                                \
+    k_gumbel_rows_bwd<PTV><<<grid64(max_u), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, GU);                             \
+    k_gumbel_rows_bwd<PTV><<<grid64(max_i), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, GI);                             \
+    k_gumbel_rows_tables<PTV><<<gridt(max_u), kRowThreads, 0, st>>>(T, GU, acc->pref);                                   \
+    k_gumbel_rows_tables<PTV><<<gridt(max_i), kRowThreads, 0, st>>>(T, GI, acc->pref);                                   \
+  }
+    if (PT == 8) GROWS(8) else if (PT == 20) GROWS(20) else GROWS(32)
+#undef GROWS
+    KGREC_CUDA_OK(cudaGetLastError());
+    k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(A.group_loss, A.L, loss);
+    KGREC_CUDA_OK(cudaGetLastError());
+    return KGREC_OK;
+  }
   SoftRows U{}, I{};
   U.table = T.user; I.table = T.item;
-  const int64_t nu = T.n_user, nit = T.n_item;
   U.ra = take(nu * d); U.wb = take(nu * d); U.g_ra = take(nu * d); U.g_wb = take(nu * d); U.zx = take(nu * P);
   I.ra = take(nit * d); I.wb = take(nit * d); I.g_ra = take(nit * d); I.g_wb = take(nit * d); I.zx = take(nit * P);
   float* gx_i_buf = nullptr;
@@ -432,17 +831,9 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   } else {
     I.gx = acc->item;
   }
-  const int cap = sm_count() * 8;
-  auto grid1 = [&](int64_t units) { const int64_t g = units < 1 ? 1 : units; return static_cast<int>(g < cap ? g : cap); };
   k_rows_compact<<<grid1((nu + 255) / 256), 256, 0, st>>>(marks_user, nu, epoch, list_u, counts);
   k_rows_compact<<<grid1((nit + 255) / 256), 256, 0, st>>>(marks_item, nit, epoch, list_i, counts + 1);
   KGREC_CUDA_OK(cudaGetLastError());
-  // rows touched: at most min(rows, ids) per side
-  const int64_t max_u = nu < n_pos ? nu : n_pos, max_i = nit < n_pos * (1 + n_neg) ? nit : n_pos * (1 + n_neg);
-  const int PT = P <= 8 ? 8 : (P <= 20 ? 20 : 32);
-  const size_t smem_t = static_cast<size_t>(2) * PT * (d / 4) * sizeof(float4);
-  const int rcap = sm_count() * 4;
-  auto grid64 = [&](int64_t rows) { const int64_t g = (rows + 63) / 64; return static_cast<int>(g < 1 ? 1 : (g < rcap ? g : rcap)); };
 #define ROWS_FWD(PTV)                                                                                                    \
   {                                                                                                                      \
     KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_fwd<PTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t))); \
@@ -462,10 +853,10 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   A.gx_u = acc->user; A.gx_i = I.gx; A.g_ra_u = U.g_ra; A.g_wb_u = U.g_wb; A.g_ra_i = I.g_ra; A.g_wb_i = I.g_wb;
   A.pos_scores = pos_scores; A.neg_scores = neg_scores; A.group_loss = static_cast<float*>(loss_workspace);
   A.status = status; A.d = d; A.l1 = T.l1;
+  A.reg_loss = norm_reg_loss; A.reg_scale = 1.f;
+  if (norm_reg_loss && ktup) { set_error("rec_rows_step: the row-norm regulariser is the TUP driver's (item_recommendation.py:177-179)"); return KGREC_ERR_UNSUPPORTED; }
   k_soft_pairs<<<grid_for(n_pos), kThreads, 0, st>>>(A);
   KGREC_CUDA_OK(cudaGetLastError());
-  const int tcap = sm_count() * 2;
-  auto gridt = [&](int64_t rows) { const int64_t g = (rows + 31) / 32; return static_cast<int>(g < 1 ? 1 : (g < tcap ? g : tcap)); };
 #define ROWS_BWD(PTV)                                                                                                    \
   {                                                                                                                      \
     KGREC_CUDA_OK(cudaFuncSetAttribute(k_soft_rows_bwd<PTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t))); \
@@ -479,7 +870,6 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   k_rows_zero2<<<grid1((max_u * (d / 4) + 255) / 256), 256, 0, st>>>(list_u, counts, U.g_ra, U.g_wb, d);
   k_rows_zero2<<<grid1((max_i * (d / 4) + 255) / 256), 256, 0, st>>>(list_i, counts + 1, I.g_ra, I.g_wb, d);
   KGREC_CUDA_OK(cudaGetLastError());
-  const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
   k_batch_loss<<<static_cast<unsigned>(n_batches), 256, 0, st>>>(A.group_loss, A.L, loss);
   KGREC_CUDA_OK(cudaGetLastError());
   return KGREC_OK;

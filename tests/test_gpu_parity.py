@@ -1087,7 +1087,7 @@ def test_sparse_row_optimizer_matches_torch(cls_name, opt_name, steps, clip):
 
 
 @pytest.mark.parametrize("ktup,gumbel,rows_path", [(False, False, False), (False, True, False), (True, False, False),
-                                                   (False, False, True), (True, False, True)])
+                                                   (False, False, True), (True, False, True), (False, True, True), (True, True, True)])
 @pytest.mark.parametrize("opt_name,steps", [("SGD", 2), ("Adagrad", 3), ("Adam", 1)])
 def test_sparse_row_optimizer_rec_models(ktup, gumbel, rows_path, opt_name, steps, monkeypatch):
     """The same for TUP / the rec branch of KTUP (tile kernel in dense-accumulate mode, KTUP's aligned
@@ -1154,11 +1154,12 @@ def test_sparse_row_optimizer_rec_models(ktup, gumbel, rows_path, opt_name, step
 
 
 @pytest.mark.parametrize("ktup", [False, True])
-@pytest.mark.parametrize("l1", [False, True])
+@pytest.mark.parametrize("l1,gumbel", [(False, False), (True, False), (False, True)])
 @pytest.mark.parametrize("loss,n_neg", [("bpr", 1), ("margin", 3)])
-def test_rec_rows_step_matches_pair_kernel(ktup, l1, loss, n_neg, monkeypatch):
-    """The row-factored soft step against the pair (tile) kernel on the same step: scores, per-batch losses and
-    every table after one SGD step (i.e. every accumulated gradient), L1 and L2, BPR and margin, 1 and 3 negatives."""
+def test_rec_rows_step_matches_pair_kernel(ktup, l1, gumbel, loss, n_neg, monkeypatch):
+    """The row-factored step (soft preferences, L1 and L2; ST-Gumbel with the L2 score, explicit noise) against the pair
+    (tile) kernel on the same step: scores, per-batch losses and every table after one SGD step (i.e. every
+    accumulated gradient), BPR and margin, 1 and 3 negatives."""
     import copy
     import kgrec_b200 as K
     from kgrec_b200.optim import SparseRowOptimizer
@@ -1168,20 +1169,22 @@ def test_rec_rows_step_matches_pair_kernel(ktup, l1, loss, n_neg, monkeypatch):
     if ktup:
         ents = rng.permutation(E)[:I]
         new_map = {i: ((int(ents[i]) if i % 10 < 7 else -1), i) for i in range(I)}
-        m1 = K.jTransUPModel(l1, d, U, I, E, P, {i: i for i in range(I)}, new_map, False, False)
+        m1 = K.jTransUPModel(l1, d, U, I, E, P, {i: i for i in range(I)}, new_map, False, gumbel)
     else:
-        m1 = K.TransUPModel(l1, d, U, I, P, False)
+        m1 = K.TransUPModel(l1, d, U, I, P, gumbel)
     m2 = copy.deepcopy(m1)
     g = torch.Generator().manual_seed(4)
     u = torch.randint(0, U, (B,), generator=g).cuda()
     pi = torch.randint(0, I, (B,), generator=g).cuda()
     ni = torch.randint(0, I, (B * n_neg,), generator=g).cuda()
     un = u.repeat_interleave(n_neg)
+    noise = torch.rand(B * (1 + n_neg), P, generator=g).cuda() if gumbel else None
     res = []
     for m, env in ((m1, "force"), (m2, "0")):
         monkeypatch.setenv("KGREC_REC_ROWS", env)
         opt = SparseRowOptimizer(m, optimizer_type="SGD", lr=0.01, clip=None)
-        res.append(opt.step_pairs((u, pi), (un, ni), target=-1.0 if loss == "bpr" else 1.0, loss=loss, batch_pos=512))
+        res.append(opt.step_pairs((u, pi), (un, ni), target=-1.0 if loss == "bpr" else 1.0, loss=loss, batch_pos=512,
+                                  gumbel_u=noise))
         _assert_optimizer_clean(opt)
         if env == "force":
             assert opt._rows_ws is not None
