@@ -357,6 +357,16 @@ def run_ours(args):
             tm.loss_step((tu, ti), (tu, tn), target=-1.0, batch_pos=BATCH)
         tup_ms = timeit(tup_step)
         reg["cfg3_tup_gumbel_forward_backward"] = 2 * n_pos / (tup_ms * 1e-3)
+        # the whole training step through the optimizer: row-factored ST-Gumbel step vs the pair kernel
+        gopt = SparseRowOptimizer(tm, optimizer_type="Adagrad", lr=0.005, clip=5.0)
+
+        def tup_gumbel_full():
+            gopt.step_pairs((tu, ti), (tu, tn), target=-1.0, batch_pos=BATCH, reg=True)
+        gum_rows_ms = timeit(tup_gumbel_full)
+        os.environ["KGREC_REC_ROWS"] = "0"
+        gum_pairs_ms = timeit(tup_gumbel_full)
+        os.environ.pop("KGREC_REC_ROWS")
+        del gopt
         qu = torch.arange(4096, device=dev) % 50_000
         gcat = tm.gumbel_catalog()                    # augmented item rows, built once per table state
         ms = timeit(lambda: tm.topk_items(qu, k=10, soft_catalog=gcat), reps=3)
@@ -380,6 +390,10 @@ def run_ours(args):
         out["regions"] = reg
         out["train_rec"] = {"tup_st_gumbel": {"ms": tup_ms, "pairs_per_s": 2 * n_pos / (tup_ms * 1e-3), "fma_per_pair": 14000,
                                               "frac_of_fp32_bound": 2 * n_pos / (tup_ms * 1e-3) * 14000 / FP32_LANE_OPS},
+                            "tup_st_gumbel_full_step": {"what": "configs[2]: forward + BPR + backward + regularisers + clip + sparse-row Adagrad, "
+                                                                "ST-Gumbel, L2, 50k users x 50k items, %d positives + 1 negative each" % n_pos,
+                                                        "row_factored_ms": gum_rows_ms, "pair_kernel_ms": gum_pairs_ms,
+                                                        "pairs_per_s": 2 * n_pos / (gum_rows_ms * 1e-3)},
                             "tup_soft_full_step": {"what": "forward + BPR + backward + regularisers + clip + sparse-row Adagrad, 50k users x 50k items, "
                                                            "%d positives + 1 negative each" % n_pos,
                                                    "row_factored_ms": soft_rows_ms, "pair_kernel_ms": soft_pairs_ms,
