@@ -62,13 +62,13 @@ elif target == "tup_step":
     for i in range(reps):
         m.zero_grad(set_to_none=True)
         m.loss_step((u, pi), (u, ni), target=-1.0, batch_pos=B)
-elif target in ("tup_soft_opt", "ktup_soft_opt"):
+elif target in ("tup_soft_opt", "ktup_soft_opt", "tup_gumbel_opt"):
     from kgrec_b200.optim import SparseRowOptimizer
     import numpy as np
     n = NB * B
-    if target == "tup_soft_opt":
+    if target in ("tup_soft_opt", "tup_gumbel_opt"):
         with device_init(dev):
-            m = K.TransUPModel(False, D, 50_000, 50_000, 20, False)
+            m = K.TransUPModel(False, D, 50_000, 50_000, 20, target == "tup_gumbel_opt")
         nu_, ni_ = 50_000, 50_000
     else:
         nu_, ni_, ne_ = 6040, 3706, 500_000
