@@ -299,6 +299,19 @@ __device__ __forceinline__ uint32_t philox_uniform_bits(uint64_t seed, uint64_t 
   }
   return c0;
 }
+// all four words of one Philox4x32-10 block (counter = (ctr, blk, 0x4b47), key = seed)
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr, uint32_t blk) {
+  uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = blk, c3 = 0x4b47u;
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
 __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t pair, uint32_t k) {
   return static_cast<float>(philox_uniform_bits(seed, pair, k) >> 8) * (1.0f / 16777216.0f);  // [0,1)
 }

@@ -497,6 +497,7 @@ k_gumbel_pairs(const GumbelPairs A) {
   float* sDP = sW + P * d;           // [P][d] one-hot table gradients of this CTA
   float* sDN = sDP + P * d;
   float* sG = sDN + P * d;           // [3][P][P]
+  float* sV = sG + 3 * P * P + (threadIdx.x >> 5) * (A.L.n_neg + 1) * P;     // this warp's z + noise of every member: [K + 1][P]
   const float hf = A.ktup ? 0.5f : 1.f;
   for (int idx = threadIdx.x; idx < P * d; idx += blockDim.x) {
     const int k = idx / d, j = idx - k * d;
@@ -511,25 +512,16 @@ k_gumbel_pairs(const GumbelPairs A) {
   const int64_t n_pos = A.L.n_pos;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   bool bad = false;
-  // z + noise of member m of group j in lane k, and its arg-max (lowest index among equals, as torch.max)
-  auto logits = [&](int64_t pid, float au, float ax) {
-    float v = -INFINITY;
-    if (kl) {
-      const float nz = A.gumbel_u ? gumbel_from_uniform(__ldg(A.gumbel_u + pid * P + lane))
-                                  : gumbel_fast(philox_uniform_bits(A.seed, static_cast<uint64_t>(pid), static_cast<uint32_t>(lane)));
-      v = au + ax + nz;
-    }
-    return v;
+  // arg-max over the lanes < P with the lowest index among equals (torch.max): one integer redux on the order-preserving
+  // key of the float, one ballot
+  auto okey = [&](float v) {
+    const uint32_t b = __float_as_uint(v);
+    return kl ? ((b & 0x80000000u) ? ~b : (b | 0x80000000u)) : 0u;
   };
   auto argmax = [&](float v) {
-    float bv = v; int bk = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(FULL, bv, o);
-      const int ok = __shfl_xor_sync(FULL, bk, o);
-      if (ov > bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-    }
-    return bk;
+    const uint32_t key = okey(v);
+    const uint32_t mx = __reduce_max_sync(FULL, key);
+    return __ffs(__ballot_sync(FULL, key == mx)) - 1;
   };
   for (int64_t j = static_cast<int64_t>(blockIdx.x) * kWarpsPerCta + wid; j < n_pos; j += static_cast<int64_t>(gridDim.x) * kWarpsPerCta) {
     int64_t iu = load_idx(A.pu, j, A.is64);
@@ -542,14 +534,34 @@ k_gumbel_pairs(const GumbelPairs A) {
     float4 u = z4;
     if (act) u = ld4(A.xu + iu * A.ldu + 4 * lane);
     const float au = kl ? __ldg(A.a_u + iu * P + lane) : 0.f, cu = kl ? __ldg(A.cn_u + iu * P + lane) : 0.f;
+    // Gumbel noise of the whole group, [K + 1][P]: explicit uniforms (parity runs), or ONE Philox block per four values
+    // (all members at once: a Philox call is a warp-wide instruction stream, so it is spent on the group, not per member)
+    __syncwarp();
+    if (A.gumbel_u) {
+      for (int m = 0; m <= K; ++m) {
+        const int64_t pid = m == 0 ? j : n_pos + j * K + (m - 1);
+        if (kl) sV[m * P + lane] = gumbel_from_uniform(__ldg(A.gumbel_u + pid * P + lane));
+      }
+    } else {
+      const int n_vals = (K + 1) * P;
+      for (int b = lane; 4 * b < n_vals; b += 32) {
+        const uint4 r = philox4(A.seed, static_cast<uint64_t>(j), static_cast<uint32_t>(b));
+        const uint32_t w4[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (4 * b + t < n_vals) sV[4 * b + t] = gumbel_fast(w4[t]);
+      }
+    }
+    __syncwarp();
     // pass 1: scores; lane m keeps member m's score, k* and s
     float my_score = 0.f, my_s = 0.f;
     int my_k = 0;
     for (int m = 0; m <= K; ++m) {
       const int64_t id = __shfl_sync(FULL, idm, m);
-      const int64_t pid = m == 0 ? j : n_pos + j * K + (m - 1);
       const float ax = kl ? __ldg(A.a_i + id * P + lane) : 0.f, cx = kl ? __ldg(A.cn_i + id * P + lane) : 0.f;
-      const int ks = argmax(logits(pid, au, ax));
+      float v = 0.f;
+      if (kl) { v = au + ax + sV[m * P + lane]; sV[m * P + lane] = v; }          // z + noise, kept for the backward
+      const int ks = argmax(v);
       const float s = hf * __shfl_sync(FULL, cu - cx, ks);
       float4 x = z4, r = z4, w = z4;
       if (act) { x = ld4(A.xi + id * A.ldi + 4 * lane); r = ld4(sR + ks * d + 4 * lane); w = ld4(sW + ks * d + 4 * lane); }
@@ -572,12 +584,11 @@ k_gumbel_pairs(const GumbelPairs A) {
       const float g = __shfl_sync(FULL, my_g, m);
       if (g == 0.f) continue;
       const int64_t id = __shfl_sync(FULL, idm, m);
-      const int64_t pid = m == 0 ? j : n_pos + j * K + (m - 1);
       const int ks = __shfl_sync(FULL, my_k, m);
       const float s = __shfl_sync(FULL, my_s, m);
       const float ax = kl ? __ldg(A.a_i + id * P + lane) : 0.f, cx = kl ? __ldg(A.cn_i + id * P + lane) : 0.f;
-      const float v = logits(pid, au, ax);
-      const float mx = warp_max(v);
+      const float v = kl ? sV[m * P + lane] : 0.f;
+      const float mx = __shfl_sync(FULL, v, ks);                  // the arg-max's value
       const float ex = kl ? __expf(v - mx) : 0.f;
       const float y = ex / warp_sum(ex);
       float4 x = z4, r = z4, w = z4;
@@ -785,7 +796,8 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
     A.acc_pref = acc->pref; A.acc_pref_norm = acc->pref_norm; A.gram = gram; A.gumbel_u = gumbel_u; A.seed = seed;
     A.pos_scores = pos_scores; A.neg_scores = neg_scores; A.group_loss = static_cast<float*>(loss_workspace);
     A.status = status; A.T = T; A.ktup = ktup ? 1 : 0;
-    const size_t smem_p = (static_cast<size_t>(4) * P * d + 3 * static_cast<size_t>(P) * P) * sizeof(float);
+    const size_t smem_p = (static_cast<size_t>(4) * P * d + 3 * static_cast<size_t>(P) * P +
+                           static_cast<size_t>(kWarpsPerCta) * (n_neg + 1) * P) * sizeof(float);
     KGREC_CUDA_OK(cudaFuncSetAttribute(k_gumbel_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_p)));
     const int64_t pg = (n_pos + kWarpsPerCta - 1) / kWarpsPerCta, pcap = static_cast<int64_t>(sm_count()) * 3;
 #define GROWS(PTV)                                                                                                       \
