@@ -394,9 +394,13 @@ k_rows_zero2(const int32_t* __restrict__ list, const int32_t* __restrict__ count
 //     eps . P'_k = 2 g (2 (A_u - A_i)[k] + hf PP[k*][k] - s hf NP[k*][k])
 //     eps . N'_k = 2 g ((CN_u - CN_i)[k] + hf NP[k][k*] - s hf NN[k*][k])
 //     gp_k = hf (eps . P'_k - ew (CN_u - CN_i)[k] - s eps . N'_k),      gz = y (gp - <y, gp>),  y = softmax(z + g)
-// (lane k of the warp handles preference k).  What is left per pair is O(d): e, gx = eps - ew w, gw, the one-hot table rows
-// dP'_k* += hf eps, dN'_k* += hf gw (shared-memory accumulators per CTA).  The logit path -- row gradient += (gz / 2) P',
-// dP' += (gz / 2)^T (u + i') -- is linear in the rows and done per DISTINCT row from GZ_x = sum of the row's gz.
+// (lane k of the warp handles preference k).  What is left per pair is O(d): e and gx = eps - ew w.  The one-hot table rows
+// dP'_k* += hf eps and dN'_k* += hf gw are NOT added per pair (d-wide atomics on P hot rows): with c1 = 2 g hf, t2 = hf ew + s c1
+//     hf eps = c1 (u - i' + R_k* - s W_k*),      hf gw = -t2 (u - i') - s c1 R_k* + s^2 c1 W_k*
+// so a pair adds four scalars to per-row coefficient vectors (CK_u[k*] += c1, CK_i[k*] -= c1, DK_u[k*] -= t2, DK_i[k*] += t2)
+// and four to per-preference sums (S1..S4[k*] in shared memory), and the d-wide work happens once per DISTINCT row.  The logit
+// path -- row gradient += (gz / 2) P', dP' += (gz / 2)^T (u + i') -- is linear in the rows too (GZ_x = sum of the row's gz):
+//     dP' += (GZ / 2 + CK)^T X + S1 R - S2 W,        dN' += DK^T X + S3 R + S4 W        (R = hf P', W = hf N').
 // =====================================================================================================================
 __global__ void __launch_bounds__(256)
 k_gumbel_gram(const kgrec_tables T, const int ktup, float* __restrict__ gram) {      // gram: [3][P][P] = PP | NP | NN
@@ -424,7 +428,8 @@ struct GumbelRows {
   float* x;                        // KTUP items: effective rows
   float *a, *cn;                   // [rows, P] logit halves x.P'_k / 2 and normal dots x.N'_k
   float *gz;                       // [rows, P] accumulated logit gradients, zeroed again by the backward
-  float *cb;                       // [rows, P] gz / 2 for the table-gradient product
+  float *ck;                       // [rows, 2, P] coefficients of this row in the one-hot table gradients dP'_k*, dN'_k* (zeroed likewise)
+  float *cb, *cbn;                 // [rows, P] gz / 2 + ck and dk: the coefficient matrices of the table-gradient products
   float* gx; float *acc_table, *acc_ent;
   const int32_t* list; const int32_t* count;
 };
@@ -478,7 +483,7 @@ struct GumbelPairs {
   int64_t n_user, n_item;
   const float *xu, *xi; int64_t ldu, ldi;
   const float *a_u, *cn_u, *a_i, *cn_i;
-  float *gx_u, *gx_i, *gz_u, *gz_i;
+  float *gx_u, *gx_i, *gz_u, *gz_i, *ck_u, *ck_i;
   float *acc_pref, *acc_pref_norm;
   const float* gram;                 // [3][P][P]
   const float* gumbel_u; uint64_t seed;
@@ -487,24 +492,24 @@ struct GumbelPairs {
   kgrec_tables T; int ktup;
 };
 
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 k_gumbel_pairs(const GumbelPairs A) {
   extern __shared__ __align__(16) float sm[];
   const kgrec_tables& T = A.T;
   const int d = T.dim, P = T.n_pref, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float* sR = sm;                    // [P][d] hf P'
   float* sW = sR + P * d;            // [P][d] hf N'
-  float* sDP = sW + P * d;           // [P][d] one-hot table gradients of this CTA
-  float* sDN = sDP + P * d;
-  float* sG = sDN + P * d;           // [3][P][P]
+  float* sS = sW + P * d;            // [4][P] per-preference sums S1..S4 of this CTA
+  float* sG = sS + 4 * P;            // [3][P][P]
   float* sV = sG + 3 * P * P + (threadIdx.x >> 5) * (A.L.n_neg + 1) * P;     // this warp's z + noise of every member: [K + 1][P]
   const float hf = A.ktup ? 0.5f : 1.f;
   for (int idx = threadIdx.x; idx < P * d; idx += blockDim.x) {
     const int k = idx / d, j = idx - k * d;
     float a = __ldg(T.pref + static_cast<int64_t>(k) * T.ld + j), b = __ldg(T.pref_norm + static_cast<int64_t>(k) * T.ld + j);
     if (A.ktup) { a += __ldg(T.rel + static_cast<int64_t>(k) * T.ld + j); b += __ldg(T.norm + static_cast<int64_t>(k) * T.ld + j); }
-    sR[idx] = hf * a; sW[idx] = hf * b; sDP[idx] = 0.f; sDN[idx] = 0.f;
+    sR[idx] = hf * a; sW[idx] = hf * b;
   }
+  for (int idx = threadIdx.x; idx < 4 * P; idx += blockDim.x) sS[idx] = 0.f;
   for (int idx = threadIdx.x; idx < 3 * P * P; idx += blockDim.x) sG[idx] = __ldg(A.gram + idx);
   __syncthreads();
   const int K = A.L.n_neg;
@@ -590,7 +595,7 @@ k_gumbel_pairs(const GumbelPairs A) {
       const float v = kl ? sV[m * P + lane] : 0.f;
       const float mx = __shfl_sync(FULL, v, ks);                  // the arg-max's value
       const float ex = kl ? __expf(v - mx) : 0.f;
-      const float y = ex / warp_sum(ex);
+      const float y = __fdividef(ex, warp_sum(ex));
       float4 x = z4, r = z4, w = z4;
       if (act) { x = ld4(A.xi + id * A.ldi + 4 * lane); r = ld4(sR + ks * d + 4 * lane); w = ld4(sW + ks * d + 4 * lane); }
       const float4 a = sub4(u, x);
@@ -599,7 +604,6 @@ k_gumbel_pairs(const GumbelPairs A) {
       const float4 eps = make_float4(g2 * e.x, g2 * e.y, g2 * e.z, g2 * e.w);
       const float ew = warp_sum(dot4(eps, w));
       const float4 gx = axpy4(-ew, w, eps);
-      const float4 gw = make_float4(-fmaf(ew, a.x, s * eps.x), -fmaf(ew, a.y, s * eps.y), -fmaf(ew, a.z, s * eps.z), -fmaf(ew, a.w, s * eps.w));
       // dL/dp_k for every k (lane k), O(1) from the Gram tables
       float gz = 0.f;
       {
@@ -615,12 +619,15 @@ k_gumbel_pairs(const GumbelPairs A) {
       }
       gu = add4(gu, gx);
       gzu += gz;
-      if (act) {
-        red_add_f4(A.gx_i + id * d + 4 * lane, -gx.x, -gx.y, -gx.z, -gx.w);
-        float* dp_row = sDP + ks * d + 4 * lane;
-        float* dn_row = sDN + ks * d + 4 * lane;
-        atomicAdd(dp_row, hf * eps.x); atomicAdd(dp_row + 1, hf * eps.y); atomicAdd(dp_row + 2, hf * eps.z); atomicAdd(dp_row + 3, hf * eps.w);
-        atomicAdd(dn_row, hf * gw.x); atomicAdd(dn_row + 1, hf * gw.y); atomicAdd(dn_row + 2, hf * gw.z); atomicAdd(dn_row + 3, hf * gw.w);
+      if (act) red_add_f4(A.gx_i + id * d + 4 * lane, -gx.x, -gx.y, -gx.z, -gx.w);
+      if (lane < 4) {   // one-hot table gradients: eight scalars instead of two d-wide rows (lanes 0/1: user ck/dk, 2/3: item)
+        const float c1 = g2 * hf, t2 = fmaf(hf, ew, s * c1);
+        const bool usr = lane < 2, isd = lane & 1;
+        float* row = usr ? A.ck_u + iu * 2 * P : A.ck_i + id * 2 * P;
+        const float v = isd ? t2 : c1;
+        atomicAdd(row + (isd ? P : 0) + ks, (usr != isd) ? v : -v);      // ck_u += c1, dk_u -= t2, ck_i -= c1, dk_i += t2
+        const float sv = lane == 0 ? c1 : (lane == 1 ? c1 * s : (lane == 2 ? -s * c1 : s * s * c1));
+        atomicAdd(sS + lane * P + ks, sv);
       }
       if (kl) atomicAdd(A.gz_i + id * P + lane, gz);
     }
@@ -628,14 +635,17 @@ k_gumbel_pairs(const GumbelPairs A) {
     if (kl && gzu != 0.f) atomicAdd(A.gz_u + iu * P + lane, gzu);
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < P * d; idx += blockDim.x) {
-    if (sDP[idx] != 0.f) atomicAdd(A.acc_pref + idx, sDP[idx]);
-    if (sDN[idx] != 0.f) atomicAdd(A.acc_pref_norm + idx, sDN[idx]);
+  for (int idx = threadIdx.x; idx < P * d; idx += blockDim.x) {        // this CTA's share of S1 R - S2 W and S3 R + S4 W
+    const int k = idx / d;
+    const float r = sR[idx], w = sW[idx];
+    const float dp = sS[k] * r - sS[P + k] * w, dn = sS[2 * P + k] * r + sS[3 * P + k] * w;
+    if (dp != 0.f) atomicAdd(A.acc_pref + idx, dp);
+    if (dn != 0.f) atomicAdd(A.acc_pref_norm + idx, dn);
   }
   if (bad && A.status) *A.status = 1;
 }
 
-// backward per row: cb = GZ / 2 (GZ cleared), row gradient += cb P'
+// backward per row: cb = GZ / 2 + CK, cbn = DK (accumulators cleared), row gradient += (GZ / 2) P'
 template <int PT>
 __global__ void __launch_bounds__(kRowThreads)
 k_gumbel_rows_bwd(const kgrec_tables T, const int ktup, const GumbelRows S) {
@@ -657,7 +667,11 @@ k_gumbel_rows_bwd(const kgrec_tables T, const int ktup, const GumbelRows S) {
     __syncwarp();
 #pragma unroll
     for (int k = 0; k < PT; ++k)
-      if (valid && k < P && (k & 3) == q) { S.cb[row * P + k] = gz[k]; S.gz[row * P + k] = 0.f; }
+      if (valid && k < P && (k & 3) == q) {
+        S.cb[row * P + k] = gz[k] + S.ck[row * 2 * P + k];
+        S.cbn[row * P + k] = S.ck[row * 2 * P + P + k];
+        S.gz[row * P + k] = 0.f; S.ck[row * 2 * P + k] = 0.f; S.ck[row * 2 * P + P + k] = 0.f;
+      }
     int64_t ia = 0;
     if (S.acc_table && valid) ia = __ldg(S.item2ent + row);
 #pragma unroll
@@ -683,30 +697,36 @@ k_gumbel_rows_bwd(const kgrec_tables T, const int ktup, const GumbelRows S) {
   }
 }
 
-// dP'[k] += sum_rows cb[row][k] x[row]
+// dP'[k] += sum_rows cb[row][k] x[row];  dN'[k] += sum_rows cbn[row][k] x[row]
 template <int PT>
-__global__ void __launch_bounds__(kRowThreads, 2)
-k_gumbel_rows_tables(const kgrec_tables T, const GumbelRows S, float* __restrict__ acc_pref) {
+__global__ void __launch_bounds__(kRowThreads, (PT <= 20 ? 2 : 1))
+k_gumbel_rows_tables(const kgrec_tables T, const GumbelRows S, float* __restrict__ acc_pref, float* __restrict__ acc_pref_norm) {
   constexpr int KH = PT / 2;
   const int d = T.dim, P = T.n_pref, NC = d >> 2;
   const int items = NC * 2, ngrp = kRowThreads / items;
   const int grp = threadIdx.x / items, item = threadIdx.x - grp * items;
   const int jc = item % NC, k0 = (item / NC) * KH;
   if (grp >= ngrp) return;
-  float4 accP[KH];
+  float4 accP[KH], accN[KH];
 #pragma unroll
-  for (int k = 0; k < KH; ++k) accP[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < KH; ++k) { accP[k] = make_float4(0.f, 0.f, 0.f, 0.f); accN[k] = accP[k]; }
   const int n = *S.count;
   for (int i = blockIdx.x * ngrp + grp; i < n; i += gridDim.x * ngrp) {
     const int64_t row = S.list[i];
     const float4 x = S.x ? ld4(S.x + row * d + 4 * jc) : ldg_f4(reinterpret_cast<const float4*>(S.table + row * T.ld) + jc);
 #pragma unroll
     for (int k = 0; k < KH; ++k)
-      if (k0 + k < P) accP[k] = axpy4(__ldg(S.cb + row * P + k0 + k), x, accP[k]);
+      if (k0 + k < P) {
+        accP[k] = axpy4(__ldg(S.cb + row * P + k0 + k), x, accP[k]);
+        accN[k] = axpy4(__ldg(S.cbn + row * P + k0 + k), x, accN[k]);
+      }
   }
 #pragma unroll
   for (int k = 0; k < KH; ++k)
-    if (k0 + k < P) red_add_f4(acc_pref + static_cast<int64_t>(k0 + k) * d + 4 * jc, accP[k].x, accP[k].y, accP[k].z, accP[k].w);
+    if (k0 + k < P) {
+      red_add_f4(acc_pref + static_cast<int64_t>(k0 + k) * d + 4 * jc, accP[k].x, accP[k].y, accP[k].z, accP[k].w);
+      red_add_f4(acc_pref_norm + static_cast<int64_t>(k0 + k) * d + 4 * jc, accN[k].x, accN[k].y, accN[k].z, accN[k].w);
+    }
 }
 
 }  // namespace
@@ -716,7 +736,7 @@ using namespace kgrec;
 
 extern "C" int64_t kgrec_rec_rows_workspace_floats(int64_t n_user, int64_t n_item, int32_t dim, int32_t n_pref, int ktup) {
   // per side: ra, wb, g_ra, g_wb [rows, d], zx [rows, P], list [rows] (+1 count); KTUP items: x, gx [rows, d]
-  const int64_t per = 4 * static_cast<int64_t>(dim) + 2 * n_pref + 2;
+  const int64_t per = 4 * static_cast<int64_t>(dim) + 8 * static_cast<int64_t>(n_pref) + 8;     // covers the soft and the ST-Gumbel layouts
   return n_user * per + n_item * (per + (ktup ? 2 * static_cast<int64_t>(dim) : 0)) + 3 * static_cast<int64_t>(n_pref) * n_pref + 64;
 }
 
@@ -764,8 +784,10 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
     if (norm_reg_loss) { set_error("rec_rows_step: the fused row-norm regulariser goes with the soft path"); return KGREC_ERR_UNSUPPORTED; }
     GumbelRows GU{}, GI{};
     GU.table = T.user; GI.table = T.item;
-    GU.a = take(nu * P); GU.cn = take(nu * P); GU.gz = take(nu * P); GU.cb = take(nu * P);
-    GI.a = take(nit * P); GI.cn = take(nit * P); GI.gz = take(nit * P); GI.cb = take(nit * P);
+    GU.a = take(nu * P); GU.cn = take(nu * P); GU.gz = take(nu * P); GU.ck = take(2 * nu * P);
+    GU.cb = take(nu * P); GU.cbn = take(nu * P);
+    GI.a = take(nit * P); GI.cn = take(nit * P); GI.gz = take(nit * P); GI.ck = take(2 * nit * P);
+    GI.cb = take(nit * P); GI.cbn = take(nit * P);
     float* gxb = nullptr;
     if (ktup) { GI.x = take(nit * d); gxb = take(nit * d); }
     int32_t* gl_u = reinterpret_cast<int32_t*>(take(nu));
@@ -774,7 +796,9 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
     float* gram = take(3 * static_cast<int64_t>(P) * P);
     if (first_use) {
       KGREC_CUDA_OK(cudaMemsetAsync(GU.gz, 0, sizeof(float) * nu * P, st));
+      KGREC_CUDA_OK(cudaMemsetAsync(GU.ck, 0, sizeof(float) * 2 * nu * P, st));
       KGREC_CUDA_OK(cudaMemsetAsync(GI.gz, 0, sizeof(float) * nit * P, st));
+      KGREC_CUDA_OK(cudaMemsetAsync(GI.ck, 0, sizeof(float) * 2 * nit * P, st));
       if (ktup) KGREC_CUDA_OK(cudaMemsetAsync(gxb, 0, sizeof(float) * nit * d, st));
     }
     KGREC_CUDA_OK(cudaMemsetAsync(gcnt, 0, 4 * sizeof(int32_t), st));
@@ -793,13 +817,14 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
     A.xu = T.user; A.ldu = T.ld; A.xi = ktup ? GI.x : T.item; A.ldi = ktup ? d : T.ld;
     A.a_u = GU.a; A.cn_u = GU.cn; A.a_i = GI.a; A.cn_i = GI.cn;
     A.gx_u = acc->user; A.gx_i = GI.gx; A.gz_u = GU.gz; A.gz_i = GI.gz;
+    A.ck_u = GU.ck; A.ck_i = GI.ck;
     A.acc_pref = acc->pref; A.acc_pref_norm = acc->pref_norm; A.gram = gram; A.gumbel_u = gumbel_u; A.seed = seed;
     A.pos_scores = pos_scores; A.neg_scores = neg_scores; A.group_loss = static_cast<float*>(loss_workspace);
     A.status = status; A.T = T; A.ktup = ktup ? 1 : 0;
-    const size_t smem_p = (static_cast<size_t>(4) * P * d + 3 * static_cast<size_t>(P) * P +
+    const size_t smem_p = (static_cast<size_t>(2) * P * d + 4 * static_cast<size_t>(P) + 3 * static_cast<size_t>(P) * P +
                            static_cast<size_t>(kWarpsPerCta) * (n_neg + 1) * P) * sizeof(float);
     KGREC_CUDA_OK(cudaFuncSetAttribute(k_gumbel_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_p)));
-    const int64_t pg = (n_pos + kWarpsPerCta - 1) / kWarpsPerCta, pcap = static_cast<int64_t>(sm_count()) * 3;
+    const int64_t pg = (n_pos + kWarpsPerCta - 1) / kWarpsPerCta, pcap = static_cast<int64_t>(sm_count()) * 4;
 #define GROWS(PTV)                                                                                                       \
   {                                                                                                                      \
     KGREC_CUDA_OK(cudaFuncSetAttribute(k_gumbel_rows_fwd<PTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_t))); \
@@ -809,8 +834,8 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
     k_gumbel_pairs<<<static_cast<int>(pg < pcap ? pg : pcap), kThreads, smem_p, st>>>(A);                                \
     k_gumbel_rows_bwd<PTV><<<grid64(max_u), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, GU);                             \
     k_gumbel_rows_bwd<PTV><<<grid64(max_i), kRowThreads, smem_t, st>>>(T, ktup ? 1 : 0, GI);                             \
-    k_gumbel_rows_tables<PTV><<<gridt(max_u), kRowThreads, 0, st>>>(T, GU, acc->pref);                                   \
-    k_gumbel_rows_tables<PTV><<<gridt(max_i), kRowThreads, 0, st>>>(T, GI, acc->pref);                                   \
+    k_gumbel_rows_tables<PTV><<<gridt(max_u), kRowThreads, 0, st>>>(T, GU, acc->pref, acc->pref_norm);                   \
+    k_gumbel_rows_tables<PTV><<<gridt(max_i), kRowThreads, 0, st>>>(T, GI, acc->pref, acc->pref_norm);                   \
   }
     if (PT == 8) GROWS(8) else if (PT == 20) GROWS(20) else GROWS(32)
 #undef GROWS
