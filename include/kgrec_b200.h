@@ -226,7 +226,10 @@ int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model,
  * those lists.  Margin loss and embedding_size <= 128 only.
  * KGREC_TRANSR is accepted by this entry point as well (embedding_size <= 128, n_neg <= 14,
  * reg_flags 0): the relation's d x d matrix is read twice per GROUP and its gradient
- * (grads->proj, always a dense [n_rel, d*d] accumulate) added once per group. */
+ * (grads->proj, always a dense [n_rel, d*d] accumulate) added once per group; the groups are
+ * visited in relation order (a counting sort of pr inside the call) so that a CTA's warps share M_r.
+ * workspace: >= kgrec_corrupt_loss_step_workspace_bytes(tables, model, n_pos) bytes. */
+int64_t kgrec_corrupt_loss_step_workspace_bytes(const kgrec_tables* tables, int model, int64_t n_pos);
 int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model,
                             const void* ph, const void* pt, const void* pr, int idx_bytes, int64_t n_pos,
                             const int32_t* corrupt, int32_t n_neg, int64_t batch_pos,

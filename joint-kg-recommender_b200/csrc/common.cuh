@@ -281,6 +281,16 @@ struct Row {
 };
 
 // L(e) partial and its derivative (torch: d|x|/dx = sign(x), sign(0) = 0)
+// ---- packed fp32x2 arithmetic (sm_100: one instruction, two lanes of the FMA pipe) ----------
+typedef unsigned long long f32x2;     // two floats in one 64-bit register pair
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 splat2(float v) { f32x2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float sum2(f32x2 v) { return lo2(v) + hi2(v); }
+__device__ __forceinline__ float abssum2(f32x2 v) { return fabsf(lo2(v)) + fabsf(hi2(v)); }
+
 __device__ __forceinline__ float dist_term(float e, int l1) { return l1 ? fabsf(e) : e * e; }
 __device__ __forceinline__ float ddist_term(float e, int l1) {
   return l1 ? ((e > 0.f) ? 1.f : ((e < 0.f) ? -1.f : 0.f)) : 2.f * e;

@@ -506,15 +506,6 @@ k_eval(const EvalArgs A) {
   }
 }
 
-// ---- packed fp32x2 arithmetic (sm_100: one instruction, two lanes of the FMA pipe) ----------
-typedef unsigned long long f32x2;     // two floats in one 64-bit register pair
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 splat2(float v) { f32x2 r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v)); return r; }
-__device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
-__device__ __forceinline__ float sum2(f32x2 v) { return lo2(v) + hi2(v); }
-__device__ __forceinline__ float abssum2(f32x2 v) { return fabsf(lo2(v)) + fabsf(hi2(v)); }
 
 // Cold path of the tiled kernel's top-K epilogue, kept out of line so the hot loop and the
 // 32 unrolled threshold tests stay small enough for the instruction cache.  Returns the new

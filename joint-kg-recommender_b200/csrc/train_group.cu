@@ -1050,7 +1050,7 @@ template <int NVT, bool MARGIN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_group_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
                float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
-               int64_t* __restrict__ slot_rel, int32_t* status) {
+               int64_t* __restrict__ slot_rel, int32_t* status, const int32_t* __restrict__ order) {
   extern __shared__ __align__(16) float rsm[];
   const kgrec_tables& T = G.T;
   const LossCfg& L = G.L;
@@ -1064,11 +1064,15 @@ k_group_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_score
   const float prm = L.param;
   float4* Vs = reinterpret_cast<float4*>(rsm) + static_cast<size_t>(wid) * (NVT * NC + d * (NVT / 4));   // [nv][NC]
   float4* GT = Vs + NVT * NC;                                                                            // [d][NVT / 4]
-  const int stride = gridDim.x * kWarpsPerCta;
   const void* pcol = lane == 0 ? G.ph : (lane == 1 ? G.pt : G.pr);
   bool bad = false;
+  // groups in relation order (`order`, k_rel_*): a CTA takes a CONTIGUOUS chunk of it, so its warps work on the same
+  // relation and M_r (40 KB at d = 100) stays in this SM's L1 across the chunk
+  const int chunk = ((n_pos + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) + kWarpsPerCta - 1) / kWarpsPerCta * kWarpsPerCta;
+  const int i_end = min(n_pos, (static_cast<int>(blockIdx.x) + 1) * chunk);
 
-  for (int j = blockIdx.x * kWarpsPerCta + wid; j < n_pos; j += stride) {
+  for (int i = blockIdx.x * chunk + wid; i < i_end; i += kWarpsPerCta) {
+    const int j = order ? __ldg(order + i) : i;
     const int32_t cv = lane < K ? __ldg(G.corrupt + static_cast<int64_t>(j) * K + lane) : 0;
     const int64_t pv = lane < 3 ? load_idx(pcol, j, G.is64) : 0;
     const int64_t vh = __shfl_sync(FULL, pv, 0), vt = __shfl_sync(FULL, pv, 1), vr = __shfl_sync(FULL, pv, 2);
@@ -1274,6 +1278,321 @@ k_group_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_score
   if (bad && status) *status = 1;
 }
 
+// --- TransR, relation runs: the CTA-level step ----------------------------------------------------------------
+// The groups of a launch are visited in relation order (`order`, k_rel_*).  A CTA walks a contiguous chunk of that order
+// tile by tile; a tile is up to (64 RB) / (2 + K) consecutive groups of ONE relation, i.e. up to 64 RB entity rows V.
+// M_r and M_r^T stay in shared memory while the relation does not change, the gradient of M_r in registers (one flush per
+// relation run and CTA), and the three products of the step are register-tiled FP32 GEMMs on shared-memory operands:
+//     Y  = V M^T            [rows x d]  (warp = 8 rows of V, lane = rows a = lane + 32 q of M, dot form along b)
+//     dM += G^T V           [d x d]     (thread = 4 QA rows a x 4 QB columns b, rank-1 form along the tile's rows)
+//     dV = G M              [rows x d]  (warp = 8 rows of G, lane = rows b = lane + 32 q of M^T, dot form along a)
+// with the scores / ranking loss / G = dL/dY stage of the warp kernel between the first and the other two (one warp per
+// group, Y read from and G written to the same shared buffer).  Both [rows x d] products are one routine (run_tile_dot):
+// two packed fma.rn.f32x2 per pair of 16-byte operands, no splats; QF = d / 32 full lane-rows, the d - 32 QF rows left
+// (4 at d = 100) in a short (row, lane) pass instead of a quarter-empty fourth accumulator column.  The row pitch is an
+// odd number of 16-byte units: the lane-per-row reads are conflict-free.
+__host__ __device__ inline int run_pitch(int d) { return ((d >> 2) & 1) ? d : d + 4; }
+
+template <int QF, typename Emit>
+__device__ __forceinline__ void run_tile_dot(const float* __restrict__ A, const float* __restrict__ B, const int d, const int NC,
+                                             const int pitch, const int lane, Emit emit) {
+  f32x2 acc[8][QF];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int q = 0; q < QF; ++q) acc[i][q] = 0ull;
+  const ulonglong2* pb[QF];
+  const ulonglong2* pa[8];
+#pragma unroll
+  for (int q = 0; q < QF; ++q) pb[q] = reinterpret_cast<const ulonglong2*>(B + (lane + 32 * q) * pitch);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pa[i] = reinterpret_cast<const ulonglong2*>(A + i * pitch);
+#pragma unroll 2
+  for (int c = 0; c < NC; ++c) {
+    ulonglong2 m[QF];
+#pragma unroll
+    for (int q = 0; q < QF; ++q) { m[q] = *pb[q]; ++pb[q]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const ulonglong2 x = *pa[i];
+      ++pa[i];
+#pragma unroll
+      for (int q = 0; q < QF; ++q) acc[i][q] = fma2(m[q].x, x.x, fma2(m[q].y, x.y, acc[i][q]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int q = 0; q < QF; ++q) emit(i, lane + 32 * q, sum2(acc[i][q]));
+  const int rem = d - 32 * QF;
+  for (int p = lane; p < 8 * rem; p += 32) {
+    const int i = p / rem, a = 32 * QF + p - i * rem;
+    const ulonglong2* xa = reinterpret_cast<const ulonglong2*>(A + i * pitch);
+    const ulonglong2* xb = reinterpret_cast<const ulonglong2*>(B + a * pitch);
+    f32x2 s = 0ull;
+    for (int c = 0; c < NC; ++c) s = fma2(xb[c].x, xa[c].x, fma2(xb[c].y, xa[c].y, s));
+    emit(i, a, sum2(s));
+  }
+}
+
+template <int QA, int QB, int QF, int RB, bool MARGIN>
+__global__ void __launch_bounds__(kThreads, 1)
+k_run_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores, float* __restrict__ neg_scores,
+             float* __restrict__ group_loss, const kgrec_grads Gr, int64_t* __restrict__ slot_ent,
+             int64_t* __restrict__ slot_rel, int32_t* status, const int32_t* __restrict__ order) {
+  extern __shared__ __align__(16) float rsm[];
+  constexpr int ROWS = 64 * RB;
+  const kgrec_tables& T = G.T;
+  const LossCfg& L = G.L;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int K = L.n_neg, nv = 2 + K, GC = min(32, ROWS / nv);
+  const int d = T.dim, NC = d >> 2, pitch = run_pitch(d);
+  const int n_pos = static_cast<int>(L.n_pos);
+  const int l1 = T.l1;
+  const int bp = static_cast<int>(L.batch_pos < 0x7fffffff ? L.batch_pos : 0x7fffffff);
+  const float prm = L.param;
+  float* sM = rsm;                                   // [d][pitch]
+  float* sMt = sM + d * pitch;                       // [d][pitch]  M^T
+  float* sV = sMt + d * pitch;                       // [ROWS][pitch]
+  float* sG = sV + ROWS * pitch;                     // [ROWS][pitch]  Y, then G
+  float** sDst = reinterpret_cast<float**>(sG + ROWS * pitch);          // [ROWS] where the row's entity gradient goes
+  int* sJ = reinterpret_cast<int*>(sDst + ROWS);     // [32] group index of the tile's groups; [32] = relation, [33] = groups
+  bool bad = false;
+
+  // dM tile of this thread: rows 4 (ta + nta q) .. + 3, column chunks tb + ntb q
+  const int nta = (NC + QA - 1) / QA, ntb = (NC + QB - 1) / QB;
+  const int ta = threadIdx.x % nta, tb = threadIdx.x / nta;
+  const bool mt = tb < ntb;
+  f32x2 accM[QA * 4][QB][2];
+#pragma unroll
+  for (int i = 0; i < QA * 4; ++i)
+#pragma unroll
+    for (int q = 0; q < QB; ++q) accM[i][q][0] = accM[i][q][1] = 0ull;
+  auto flush = [&](int rel) {
+    if (rel < 0 || !mt) return;
+    float* gM = Gr.proj + static_cast<uint64_t>(rel) * d * d;
+#pragma unroll
+    for (int qa = 0; qa < QA; ++qa)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int a = 4 * (ta + nta * qa) + r;
+#pragma unroll
+        for (int q = 0; q < QB; ++q) {
+          const int cb = tb + ntb * q;
+          f32x2(&v)[2] = accM[4 * qa + r][q];
+          if (a < d && cb < NC) red_add_f4(gM + static_cast<size_t>(a) * d + 4 * cb, lo2(v[0]), hi2(v[0]), lo2(v[1]), hi2(v[1]));
+          v[0] = v[1] = 0ull;
+        }
+      }
+  };
+
+  const int chunk = (n_pos + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int i_end = min(n_pos, (static_cast<int>(blockIdx.x) + 1) * chunk);
+  int cur_rel = -1;
+  float rr[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int i0 = blockIdx.x * chunk; i0 < i_end;) {
+    // ---- the tile: leading groups of the chunk's rest that share a relation
+    if (wid == 0) {
+      int j = -1;
+      int64_t r = -1;
+      if (lane < GC && i0 + lane < i_end) {
+        j = order ? __ldg(order + i0 + lane) : i0 + lane;
+        r = load_idx(G.pr, j, G.is64);
+        if (static_cast<uint64_t>(r) >= static_cast<uint64_t>(T.n_rel)) { bad = true; r = 0; }
+      }
+      const int64_t r0 = __shfl_sync(FULL, r, 0);
+      const uint32_t same = __ballot_sync(FULL, j >= 0 && r == r0);
+      const int ng = same == FULL ? 32 : __ffs(~same) - 1;       // leading ones (lane 0 is always in)
+      sJ[lane] = j;
+      if (lane == 0) { sJ[32] = static_cast<int>(r0); sJ[33] = ng; }
+    }
+    __syncthreads();
+    const int rel = sJ[32], ng = sJ[33], rows = ng * nv;
+    if (rel != cur_rel) {
+      flush(cur_rel);
+      cur_rel = rel;
+      const float4* M4 = reinterpret_cast<const float4*>(T.proj + static_cast<uint64_t>(rel) * d * d);
+      for (int idx = threadIdx.x; idx < d * NC; idx += kThreads) {
+        const int a = idx / NC, c = idx - a * NC;
+        const float4 m = __ldg(M4 + idx);
+        *reinterpret_cast<float4*>(sM + a * pitch + 4 * c) = m;
+        sMt[(4 * c) * pitch + a] = m.x; sMt[(4 * c + 1) * pitch + a] = m.y;
+        sMt[(4 * c + 2) * pitch + a] = m.z; sMt[(4 * c + 3) * pitch + a] = m.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = lane + 32 * i;
+        rr[i] = a < d ? __ldg(T.rel + static_cast<uint64_t>(rel) * T.ld + a) : 0.f;
+      }
+    }
+    // ---- stage V: the warp's 8-row blocks; lane i finds the table row of block row i (one round of dependent index
+    //      loads for the block), then the 8 row loads are in flight together
+#pragma unroll 1
+    for (int rb = 0; rb < RB; ++rb) {
+      const int base = 8 * (wid + kWarpsPerCta * rb);
+      if (base >= rows) break;
+      int64_t id = 0;
+      if (lane < 8 && base + lane < rows) {
+        const int n = base + lane, gq = n / nv, v = n - gq * nv, j = sJ[gq];
+        if (v == 0) id = load_idx(G.ph, j, G.is64);
+        else if (v == 1) id = load_idx(G.pt, j, G.is64);
+        else { const int32_t c = __ldg(G.corrupt + static_cast<int64_t>(j) * K + (v - 2)); id = c < 0 ? ~c : c; }
+        if (slot_ent) {
+          slot_ent[static_cast<int64_t>(j) * nv + v] = id;
+          if (v == 0) slot_rel[j] = load_idx(G.pr, j, G.is64);
+        }
+        if (static_cast<uint64_t>(id) >= static_cast<uint64_t>(T.n_ent)) { bad = true; id = 0; }
+        sDst[n] = Gr.mode == 0 ? Gr.ent + (static_cast<int64_t>(j) * nv + v) * d : Gr.ent + static_cast<uint64_t>(id) * d;
+      }
+      float4 x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t idi = __shfl_sync(FULL, id, i);
+        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < NC && base + i < rows) x[i] = ldg_f4(reinterpret_cast<const float4*>(T.ent + static_cast<uint64_t>(idi) * T.ld) + lane);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (lane < NC) *reinterpret_cast<float4*>(sV + (base + i) * pitch + 4 * lane) = x[i];       // rows past the tile: zero
+    }
+    __syncthreads();
+    // ---- Y = V M^T
+#pragma unroll 1
+    for (int rb = 0; rb < RB; ++rb) {
+      const int base = 8 * (wid + kWarpsPerCta * rb);
+      if (base >= rows) break;
+      float* yrow = sG + base * pitch;
+      run_tile_dot<QF>(sV + base * pitch, sM, d, NC, pitch, lane, [&](int i, int a, float v) { yrow[i * pitch + a] = v; });
+    }
+    __syncthreads();
+    // ---- scores, ranking loss, G = dL/dY in place: one warp per group
+    for (int gq = wid; gq < ng; gq += kWarpsPerCta) {
+      const int j = sJ[gq];
+      float* Y = sG + gq * nv * pitch;
+      const int32_t cv = lane < K ? __ldg(G.corrupt + static_cast<int64_t>(j) * K + lane) : 0;
+      float up = up0;
+      if (!MARGIN) {
+        const int b = j / bp;
+        up /= static_cast<float>(min(bp, n_pos - b * bp)) * static_cast<float>(K);
+      }
+      float yh[4], yt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = lane + 32 * i;
+        yh[i] = a < d ? Y[a] : 0.f;
+        yt[i] = a < d ? Y[pitch + a] : 0.f;
+      }
+      float sp = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sp += (lane + 32 * i < d) ? dist_term(yh[i] + rr[i] - yt[i], l1) : 0.f;
+      sp = warp_sum(sp);
+      float lsum = 0.f, cpos = 0.f, mys = 0.f;
+      float gp[4] = {0.f, 0.f, 0.f, 0.f}, gh[4] = {0.f, 0.f, 0.f, 0.f}, gt[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < K; ++k) {
+        const bool head = __shfl_sync(FULL, cv, k) < 0;
+        float* Yc = Y + (2 + k) * pitch;
+        float e[4], sn = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int a = lane + 32 * i;
+          const float yc = a < d ? Yc[a] : 0.f;
+          e[i] = head ? yc + rr[i] - yt[i] : yh[i] + rr[i] - yc;
+          sn += a < d ? dist_term(e[i], l1) : 0.f;
+        }
+        sn = warp_sum(sn);
+        if (lane == k) mys = sn;
+        float coef;
+        if (MARGIN) {
+          const float tt = sp - sn + prm;
+          lsum += fmaxf(tt, 0.f);
+          coef = tt > 0.f ? -up : 0.f;
+          cpos += tt > 0.f ? 1.f : 0.f;
+        } else {
+          const float xx = prm * (sp - sn);
+          lsum += fmaxf(-xx, 0.f) + log1pf(expf(-fabsf(xx)));
+          const float dp = -prm / (1.f + expf(xx));
+          cpos += dp;
+          coef = -dp * up;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int a = lane + 32 * i;
+          const float g = coef * ddist_term(e[i], l1);
+          gp[i] += g;
+          if (head) gt[i] -= g; else gh[i] += g;
+          if (a < d) Yc[a] = head ? g : -g;
+        }
+      }
+      const float cp = cpos * up;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = lane + 32 * i;
+        const float g = cp * ddist_term(yh[i] + rr[i] - yt[i], l1);
+        gp[i] += g;
+        if (a < d) {
+          Y[a] = gh[i] + g;
+          Y[pitch + a] = gt[i] - g;
+          if (Gr.mode == 0) Gr.rel[static_cast<int64_t>(j) * d + a] = gp[i];
+          else atomicAdd(Gr.rel + static_cast<uint64_t>(rel) * d + a, gp[i]);
+        }
+      }
+      if (lane == 0) { pos_scores[j] = sp; group_loss[j] = lsum; }
+      if (lane < K) neg_scores[static_cast<int64_t>(j) * K + lane] = mys;
+    }
+    __syncthreads();
+    // ---- dM += G^T V   (chunks past the row end are clamped: they accumulate values that are never flushed)
+    if (mt) {
+      const float4* gp[QA];
+      const ulonglong2* vp[QB];
+#pragma unroll
+      for (int qa = 0; qa < QA; ++qa) gp[qa] = reinterpret_cast<const float4*>(sG + 4 * min(ta + nta * qa, NC - 1));
+#pragma unroll
+      for (int q = 0; q < QB; ++q) vp[q] = reinterpret_cast<const ulonglong2*>(sV + 4 * min(tb + ntb * q, NC - 1));
+      const int p4 = pitch >> 2;
+#pragma unroll 2
+      for (int n = 0; n < rows; ++n) {
+        float4 g[QA];
+        ulonglong2 v[QB];
+#pragma unroll
+        for (int qa = 0; qa < QA; ++qa) { g[qa] = *gp[qa]; gp[qa] += p4; }
+#pragma unroll
+        for (int q = 0; q < QB; ++q) { v[q] = *vp[q]; vp[q] += p4; }
+#pragma unroll
+        for (int qa = 0; qa < QA; ++qa) {
+          const float gs[4] = {g[qa].x, g[qa].y, g[qa].z, g[qa].w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const f32x2 s2 = splat2(gs[r]);
+#pragma unroll
+            for (int q = 0; q < QB; ++q) {
+              accM[4 * qa + r][q][0] = fma2(s2, v[q].x, accM[4 * qa + r][q][0]);
+              accM[4 * qa + r][q][1] = fma2(s2, v[q].y, accM[4 * qa + r][q][1]);
+            }
+          }
+        }
+      }
+    }
+    // ---- dV = G M
+#pragma unroll 1
+    for (int rb = 0; rb < RB; ++rb) {
+      const int base = 8 * (wid + kWarpsPerCta * rb);
+      if (base >= rows) break;
+      const int dense = Gr.mode;
+      run_tile_dot<QF>(sG + base * pitch, sMt, d, NC, pitch, lane, [&](int i, int b, float v) {
+        if (base + i < rows) {
+          float* dst = sDst[base + i] + b;
+          if (dense) atomicAdd(dst, v); else __stcs(dst, v);
+        }
+      });
+    }
+    __syncthreads();
+    i0 += ng;
+  }
+  flush(cur_rel);
+  if (bad && status) *status = 1;
+}
+
 // slot row ids for the general step kernel (TransH, wide rows): one thread per slot
 __global__ void __launch_bounds__(256)
 k_group_slot_ids(const void* ph, const void* pt, const void* pr, const int is64, const int32_t* __restrict__ corrupt,
@@ -1287,6 +1606,45 @@ k_group_slot_ids(const void* ph, const void* pt, const void* pr, const int is64,
     else if (t == 1) v = load_idx(pt, j, is64);
     else { const int32_t c = __ldg(corrupt + j * K + (t - 2)); v = c < 0 ? ~c : c; }
     slot_ent[i] = v;
+  }
+}
+
+// --- groups in relation order (TransR): counting sort of the positives' relation ids --------------------------------
+__global__ void __launch_bounds__(256)
+k_rel_hist(const void* pr, const int is64, const int n_pos, const int64_t n_rel, int32_t* __restrict__ count) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pos; j += gridDim.x * blockDim.x) {
+    int64_t r = load_idx(pr, j, is64);
+    if (static_cast<uint64_t>(r) >= static_cast<uint64_t>(n_rel)) r = 0;          // the step kernel reports it
+    atomicAdd(count + r, 1);
+  }
+}
+
+// exclusive scan of count[0 .. n_rel) in place, one CTA (n_rel is a table height: thousands at most in practice)
+__global__ void __launch_bounds__(1024)
+k_rel_scan(int32_t* __restrict__ count, const int64_t n_rel) {
+  __shared__ int32_t part[1024];
+  const int64_t per = (n_rel + 1023) / 1024, lo = threadIdx.x * per, hi = lo + per < n_rel ? lo + per : n_rel;
+  int32_t s = 0;
+  for (int64_t r = lo; r < hi; ++r) s += count[r];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int32_t run = part[threadIdx.x] - s;
+  for (int64_t r = lo; r < hi; ++r) { const int32_t c = count[r]; count[r] = run; run += c; }
+}
+
+__global__ void __launch_bounds__(256)
+k_rel_scatter(const void* pr, const int is64, const int n_pos, const int64_t n_rel, int32_t* __restrict__ cursor,
+              int32_t* __restrict__ order) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_pos; j += gridDim.x * blockDim.x) {
+    int64_t r = load_idx(pr, j, is64);
+    if (static_cast<uint64_t>(r) >= static_cast<uint64_t>(n_rel)) r = 0;
+    order[atomicAdd(cursor + r, 1)] = j;
   }
 }
 
@@ -1440,6 +1798,12 @@ extern "C" int kgrec_corrupt_loss_bwd(const kgrec_tables* tables, int model, con
   return KGREC_OK;
 }
 
+extern "C" int64_t kgrec_corrupt_loss_step_workspace_bytes(const kgrec_tables* tables, int model, int64_t n_pos) {
+  const int64_t n = n_pos > 0 ? n_pos : 1;
+  if (model == KGREC_TRANSR && tables) return 4 * (2 * n + tables->n_rel + 1);      // + relation order and its cursors
+  return 4 * n;
+}
+
 extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, const void* ph, const void* pt,
                                        const void* pr, int idx_bytes, int64_t n_pos, const int32_t* corrupt,
                                        int32_t n_neg, int64_t batch_pos, int loss_kind, float margin_or_target,
@@ -1463,19 +1827,56 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
     const GroupArgs GA{*tables, ph, pt, pr, idx_bytes == 8, corrupt, LossCfg{loss_kind, margin_or_target, n_neg, n_pos, batch_pos}, 1.f};
     float* gl = static_cast<float*>(workspace);
     cudaStream_t s2 = static_cast<cudaStream_t>(stream);
+    // workspace: [group_loss n_pos | order n_pos | cursor n_rel]
+    int32_t* order = reinterpret_cast<int32_t*>(gl + n_pos);
+    int32_t* cursor = order + n_pos;
+    {
+      const char* env = group_step_env();
+      if (env && env[0] == 'u') order = nullptr;                      // KGREC_GROUP_STEP=u: batch order (A/B)
+    }
+    if (order) {
+      KGREC_CUDA_OK(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * tables->n_rel, s2));
+      const int gs = static_cast<int>((n_pos + 255) / 256 < sm_count() * 4 ? (n_pos + 255) / 256 : sm_count() * 4);
+      k_rel_hist<<<gs, 256, 0, s2>>>(pr, idx_bytes == 8, static_cast<int>(n_pos), tables->n_rel, cursor);
+      k_rel_scan<<<1, 1024, 0, s2>>>(cursor, tables->n_rel);
+      k_rel_scatter<<<gs, 256, 0, s2>>>(pr, idx_bytes == 8, static_cast<int>(n_pos), tables->n_rel, cursor, order);
+    }
+    const bool mg = loss_kind == KGREC_LOSS_MARGIN;
+    const char* env_r = group_step_env();
+    if (tables->dim >= 32 && !(env_r && (env_r[0] == 'w' || env_r[0] == 'u'))) {
+      // the CTA-level run kernel; KGREC_GROUP_STEP=w keeps the warp-per-group kernel (A/B), =u that kernel in batch order
+      const int d = tables->dim, NC = d / 4, pitch = run_pitch(d), qf = d / 32;
+      auto smem_for = [&](int rb) { return (2 * static_cast<size_t>(d) + 2 * 64 * rb) * pitch * 4 + 64 * rb * 8 + 34 * 4; };
+      const int rb = (NC <= 27 && smem_for(2) <= 220 * 1024) ? 2 : 1;
+      const size_t smem = smem_for(rb);
+      const int64_t want = (n_pos + 3) / 4;                                  // at least ~4 groups per CTA
+      const int grid = static_cast<int>(want < sm_count() ? want : sm_count());
+#define CALL_RUN(QAV, QBV, QFV, RBV)                                                                                     \
+  {                                                                                                                      \
+    auto kern = mg ? k_run_step_r<QAV, QBV, QFV, RBV, true> : k_run_step_r<QAV, QBV, QFV, RBV, false>;                   \
+    KGREC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));       \
+    kern<<<grid, kThreads, smem, s2>>>(GA, grad_loss, pos_scores, neg_scores, gl, *grads, slot_ent_ids, slot_rel_ids, status, order); \
+  }
+      if (NC <= 16) { if (qf <= 1) CALL_RUN(1, 1, 1, 2) else CALL_RUN(1, 1, 2, 2) }
+      else if (NC <= 27) { if (qf <= 2) CALL_RUN(1, 3, 2, 2) else CALL_RUN(1, 3, 3, 2) }
+      else { if (qf <= 3) CALL_RUN(2, 2, 3, 1) else CALL_RUN(2, 2, 4, 1) }
+#undef CALL_RUN
+    } else {
+    const int64_t want = (n_pos + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int grid_r = static_cast<int>(want < sm_count() ? want : sm_count());          // one resident CTA per SM
     const int nvt = n_neg <= 2 ? 4 : (n_neg <= 10 ? 12 : 16);
     const size_t smem = static_cast<size_t>(kWarpsPerCta) * (static_cast<size_t>(nvt) * (tables->dim / 4) + static_cast<size_t>(tables->dim) * (nvt / 4)) * 16;
-    const bool mg = loss_kind == KGREC_LOSS_MARGIN;
 #define CALL_R(NVTV, MV)                                                                                             \
   {                                                                                                                  \
     auto kern = k_group_step_r<NVTV, MV>;                                                                            \
     KGREC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));   \
-    kern<<<grid_for(n_pos), kThreads, smem, s2>>>(GA, grad_loss, pos_scores, neg_scores, gl, *grads, slot_ent_ids, slot_rel_ids, status); \
+    kern<<<grid_r, kThreads, smem, s2>>>(GA, grad_loss, pos_scores, neg_scores, gl, *grads, slot_ent_ids, slot_rel_ids, status, order); \
   }
     if (nvt == 4) { if (mg) CALL_R(4, true) else CALL_R(4, false) }
     else if (nvt == 12) { if (mg) CALL_R(12, true) else CALL_R(12, false) }
     else { if (mg) CALL_R(16, true) else CALL_R(16, false) }
 #undef CALL_R
+    }
     KGREC_CUDA_OK(cudaGetLastError());
     const int64_t nbt = (n_pos + batch_pos - 1) / batch_pos;
     k_batch_loss<<<static_cast<unsigned>(nbt), 256, 0, s2>>>(gl, GA.L, loss);

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "kgrec_score_bwd": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int64, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(Grads), C.c_void_p]),
     "kgrec_rank_loss_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "kgrec_corrupt_loss_step_workspace_bytes": (C.c_int64, [C.POINTER(Tables), C.c_int, C.c_int64]),
     "kgrec_rank_loss_fwd": (C.c_int, [C.POINTER(Tables), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int32,
                                       C.c_int64, C.c_int, C.c_float, C.c_void_p, C.c_uint64,

@@ -355,7 +355,8 @@ def corrupt_loss_step(cfg, weights, pos, corrupt, n_neg, batch_pos, loss_kind, p
     pos_s = torch.empty(n_pos, dtype=torch.float32, device=dev)
     neg_s = torch.empty(n_pos * n_neg, dtype=torch.float32, device=dev)
     loss = torch.empty((n_pos + batch_pos - 1) // batch_pos, dtype=torch.float32, device=dev)
-    ws = torch.empty(max(1, n_pos), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    ws = torch.empty(lib.kgrec_corrupt_loss_step_workspace_bytes(C.byref(T), cfg.model, n_pos) // 4, dtype=torch.float32, device=dev)
     g = Grads()
     dense = cfg.grad_mode == "dense"
     g.mode = 1 if dense else 0

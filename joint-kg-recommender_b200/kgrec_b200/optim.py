@@ -137,7 +137,7 @@ class SparseRowOptimizer:
         g = self._grads(names)
         pos_s = torch.empty(n_pos, dtype=torch.float32, device=dev)
         neg_s = torch.empty(n_pos * n_neg, dtype=torch.float32, device=dev)
-        ws = torch.empty(max(1, n_pos), dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.kgrec_corrupt_loss_step_workspace_bytes(C.byref(T), kmodel, n_pos) // 4, dtype=torch.float32, device=dev)
         kind = {"margin": _lib.LOSS_MARGIN, "bpr": _lib.LOSS_BPR}[loss]
         _lib.check(lib.kgrec_corrupt_loss_step(
             C.byref(T), kmodel, ptr(pos[0]), ptr(pos[1]), ptr(pos[2]), idx_bytes, n_pos, ptr(corrupt),

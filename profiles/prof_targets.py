@@ -1,6 +1,6 @@
 """One small workload per kernel, for `ncu -k regex:<kernel>` captures (round 2).
     python profiles/prof_targets.py <target> [reps]
-targets: step_e100k step_e500k step_e5m step_tma5m eval_d128 eval_h_d128 opt transr_eval tup_step gumbel_eval soft_eval_d128"""
+targets: transr_step step_e100k step_e500k step_e5m step_tma5m eval_d128 eval_h_d128 opt transr_eval tup_step gumbel_eval soft_eval_d128"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "joint-kg-recommender_b200")]
@@ -32,6 +32,15 @@ if target.startswith("step_"):
     for i in range(reps):
         m.zero_grad(set_to_none=True)
         m.loss_step_corrupt(sets[i % 2][0], sets[i % 2][1], margin=1.0, batch_pos=B)
+elif target == "transr_step":
+    with device_init(dev):
+        m = K.TransRModel(False, D, 100_000, 500)
+    m.grad_mode = "sparse"
+    NB = 32
+    pos, c = kg_ids(100_000)
+    for i in range(reps):
+        m.zero_grad(set_to_none=True)
+        m.loss_step_corrupt(pos, c, margin=1.0, batch_pos=B)
 elif target in ("eval_d128", "eval_h_d128"):
     with device_init(dev):
         m = (K.TransEModel if target == "eval_d128" else K.TransHModel)(False, 128, 5_000_000, 500)
