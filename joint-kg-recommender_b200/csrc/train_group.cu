@@ -1355,8 +1355,9 @@ k_run_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
   float* sMt = sM + d * pitch;                       // [d][pitch]  M^T
   float* sV = sMt + d * pitch;                       // [ROWS][pitch]
   float* sG = sV + ROWS * pitch;                     // [ROWS][pitch]  Y, then G
-  float** sDst = reinterpret_cast<float**>(sG + ROWS * pitch);          // [ROWS] where the row's entity gradient goes
-  int* sJ = reinterpret_cast<int*>(sDst + ROWS);     // [32] group index of the tile's groups; [32] = relation, [33] = groups
+  float** sDst = reinterpret_cast<float**>(sG + ROWS * pitch);          // [2][ROWS] where the row's entity gradient goes
+  const float** sSrc = const_cast<const float**>(sDst + 2 * ROWS);      // [ROWS] table rows of the NEXT tile (nullptr: zero row)
+  int* sJ = reinterpret_cast<int*>(sSrc + ROWS);     // [2][36]: group index of the tile's groups; [32] relation, [33] groups
   bool bad = false;
 
   // dM tile of this thread: rows 4 (ta + nta q) .. + 3, column chunks tb + ntb q
@@ -1391,31 +1392,77 @@ k_run_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
   int cur_rel = -1;
   float rr[4] = {0.f, 0.f, 0.f, 0.f};
 
-  for (int i0 = blockIdx.x * chunk; i0 < i_end;) {
-    // ---- the tile: leading groups of the chunk's rest that share a relation
-    if (wid == 0) {
-      int j = -1;
-      int64_t r = -1;
-      if (lane < GC && i0 + lane < i_end) {
-        j = order ? __ldg(order + i0 + lane) : i0 + lane;
-        r = load_idx(G.pr, j, G.is64);
-        if (static_cast<uint64_t>(r) >= static_cast<uint64_t>(T.n_rel)) { bad = true; r = 0; }
-      }
-      const int64_t r0 = __shfl_sync(FULL, r, 0);
-      const uint32_t same = __ballot_sync(FULL, j >= 0 && r == r0);
-      const int ng = same == FULL ? 32 : __ffs(~same) - 1;       // leading ones (lane 0 is always in)
-      sJ[lane] = j;
-      if (lane == 0) { sJ[32] = static_cast<int>(r0); sJ[33] = ng; }
+  // The tile that starts at group i_from of the order (one warp): its groups -- the leading ones of the chunk's rest that
+  // share a relation --, then per tile row the table row to copy from and the place its gradient goes to.
+  auto plan = [&](int buf, int i_from) {
+    int* J = sJ + 36 * buf;
+    int j = -1;
+    int64_t r = -1;
+    if (lane < GC && i_from + lane < i_end) {
+      j = order ? __ldg(order + i_from + lane) : i_from + lane;
+      r = load_idx(G.pr, j, G.is64);
+      if (static_cast<uint64_t>(r) >= static_cast<uint64_t>(T.n_rel)) { bad = true; r = 0; }
     }
-    __syncthreads();
-    const int rel = sJ[32], ng = sJ[33], rows = ng * nv;
+    const int64_t r0 = __shfl_sync(FULL, r, 0);
+    const uint32_t same = __ballot_sync(FULL, j >= 0 && r == r0);
+    const int ng = same == FULL ? 32 : __ffs(~same) - 1;          // leading ones; 0 past the chunk's end
+    J[lane] = j;
+    if (lane == 0) { J[32] = static_cast<int>(r0); J[33] = ng; }
+    __syncwarp();
+    const int rows = ng * nv;
+    for (int n = lane; n < ROWS; n += 32) {
+      const float* src = nullptr;
+      if (n < rows) {
+        const int gq = n / nv, v = n - gq * nv, jj = J[gq];
+        int64_t id;
+        if (v == 0) id = load_idx(G.ph, jj, G.is64);
+        else if (v == 1) id = load_idx(G.pt, jj, G.is64);
+        else { const int32_t c = __ldg(G.corrupt + static_cast<int64_t>(jj) * K + (v - 2)); id = c < 0 ? ~c : c; }
+        if (slot_ent) {
+          slot_ent[static_cast<int64_t>(jj) * nv + v] = id;
+          if (v == 0) slot_rel[jj] = load_idx(G.pr, jj, G.is64);
+        }
+        if (static_cast<uint64_t>(id) >= static_cast<uint64_t>(T.n_ent)) { bad = true; id = 0; }
+        sDst[buf * ROWS + n] = Gr.mode == 0 ? Gr.ent + (static_cast<int64_t>(jj) * nv + v) * d : Gr.ent + static_cast<uint64_t>(id) * d;
+        src = T.ent + static_cast<uint64_t>(id) * T.ld;
+      }
+      sSrc[n] = src;
+    }
+  };
+  // V of the planned tile: 16-byte asynchronous copies straight into shared memory (zero rows past the tile's last group)
+  auto copy_rows = [&]() {
+    for (int idx = threadIdx.x; idx < ROWS * NC; idx += kThreads) {
+      const int n = idx / NC, c = idx - n * NC;
+      const float* src = sSrc[n];
+      float* dst = sV + n * pitch + 4 * c;
+      if (src) {
+        const uint32_t sa = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 4 * c) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int i0 = blockIdx.x * chunk, buf = 0;
+  if (wid == 0) plan(0, i0);
+  __syncthreads();
+  copy_rows();
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  while (true) {
+    const int* J = sJ + 36 * buf;
+    const int rel = J[32], ng = J[33], rows = ng * nv;
+    if (ng == 0) break;
     if (rel != cur_rel) {
       flush(cur_rel);
       cur_rel = rel;
       const float4* M4 = reinterpret_cast<const float4*>(T.proj + static_cast<uint64_t>(rel) * d * d);
       for (int idx = threadIdx.x; idx < d * NC; idx += kThreads) {
-        const int a = idx / NC, c = idx - a * NC;
-        const float4 m = __ldg(M4 + idx);
+        const int c = idx / d, a = idx - c * d;                   // lanes along a: the transposed stores are conflict-free
+        const float4 m = __ldg(M4 + a * NC + c);
         *reinterpret_cast<float4*>(sM + a * pitch + 4 * c) = m;
         sMt[(4 * c) * pitch + a] = m.x; sMt[(4 * c + 1) * pitch + a] = m.y;
         sMt[(4 * c + 2) * pitch + a] = m.z; sMt[(4 * c + 3) * pitch + a] = m.w;
@@ -1425,38 +1472,8 @@ k_run_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
         const int a = lane + 32 * i;
         rr[i] = a < d ? __ldg(T.rel + static_cast<uint64_t>(rel) * T.ld + a) : 0.f;
       }
+      __syncthreads();
     }
-    // ---- stage V: the warp's 8-row blocks; lane i finds the table row of block row i (one round of dependent index
-    //      loads for the block), then the 8 row loads are in flight together
-#pragma unroll 1
-    for (int rb = 0; rb < RB; ++rb) {
-      const int base = 8 * (wid + kWarpsPerCta * rb);
-      if (base >= rows) break;
-      int64_t id = 0;
-      if (lane < 8 && base + lane < rows) {
-        const int n = base + lane, gq = n / nv, v = n - gq * nv, j = sJ[gq];
-        if (v == 0) id = load_idx(G.ph, j, G.is64);
-        else if (v == 1) id = load_idx(G.pt, j, G.is64);
-        else { const int32_t c = __ldg(G.corrupt + static_cast<int64_t>(j) * K + (v - 2)); id = c < 0 ? ~c : c; }
-        if (slot_ent) {
-          slot_ent[static_cast<int64_t>(j) * nv + v] = id;
-          if (v == 0) slot_rel[j] = load_idx(G.pr, j, G.is64);
-        }
-        if (static_cast<uint64_t>(id) >= static_cast<uint64_t>(T.n_ent)) { bad = true; id = 0; }
-        sDst[n] = Gr.mode == 0 ? Gr.ent + (static_cast<int64_t>(j) * nv + v) * d : Gr.ent + static_cast<uint64_t>(id) * d;
-      }
-      float4 x[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int64_t idi = __shfl_sync(FULL, id, i);
-        x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < NC && base + i < rows) x[i] = ldg_f4(reinterpret_cast<const float4*>(T.ent + static_cast<uint64_t>(idi) * T.ld) + lane);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (lane < NC) *reinterpret_cast<float4*>(sV + (base + i) * pitch + 4 * lane) = x[i];       // rows past the tile: zero
-    }
-    __syncthreads();
     // ---- Y = V M^T
 #pragma unroll 1
     for (int rb = 0; rb < RB; ++rb) {
@@ -1468,7 +1485,7 @@ k_run_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
     __syncthreads();
     // ---- scores, ranking loss, G = dL/dY in place: one warp per group
     for (int gq = wid; gq < ng; gq += kWarpsPerCta) {
-      const int j = sJ[gq];
+      const int j = J[gq];
       float* Y = sG + gq * nv * pitch;
       const int32_t cv = lane < K ? __ldg(G.corrupt + static_cast<int64_t>(j) * K + lane) : 0;
       float up = up0;
@@ -1540,6 +1557,7 @@ k_run_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
       if (lane == 0) { pos_scores[j] = sp; group_loss[j] = lsum; }
       if (lane < K) neg_scores[static_cast<int64_t>(j) * K + lane] = mys;
     }
+    if (wid == kWarpsPerCta - 1) plan(buf ^ 1, i0 + ng);          // the next tile's rows, while the other warps finish their groups
     __syncthreads();
     // ---- dM += G^T V   (chunks past the row end are clamped: they accumulate values that are never flushed)
     if (mt) {
@@ -1573,21 +1591,26 @@ k_run_step_r(const GroupArgs G, const float up0, float* __restrict__ pos_scores,
         }
       }
     }
+    __syncthreads();
+    copy_rows();                                                   // V of the next tile lands while dV is computed
     // ---- dV = G M
 #pragma unroll 1
     for (int rb = 0; rb < RB; ++rb) {
       const int base = 8 * (wid + kWarpsPerCta * rb);
       if (base >= rows) break;
       const int dense = Gr.mode;
+      float* const* dstp = sDst + buf * ROWS + base;
       run_tile_dot<QF>(sG + base * pitch, sMt, d, NC, pitch, lane, [&](int i, int b, float v) {
         if (base + i < rows) {
-          float* dst = sDst[base + i] + b;
+          float* dst = dstp[i] + b;
           if (dense) atomicAdd(dst, v); else __stcs(dst, v);
         }
       });
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     i0 += ng;
+    buf ^= 1;
   }
   flush(cur_rel);
   if (bad && status) *status = 1;
@@ -1843,10 +1866,12 @@ extern "C" int kgrec_corrupt_loss_step(const kgrec_tables* tables, int model, co
     }
     const bool mg = loss_kind == KGREC_LOSS_MARGIN;
     const char* env_r = group_step_env();
-    if (tables->dim >= 32 && !(env_r && (env_r[0] == 'w' || env_r[0] == 'u'))) {
+    // short runs (fewer than ~4 groups per relation of the table): staging M_r per tile does not pay, the warp kernel stays
+    const bool long_runs = n_pos >= 4 * tables->n_rel || (env_r && env_r[0] == 'r');
+    if (tables->dim >= 32 && long_runs && !(env_r && (env_r[0] == 'w' || env_r[0] == 'u'))) {
       // the CTA-level run kernel; KGREC_GROUP_STEP=w keeps the warp-per-group kernel (A/B), =u that kernel in batch order
       const int d = tables->dim, NC = d / 4, pitch = run_pitch(d), qf = d / 32;
-      auto smem_for = [&](int rb) { return (2 * static_cast<size_t>(d) + 2 * 64 * rb) * pitch * 4 + 64 * rb * 8 + 34 * 4; };
+      auto smem_for = [&](int rb) { return (2 * static_cast<size_t>(d) + 2 * 64 * rb) * pitch * 4 + 3 * 64 * rb * 8 + 72 * 4; };
       const int rb = (NC <= 27 && smem_for(2) <= 220 * 1024) ? 2 : 1;
       const size_t smem = smem_for(rb);
       const int64_t want = (n_pos + 3) / 4;                                  // at least ~4 groups per CTA
