@@ -434,6 +434,25 @@ def run_ours(args):
             "with_device_negative_sampling_triples_per_s": n_tri / (loop_ms * 1e-3)}
         del omodel, opt, smp
 
+        # TransR (configs[1] shapes, d x d projection per relation): the relation-run step kernel through the optimizer
+        with device_init(dev):
+            rmodel = K.TransRModel(False, D, N_ENT, N_REL)
+        ropt = SparseRowOptimizer(rmodel, optimizer_type="Adagrad", lr=0.01, clip=5.0)
+        nb_r = min(nb, 32)
+        rix = [x[: nb_r * BATCH * (K_NEG if i == 3 else 1)] for i, x in enumerate(dev_sets[0])]
+
+        def transr_step():
+            ropt.step_corrupt(tuple(rix[:3]), rix[3], margin=1.0, batch_pos=BATCH)
+        tr_ms = timeit(transr_step, reps=5, warm=2)
+        n_grp = nb_r * BATCH
+        fma_grp = 3 * (2 + K_NEG) * D * D                # Y = V M^T, dM += G^T V, dV = G M over the group's 2 + K rows
+        out["train_transr"] = {
+            "what": "TransR d=%d, %d relations: counting sort by relation + k_run_step_r (M_r, M_r^T resident per run, packed-FMA "
+                    "register-tiled GEMMs) + clip + sparse-row Adagrad; %d batches of 1024 positives + %d negatives per step" % (D, N_REL, nb_r, K_NEG),
+            "ms": tr_ms, "triples_per_s": n_grp * (1 + K_NEG) / (tr_ms * 1e-3), "fma_per_group": fma_grp,
+            "frac_of_fp32_bound": n_grp / (tr_ms * 1e-3) * fma_grp / FP32_LANE_OPS}
+        del rmodel, ropt
+
         # configs[3]: KTUP joint training, ml1m-scale rec (6040 x 3706) + 500k entities, R = P = 20, joint_ratio 0.5:
         # 5 rec steps then 5 KG steps per 10 (knowledgable_recommendation.py:209,320), each step = `nb` batches of 1024
         import numpy as np

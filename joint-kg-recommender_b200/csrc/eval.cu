@@ -103,6 +103,7 @@ struct EvalArgs {
   // outputs
   float* out; int64_t ld_out;               // FULL
   uint64_t* part_keys; int k;               // TOPK: [n_splits][nq][k]
+  uint32_t* thr_glob;                       // TOPK, tiled kernels: [nq] score bits no top-K entry of the call can exceed (shared by the pieces)
   const int64_t* filter_ptr; const int32_t* filter_ids;
   const float* gold_scores; const int32_t* gold_ids; int32_t* counts;   // RANK
 };
@@ -734,12 +735,14 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     }
   };
 
-  for (int64_t g = 0; g < my_units; ++g) {
+  int since = 0;                                 // tiles since this CTA entered its current query tile
+  for (int64_t g = 0; g < my_units; ++g, ++since) {
     const int64_t u = u_begin + g;
     const int64_t qt = u / n_tiles, ti = u - qt * n_tiles;
     if (qt != cur_qt) {
       if (cur_qt >= 0) end_qtile();
       begin_qtile(qt);
+      since = 0;
     }
     const int s = static_cast<int>(g % stages);
     if (wid == 0 && g + prefetch < my_units) issue_tile(g + prefetch);
@@ -747,6 +750,13 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     const int64_t row0 = ti * TN;
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
     mbar_wait(full + s, static_cast<uint32_t>((g / stages) & 1));
+    // The K-th best score any OTHER piece of these queries has reached bounds this piece's candidates too: one L2 load
+    // per query and tile (lane qi holds query qi's), merged into the register thresholds in the epilogue.  A piece's
+    // list costs K (1 + ln(rows / K)) insertions on its own; with the shared bound the pieces of a query warm up together.
+    [[maybe_unused]] uint32_t gthr = 0xffffffffu;
+    [[maybe_unused]] const bool refresh = since < 16 || (since & 15) == 0;     // every tile while the piece's lists warm up, then every 16th
+    if constexpr (MODE == MODE_TOPK)
+      if (refresh && A.thr_glob && lane < RQ && q0 + lane < A.nq) gthr = __ldcg(A.thr_glob + q0 + lane);
 
     // accumulators hold two partial sums each (even / odd dimension of every 8-byte pair)
     f32x2 acc2[RQ][RN];
@@ -897,6 +907,8 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
 #pragma unroll
     for (int qi = 0; qi < RQ; ++qi) {
       const int64_t q = q0 + qi;
+      if constexpr (MODE == MODE_TOPK)
+        if (refresh) thr_hi[qi] = min(thr_hi[qi], __shfl_sync(FULL, gthr, qi));
       if (q >= A.nq) continue;                 // warp-uniform
 #pragma unroll
       for (int j = 0; j < RN; ++j) {
@@ -912,9 +924,14 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
           if (valid && (sb < gh || (sb == gh && id < gi))) ++cnt[qi];
         } else {
           const unsigned mask = __ballot_sync(FULL, valid && sb <= thr_hi[qi]);
-          if (mask)                              // rare once the lists have warmed up
-            thr_hi[qi] = topk_insert_candidates(mask, sb, static_cast<uint32_t>(A.id_base + row0 + 32 * j), lists + qi * A.k,
-                                                A.k, A.filter_ptr, A.filter_ids, q, lane);
+          if (mask) {                            // rare once the lists have warmed up
+            const uint32_t nt = topk_insert_candidates(mask, sb, static_cast<uint32_t>(A.id_base + row0 + 32 * j), lists + qi * A.k,
+                                                       A.k, A.filter_ptr, A.filter_ids, q, lane);
+            if (nt < thr_hi[qi]) {
+              thr_hi[qi] = nt;
+              if (A.thr_glob && lane == 0) atomicMin(A.thr_glob + q, nt);
+            }
+          }
         }
       }
     }
@@ -1101,12 +1118,14 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     }
   };
 
-  for (int64_t g = 0; g < my_units; ++g) {
+  int since = 0;                                 // tiles since this CTA entered its current query tile
+  for (int64_t g = 0; g < my_units; ++g, ++since) {
     const int64_t u = u_begin + g;
     const int64_t qt = u / n_tiles, ti = u - qt * n_tiles;
     if (qt != cur_qt) {
       if (cur_qt >= 0) end_qtile();
       begin_qtile(qt);
+      since = 0;
     }
     const int s = static_cast<int>(g % stages);
     if (threadIdx.x == 0 && g + prefetch < my_units) issue_tile(g + prefetch);
@@ -1115,6 +1134,10 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
     const int64_t row0 = ti * TN;
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
     mbar_wait(full + s, static_cast<uint32_t>((g / stages) & 1));
+    [[maybe_unused]] uint32_t gthr = 0xffffffffu;          // the bound the other pieces of these queries have reached (k_eval_tiled)
+    [[maybe_unused]] const bool refresh = since < 16 || (since & 15) == 0;
+    if constexpr (MODE == MODE_TOPK)
+      if (refresh && A.thr_glob && lane < RQ && q0 + lane < A.nq) gthr = __ldcg(A.thr_glob + q0 + lane);
 
     // pass 1: cross dots  sum_j ( U_q IB_n + I_n (-UB_q) )
     f32x2 sd2[RQ];
@@ -1166,6 +1189,8 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
 #pragma unroll
     for (int qi = 0; qi < RQ; ++qi) {
       const int64_t q = q0 + qi;
+      if constexpr (MODE == MODE_TOPK)
+        if (refresh) thr_hi[qi] = min(thr_hi[qi], __shfl_sync(FULL, gthr, qi));
       if (q >= A.nq) continue;
       const float sc = sum2(acc2[qi]);
       if constexpr (MODE == MODE_FULL) {
@@ -1173,9 +1198,14 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       } else {
         const uint32_t sb = __float_as_uint(sc);
         const unsigned mask = __ballot_sync(FULL, valid && sb <= thr_hi[qi]);
-        if (mask)
-          thr_hi[qi] = topk_insert_candidates(mask, sb, static_cast<uint32_t>(A.id_base + row0), lists + qi * A.k, A.k,
-                                              A.filter_ptr, A.filter_ids, q, lane);
+        if (mask) {
+          const uint32_t nt = topk_insert_candidates(mask, sb, static_cast<uint32_t>(A.id_base + row0), lists + qi * A.k, A.k,
+                                                     A.filter_ptr, A.filter_ids, q, lane);
+          if (nt < thr_hi[qi]) {
+            thr_hi[qi] = nt;
+            if (A.thr_glob && lane == 0) atomicMin(A.thr_glob + q, nt);
+          }
+        }
       }
     }
   }
@@ -1490,7 +1520,7 @@ using namespace kgrec;
 extern "C" int64_t kgrec_eval_workspace_bytes(int64_t nq, int32_t k) {
   // worst case number of catalog splits is 2 * SMs (eval_plan)
   const int64_t splits = 3 * static_cast<int64_t>(sm_count());
-  return splits * (nq > 0 ? nq : 1) * (k > 0 ? k : 1) * static_cast<int64_t>(sizeof(uint64_t));
+  return splits * (nq > 0 ? nq : 1) * (k > 0 ? k : 1) * static_cast<int64_t>(sizeof(uint64_t)) + 4 * (nq > 0 ? nq : 1) + 16;
 }
 
 extern "C" int kgrec_eval_scores(const kgrec_tables* tables, int model, int side, const void* q, const void* r,
@@ -1540,7 +1570,16 @@ extern "C" int kgrec_eval_topk(const kgrec_tables* tables, int model, int side, 
     return KGREC_ERR_INVALID;
   }
   A.part_keys = static_cast<uint64_t*>(workspace);
-  if (pl.tiled || pl.soft_aug) KGREC_CUDA_OK(cudaMemsetAsync(workspace, 0xff, static_cast<size_t>(need), st));   // unused pieces = empty lists
+  if (pl.tiled || pl.soft_aug) {
+    // unused pieces = empty lists; and, room permitting, the per-query bound the pieces share (0xffffffff = none yet)
+    int64_t fill = need;
+    static const bool share = [] { const char* e = getenv("KGREC_EVAL_SHARE"); return !(e && e[0] == '0'); }();
+    if (share && pl.n_splits > 1 && workspace_bytes >= need + 4 * nq) {
+      A.thr_glob = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(workspace) + need);
+      fill = need + 4 * nq;
+    }
+    KGREC_CUDA_OK(cudaMemsetAsync(workspace, 0xff, static_cast<size_t>(fill), st));
+  }
   if ((rc = launch_eval<MODE_TOPK>(A, pl, st))) return rc;
   return kgrec_merge_topk(A.part_keys, pl.n_splits, nq, k, out_keys, stream);
 }

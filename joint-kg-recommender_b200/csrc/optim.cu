@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(256) k_rows_mark(const MarkArgs A, int32_t* st
 struct SweepArgs {
   kgrec_opt_table tab[kMaxOptTables];
   int64_t chunk_begin[kMaxOptTables + 1];    // prefix sums of ceil(rows / 32)
+  int32_t div[kMaxOptTables];                // sweep rows per table row (wide rows are swept in segments)
   int n_tabs;
   int32_t epoch;
   int kind;
@@ -82,7 +83,7 @@ __device__ __forceinline__ void sweep_rows(const SweepArgs& A, F&& f) {
     const int64_t row0 = (c - A.chunk_begin[t]) * 32;
     const int64_t row = row0 + lane;
     bool mine = row < T.rows;
-    if (mine && T.marks) mine = __ldg(T.marks + row) == A.epoch;
+    if (mine && T.marks) mine = __ldg(T.marks + row / A.div[t]) == A.epoch;
     unsigned m = __ballot_sync(FULL, mine);
     while (m) {
       int64_t rows[kRowsInFlight];
@@ -214,6 +215,12 @@ static int sweep_args(const kgrec_opt_table* tabs, int n_tabs, int32_t epoch, in
             (!T.table || reinterpret_cast<uintptr_t>(T.table) % 16 == 0) &&
             (!T.state1 || reinterpret_cast<uintptr_t>(T.state1) % 16 == 0) &&
             (!T.state2 || reinterpret_cast<uintptr_t>(T.state2) % 16 == 0);
+    // wide rows (TransR's d x d matrices: 10^4 floats per row, a few hundred rows) are swept as rows of a segment each, or
+    // a handful of warps would walk the whole table
+    A.div[t] = 1;
+    if (T.dim > 512)
+      for (int seg = 512; seg >= 64; seg -= 4)
+        if (T.dim % seg == 0) { A.div[t] = T.dim / seg; T.rows *= A.div[t]; T.dim = seg; break; }
     A.tab[t] = T;
     A.chunk_begin[t + 1] = A.chunk_begin[t] + (T.rows + 31) / 32;
   }

@@ -33,3 +33,10 @@ for nb, n_rel in ((32, 500), (32, 20), (1, 500), (1, 20)):
     a = t(step)
     b = t(generic) if nb == 32 and n_rel == 500 else float("nan")
     print(f"batches {nb:3d} relations {n_rel:4d}: group step {a:.3f} ms ({n_tri / a * 1e3:.3g} triples/s)   generic fwd+bwd: {b:.3f} ms")
+# the whole training step through the optimizer (clip + sparse-row Adagrad; the d x d matrices are swept in segments)
+from kgrec_b200.optim import SparseRowOptimizer
+ix = [x.to(dev) for x in bench.make_indices(torch, gen, 32)]
+m = K.TransRModel(False, 100, 100_000, 500)
+opt = SparseRowOptimizer(m, optimizer_type="Adagrad", lr=0.01, clip=5.0)
+a = t(lambda: opt.step_corrupt(tuple(ix[:3]), ix[3], margin=1.0, batch_pos=1024))
+print(f"optimizer step, batches 32 relations 500: {a:.3f} ms")

@@ -598,6 +598,60 @@ def test_transr_group_step(Kn, l1, loss, param):
             assert torch.allclose(got[k], want[k], rtol=3e-3, atol=3e-4 * max(1.0, float(want[k].abs().max()))), (k, gm)
 
 
+@pytest.mark.parametrize("d,R,n_pos", [(32, 5, 300), (36, 5, 300), (64, 3, 257), (68, 5, 300), (96, 4, 300), (108, 5, 211),
+                                       (112, 5, 300), (128, 6, 403), (100, 1, 97), (100, 200, 403), (20, 4, 300)])
+def test_transr_run_kernel_shapes(d, R, n_pos):
+    """The relation-run TransR step (k_run_step_r) over its tile configurations -- d < 64 / d <= 108 / d <= 128 dM tiles,
+    d % 32 != 0 remainder rows, 64- and 128-row tiles, a single relation, runs cut by the chunk ends -- and the shapes that
+    keep the warp kernel (fewer than 4 groups per relation; d < 32), against the generic kernels on the expanded triples."""
+    import kgrec_b200 as K
+    torch.manual_seed(d)
+    rng = np.random.RandomState(d + R)
+    E, Kn, bp = 500, 3, 100
+    m = K.TransRModel(False, d, E, R)
+    h, t, r = rng.randint(0, E, n_pos), rng.randint(0, E, n_pos), rng.randint(0, R, n_pos)
+    ce = rng.randint(0, E, n_pos * Kn)
+    head = rng.rand(n_pos * Kn) < 0.5
+    corrupt = torch.as_tensor(np.where(head, ~ce, ce).astype(np.int32), device=dev())
+    nh = np.where(head, ce, np.repeat(h, Kn))
+    nt = np.where(head, np.repeat(t, Kn), ce)
+    pos, neg = (lt(h), lt(t), lt(r)), (lt(nh), lt(nt), lt(np.repeat(r, Kn)))
+    m.grad_mode = "dense"
+    m.zero_grad()
+    l, ps, ns = m.rank_loss(pos, neg, margin=1.0, batch_pos=bp)
+    l.sum().backward()
+    want = {k: v.clone() for k, v in grads_by_name(m).items()}
+    for gm in ("dense", "sparse"):
+        m.grad_mode = gm
+        m.zero_grad()
+        sl, sp, sn = m.loss_step_corrupt(pos, corrupt, margin=1.0, batch_pos=bp)
+        assert torch.allclose(sp, ps, rtol=2e-4, atol=1e-5) and torch.allclose(sn, ns, rtol=2e-4, atol=1e-5)
+        assert torch.allclose(sl, l, rtol=2e-4, atol=1e-4)
+        got = grads_by_name(m)
+        for k in want:
+            assert torch.allclose(got[k], want[k], rtol=3e-3, atol=3e-4 * max(1.0, float(want[k].abs().max()))), (k, gm)
+    m.check_indices()
+
+
+def test_transr_run_kernel_reports_bad_ids():
+    """An out-of-range relation or entity id in the relation-run step is clamped to row 0 and reported
+    through the status word (check_indices raises), like in the other kernels."""
+    import kgrec_b200 as K
+    rng = np.random.RandomState(1)
+    E, R, n_pos, Kn = 300, 4, 128, 2
+    for what in ("rel", "ent", "corrupt"):
+        m = K.TransRModel(False, 64, E, R)
+        m.grad_mode = "dense"
+        h, t, r = rng.randint(0, E, n_pos), rng.randint(0, E, n_pos), rng.randint(0, R, n_pos)
+        ce = rng.randint(0, E, n_pos * Kn).astype(np.int32)
+        if what == "rel": r[17] = R + 3
+        elif what == "ent": t[5] = E
+        else: ce[9] = E + 11
+        m.loss_step_corrupt((lt(h), lt(t), lt(r)), torch.as_tensor(ce, device=dev()), margin=1.0, batch_pos=n_pos)
+        with pytest.raises(IndexError):
+            m.check_indices()
+
+
 def test_rank_loss_step_other_shapes():
     """kgrec_rank_loss_step outside the single-pass kernel's shapes (KG model; many negatives) falls
     back to forward + backward kernels behind the same call."""
