@@ -309,7 +309,7 @@ k_eval(const EvalArgs A) {
     const float* tile = tiles + static_cast<size_t>(s) * tn * ld;
     const int64_t row0 = (tile0 + t) * tn;
     const int rows = static_cast<int>(min(static_cast<int64_t>(tn), A.n_cat - row0));
-    if (threadIdx.x == 0 && t + kPrefetch < my_tiles) issue_tile(t + kPrefetch);
+    if (lane == 0 && wid == static_cast<int>(t % kWarpsPerCta) && t + kPrefetch < my_tiles) issue_tile(t + kPrefetch);   // rotating issue duty
     __syncwarp();
     mbar_wait(full + s, static_cast<uint32_t>((t / kStages) & 1));
 
@@ -745,7 +745,7 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       since = 0;
     }
     const int s = static_cast<int>(g % stages);
-    if (wid == 0 && g + prefetch < my_units) issue_tile(g + prefetch);
+    if (wid == static_cast<int>(g % kTiledWarps) && g + prefetch < my_units) issue_tile(g + prefetch);   // the issue duty rotates: no warp is always the late one
     const float* tile = tiles + static_cast<size_t>(s) * TN * pitch;
     const int64_t row0 = ti * TN;
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
@@ -1067,7 +1067,7 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
   }
   __syncthreads();
   if (my_units <= 0) return;
-  auto issue_tile = [&](int64_t g) {          // lane 0 of warp 0
+  auto issue_tile = [&](int64_t g) {          // lane 0 of the warp whose turn it is
     const int s = static_cast<int>(g % stages);
     const int64_t row0 = ((u_begin + g) % n_tiles) * TN;
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
@@ -1128,7 +1128,7 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       since = 0;
     }
     const int s = static_cast<int>(g % stages);
-    if (threadIdx.x == 0 && g + prefetch < my_units) issue_tile(g + prefetch);
+    if (lane == 0 && wid == static_cast<int>(g % W) && g + prefetch < my_units) issue_tile(g + prefetch);   // rotating issue duty
     __syncwarp();
     const float* xr = tiles + static_cast<size_t>(s) * TN * lda + lane * lda;   // this lane's catalog row
     const int64_t row0 = ti * TN;
