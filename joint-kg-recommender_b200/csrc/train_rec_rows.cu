@@ -490,6 +490,8 @@ struct GumbelPairs {
   float *pos_scores, *neg_scores, *group_loss;
   int32_t* status;
   kgrec_tables T; int ktup;
+  float* reg_loss;                 // TUP driver's normLoss over cat[u], cat[pos items, neg items] (item_recommendation.py:177-179), or NULL
+  float reg_scale;
 };
 
 __global__ void __launch_bounds__(kThreads, 4)
@@ -539,6 +541,9 @@ k_gumbel_pairs(const GumbelPairs A) {
     float4 u = z4;
     if (act) u = ld4(A.xu + iu * A.ldu + 4 * lane);
     const float au = kl ? __ldg(A.a_u + iu * P + lane) : 0.f, cu = kl ? __ldg(A.cn_u + iu * P + lane) : 0.f;
+    const bool reg = A.reg_loss != nullptr;
+    const float n2u = reg ? warp_sum(dot4(u, u)) : 0.f;
+    float reg_sum = (reg && n2u > 1.f) ? n2u - 1.f : 0.f, my_n2 = 0.f;
     // Gumbel noise of the whole group, [K + 1][P]: explicit uniforms (parity runs), or ONE Philox block per four values
     // (all members at once: a Philox call is a warp-wide instruction stream, so it is spent on the group, not per member)
     __syncwarp();
@@ -571,8 +576,10 @@ k_gumbel_pairs(const GumbelPairs A) {
       float4 x = z4, r = z4, w = z4;
       if (act) { x = ld4(A.xi + id * A.ldi + 4 * lane); r = ld4(sR + ks * d + 4 * lane); w = ld4(sW + ks * d + 4 * lane); }
       const float4 e = axpy4(-s, w, add4(sub4(u, x), r));
-      const float sc = warp_sum(dot4(e, e));
-      if (lane == m) { my_score = sc; my_s = s; my_k = ks; }
+      float sc = dot4(e, e), n2x = reg ? dot4(x, x) : 0.f;
+      if (reg) warp_sum2(sc, n2x); else sc = warp_sum(sc);
+      if (reg && n2x > 1.f) reg_sum += n2x - 1.f;
+      if (lane == m) { my_score = sc; my_s = s; my_k = ks; my_n2 = n2x; }
     }
     const float sp = __shfl_sync(FULL, my_score, 0);
     const float up = A.grad_loss * loss_batch_scale(A.L, j);
@@ -587,8 +594,17 @@ k_gumbel_pairs(const GumbelPairs A) {
     float gzu = 0.f;
     for (int m = 0; m <= K; ++m) {
       const float g = __shfl_sync(FULL, my_g, m);
-      if (g == 0.f) continue;
+      const bool regx = reg && __shfl_sync(FULL, my_n2, m) > 1.f;
+      if (g == 0.f && !regx) continue;
       const int64_t id = __shfl_sync(FULL, idm, m);
+      if (g == 0.f) {              // inactive hinge, row outside the unit ball: the regulariser's gradient only
+        if (act) {
+          const float4 x = ld4(A.xi + id * A.ldi + 4 * lane);
+          const float c = 2.f * A.reg_scale;
+          red_add_f4(A.gx_i + id * d + 4 * lane, c * x.x, c * x.y, c * x.z, c * x.w);
+        }
+        continue;
+      }
       const int ks = __shfl_sync(FULL, my_k, m);
       const float s = __shfl_sync(FULL, my_s, m);
       const float ax = kl ? __ldg(A.a_i + id * P + lane) : 0.f, cx = kl ? __ldg(A.cn_i + id * P + lane) : 0.f;
@@ -619,7 +635,11 @@ k_gumbel_pairs(const GumbelPairs A) {
       }
       gu = add4(gu, gx);
       gzu += gz;
-      if (act) red_add_f4(A.gx_i + id * d + 4 * lane, -gx.x, -gx.y, -gx.z, -gx.w);
+      if (act) {
+        float4 gxi = make_float4(-gx.x, -gx.y, -gx.z, -gx.w);
+        if (regx) gxi = axpy4(2.f * A.reg_scale, x, gxi);
+        red_add_f4(A.gx_i + id * d + 4 * lane, gxi.x, gxi.y, gxi.z, gxi.w);
+      }
       if (lane < 4) {   // one-hot table gradients: eight scalars instead of two d-wide rows (lanes 0/1: user ck/dk, 2/3: item)
         const float c1 = g2 * hf, t2 = fmaf(hf, ew, s * c1);
         const bool usr = lane < 2, isd = lane & 1;
@@ -631,6 +651,8 @@ k_gumbel_pairs(const GumbelPairs A) {
       }
       if (kl) atomicAdd(A.gz_i + id * P + lane, gz);
     }
+    if (reg && n2u > 1.f) gu = axpy4(2.f * A.reg_scale, u, gu);
+    if (reg && lane == 0 && reg_sum != 0.f) atomicAdd(A.reg_loss, A.reg_scale * reg_sum);
     if (act) red_add_f4(A.gx_u + iu * d + 4 * lane, gu.x, gu.y, gu.z, gu.w);
     if (kl && gzu != 0.f) atomicAdd(A.gz_u + iu * P + lane, gzu);
   }
@@ -781,7 +803,7 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
   auto gridt = [&](int64_t rows) { const int64_t g = (rows + 31) / 32; return static_cast<int>(g < 1 ? 1 : (g < tcap ? g : tcap)); };
   const int64_t n_batches = (n_pos + batch_pos - 1) / batch_pos;
   if (T.use_gumbel) {
-    if (norm_reg_loss) { set_error("rec_rows_step: the fused row-norm regulariser goes with the soft path"); return KGREC_ERR_UNSUPPORTED; }
+    if (norm_reg_loss && ktup) { set_error("rec_rows_step: the row-norm regulariser is the TUP driver's (item_recommendation.py:177-179)"); return KGREC_ERR_UNSUPPORTED; }
     GumbelRows GU{}, GI{};
     GU.table = T.user; GI.table = T.item;
     GU.a = take(nu * P); GU.cn = take(nu * P); GU.gz = take(nu * P); GU.ck = take(2 * nu * P);
@@ -821,6 +843,7 @@ extern "C" int kgrec_rec_rows_step(const kgrec_tables* tables, int model, const 
     A.acc_pref = acc->pref; A.acc_pref_norm = acc->pref_norm; A.gram = gram; A.gumbel_u = gumbel_u; A.seed = seed;
     A.pos_scores = pos_scores; A.neg_scores = neg_scores; A.group_loss = static_cast<float*>(loss_workspace);
     A.status = status; A.T = T; A.ktup = ktup ? 1 : 0;
+    A.reg_loss = norm_reg_loss; A.reg_scale = 1.f;
     const size_t smem_p = (static_cast<size_t>(2) * P * d + 4 * static_cast<size_t>(P) + 3 * static_cast<size_t>(P) * P +
                            static_cast<size_t>(kWarpsPerCta) * (n_neg + 1) * P) * sizeof(float);
     KGREC_CUDA_OK(cudaFuncSetAttribute(k_gumbel_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_p)));

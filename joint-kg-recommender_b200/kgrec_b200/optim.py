@@ -206,7 +206,7 @@ class SparseRowOptimizer:
                 C.byref(T), m.MODEL, ptr(pu), ptr(pi), ptr(ni), idx_bytes, n_pos, n_neg, bp, kind, float(target), 1.0,
                 ptr(self.marks["user"]), ptr(self.marks["item"]), self.t, ptr(self._rows_ws), first, C.byref(g),
                 ptr(pos_s), ptr(neg_s), ptr(out), ptr(ws),
-                ptr(self.reg_loss) if (reg and not ktup and not m.use_st_gumbel) else None,
+                ptr(self.reg_loss) if (reg and not ktup) else None,
                 ptr(gumbel_u), seed, ptr(m._status_buf(dev)), stream))
             KF.count_launches(8)
         else:
@@ -226,7 +226,7 @@ class SparseRowOptimizer:
             KF.count_launches(1)
             if not ktup:
                 status = ptr(m._status_buf(dev))
-                fused = rows_path and not m.use_st_gumbel          # soft rows path: fused into its pair kernel
+                fused = rows_path                                  # rows path: normLoss of the gathered rows is fused into its pair kernel
                 for tab, ids in (() if fused else (("user", pu), ("item", pi), ("item", ni))):
                     _lib.check(lib.kgrec_reg_norm_rows(ptr(w[tab]), w[tab].shape[0], d, ptr(ids), ids.element_size(),
                                                        ids.numel(), 1.0, ptr(self.reg_loss), ptr(self.acc[tab]), status, stream))
