@@ -103,6 +103,7 @@ struct EvalArgs {
   // outputs
   float* out; int64_t ld_out;               // FULL
   uint64_t* part_keys; int k;               // TOPK: [n_splits][nq][k]
+  int rotate;                               // tile-issue duty rotates over the warps (0: warp 0 issues; KGREC_EVAL_ROTATE=0, A/B)
   uint32_t* thr_glob;                       // TOPK, tiled kernels: [nq] score bits no top-K entry of the call can exceed (shared by the pieces)
   const int64_t* filter_ptr; const int32_t* filter_ids;
   const float* gold_scores; const int32_t* gold_ids; int32_t* counts;   // RANK
@@ -309,7 +310,7 @@ k_eval(const EvalArgs A) {
     const float* tile = tiles + static_cast<size_t>(s) * tn * ld;
     const int64_t row0 = (tile0 + t) * tn;
     const int rows = static_cast<int>(min(static_cast<int64_t>(tn), A.n_cat - row0));
-    if (lane == 0 && wid == static_cast<int>(t % kWarpsPerCta) && t + kPrefetch < my_tiles) issue_tile(t + kPrefetch);   // rotating issue duty
+    if (threadIdx.x == 0 && t + kPrefetch < my_tiles) issue_tile(t + kPrefetch);
     __syncwarp();
     mbar_wait(full + s, static_cast<uint32_t>((t / kStages) & 1));
 
@@ -745,7 +746,7 @@ k_eval_tiled(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       since = 0;
     }
     const int s = static_cast<int>(g % stages);
-    if (wid == static_cast<int>(g % kTiledWarps) && g + prefetch < my_units) issue_tile(g + prefetch);   // the issue duty rotates: no warp is always the late one
+    if (wid == (A.rotate ? static_cast<int>(g % kTiledWarps) : 0) && g + prefetch < my_units) issue_tile(g + prefetch);   // the issue duty rotates: no warp is always the late one
     const float* tile = tiles + static_cast<size_t>(s) * TN * pitch;
     const int64_t row0 = ti * TN;
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
@@ -1067,7 +1068,7 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
   }
   __syncthreads();
   if (my_units <= 0) return;
-  auto issue_tile = [&](int64_t g) {          // lane 0 of the warp whose turn it is
+  auto issue_tile = [&](int64_t g) {          // lane 0 of warp 0
     const int s = static_cast<int>(g % stages);
     const int64_t row0 = ((u_begin + g) % n_tiles) * TN;
     const int rows = static_cast<int>(min(static_cast<int64_t>(TN), A.n_cat - row0));
@@ -1128,7 +1129,7 @@ k_eval_soft(const EvalArgs A, const int stages, const int64_t units_per_cta) {
       since = 0;
     }
     const int s = static_cast<int>(g % stages);
-    if (lane == 0 && wid == static_cast<int>(g % W) && g + prefetch < my_units) issue_tile(g + prefetch);   // rotating issue duty
+    if (threadIdx.x == 0 && g + prefetch < my_units) issue_tile(g + prefetch);   // (rotating the duty as in k_eval_tiled LOSES here: 7.3 -> 9.6 ms)
     __syncwarp();
     const float* xr = tiles + static_cast<size_t>(s) * TN * lda + lane * lda;   // this lane's catalog row
     const int64_t row0 = ti * TN;
@@ -1317,6 +1318,11 @@ struct EvalPlan {
   int64_t units_per_cta;
 };
 
+static int eval_rotate() {
+  static const int v = [] { const char* e = getenv("KGREC_EVAL_ROTATE"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v;
+}
+
 static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const float* cat, int64_t cat_ld,
                      int64_t nq, int64_t n_cat, int k, bool have_qvec, EvalArgs* A, EvalPlan* pl) {
   if (!T) { set_error("tables is NULL"); return KGREC_ERR_INVALID; }
@@ -1369,7 +1375,7 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
     pl->units_per_cta = (total_units + ctas - 1) / ctas;
     pl->grid = static_cast<int>((total_units + pl->units_per_cta - 1) / pl->units_per_cta);
     pl->n_splits = static_cast<int>((n_tiles_t + pl->units_per_cta - 1) / pl->units_per_cta + 1);
-    A->T = *T; A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
+    A->T = *T; A->rotate = eval_rotate(); A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
     A->n_splits = pl->n_splits; A->tn = tn_t; A->k = k;
     return KGREC_OK;
   }
@@ -1395,7 +1401,7 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
     pl->units_per_cta = (total_units + ctas - 1) / ctas;
     pl->grid = static_cast<int>((total_units + pl->units_per_cta - 1) / pl->units_per_cta);
     pl->n_splits = static_cast<int>((n_tiles_t + pl->units_per_cta - 1) / pl->units_per_cta + 1);
-    A->T = *T; A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
+    A->T = *T; A->rotate = eval_rotate(); A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
     A->n_splits = pl->n_splits; A->tn = 32; A->k = k;
     return KGREC_OK;
   }
@@ -1432,7 +1438,7 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
     pl->grid = static_cast<int>((total_units + pl->units_per_cta - 1) / pl->units_per_cta);
     // pieces of partial top-K lists per query tile: CTAs whose ranges touch one query tile
     pl->n_splits = static_cast<int>((n_tiles_t + pl->units_per_cta - 1) / pl->units_per_cta + 1);
-    A->T = *T; A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
+    A->T = *T; A->rotate = eval_rotate(); A->side = side; A->nq = nq; A->cat = cat; A->cat_ld = cat_ld; A->n_cat = n_cat;
     A->n_splits = pl->n_splits; A->tn = tn_t; A->k = k;
     return KGREC_OK;
   }
@@ -1449,7 +1455,7 @@ static int eval_plan(const kgrec_tables* T, int model, int side, int mode, const
   pl->n_splits = static_cast<int>(splits);
   pl->smem = eval_smem_layout(pl->kind, mode, d, cat_ld, T->n_pref, tn, k).total;
   if (pl->smem > 220 * 1024) { set_error("eval: shared-memory budget exceeded (%zu bytes)", pl->smem); return KGREC_ERR_UNSUPPORTED; }
-  A->T = *T;
+  A->T = *T; A->rotate = eval_rotate();
   A->side = side;
   A->nq = nq;
   A->cat = cat;
