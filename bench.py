@@ -386,6 +386,7 @@ def run_ours(args):
         os.environ["KGREC_REC_ROWS"] = "0"
         soft_pairs_ms = timeit(tup_soft_step)
         os.environ.pop("KGREC_REC_ROWS")
+        tables_finite = all(bool(torch.isfinite(v).all()) for v in tm._weights().values())   # after ~30 optimizer steps of both kinds
         del tm, soft_cat, topt
         out["regions"] = reg
         out["train_rec"] = {"tup_st_gumbel": {"ms": tup_ms, "pairs_per_s": 2 * n_pos / (tup_ms * 1e-3), "fma_per_pair": 14000,
@@ -394,6 +395,7 @@ def run_ours(args):
                                                                 "ST-Gumbel, L2, 50k users x 50k items, %d positives + 1 negative each" % n_pos,
                                                         "row_factored_ms": gum_rows_ms, "pair_kernel_ms": gum_pairs_ms,
                                                         "pairs_per_s": 2 * n_pos / (gum_rows_ms * 1e-3)},
+                            "tables_finite_after_training": tables_finite,
                             "tup_soft_full_step": {"what": "forward + BPR + backward + regularisers + clip + sparse-row Adagrad, 50k users x 50k items, "
                                                            "%d positives + 1 negative each" % n_pos,
                                                    "row_factored_ms": soft_rows_ms, "pair_kernel_ms": soft_pairs_ms,

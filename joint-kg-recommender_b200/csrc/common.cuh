@@ -334,8 +334,11 @@ __device__ __forceinline__ float gumbel_from_uniform(float u) {
 // In-kernel draws (no caller-supplied uniforms to reproduce): u in (0,1) strictly, so the two
 // eps terms of the reference formula are not needed and the logs can be the 2-instruction
 // lg2.approx form.  Same distribution; used only when the noise is generated on the device.
+// 23 bits, not 24: n + 0.5 must be exact in fp32.  With bits >> 8 the top value 16777215.5 rounds to 2^24, u = 1, the
+// noise +inf -- one draw in 2^24, i.e. a few per training step at configs[2] sizes -- and exp(inf - inf) in the
+// straight-through soft-max turns the step's gradients, then the tables, into NaN.
 __device__ __forceinline__ float gumbel_fast(uint32_t bits) {
-  const float u = (static_cast<float>(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+  const float u = (static_cast<float>(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);   // (0, 1) strictly
   return -__logf(-__logf(u));
 }
 

@@ -298,3 +298,16 @@ def test_vocab_and_alignment_loaders_match_the_reference(tmp_path):
     got = build_item2ent(item_total, pad, ds.i_remap, ds.ikg_map).tolist()
     assert got == want_table
     assert sum(1 for e in got if e != pad) == ds.aligned == info["aligned"]
+
+
+def test_device_gumbel_uniform_stays_inside_the_unit_interval():
+    """common.cuh gumbel_fast: u = (float(bits >> 9) + 0.5) * 2^-23 in fp32.  With 24 bits (bits >> 8) the top value
+    16777215.5 is not representable, rounds to 2^24 and gives u = 1.0 -> noise +inf -> NaN gradients about once per
+    2^24 draws (a few per configs[2] training step).  The fp32 arithmetic restated in numpy for the edge inputs."""
+    f = np.float32
+    for bits in (0, 1, 0x1ff, 0x200, 0x7fffffff, 0xfffffdff, 0xfffffe00, 0xffffffff):
+        u = (f(bits >> 9) + f(0.5)) * f(1.0 / 8388608.0)
+        assert f(0.0) < u < f(1.0), (bits, u)
+        g = -np.log(-np.log(u.astype(np.float64)))
+        assert np.isfinite(g)
+    assert (f(0xffffffff >> 8) + f(0.5)) * f(1.0 / 16777216.0) == f(1.0)       # the 24-bit form that was shipped before
