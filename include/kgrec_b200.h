@@ -385,7 +385,9 @@ int kgrec_eval_scores(const kgrec_tables* tables, int model, int side,
  * lexicographic.  filter_ptr / filter_ids: optional CSR (ptr [nq+1], ascending global ids)
  * of catalog ids to skip per query (train + other eval files' positives,
  * item_recommendation.py:108-111).  out_keys: [nq, k] uint64 = score bits << 32 | global id,
- * ascending; unused places hold UINT64_MAX.  workspace: kgrec_eval_workspace_bytes(nq, k). */
+ * ascending; unused places hold UINT64_MAX.  workspace: kgrec_eval_workspace_bytes(nq, k) -- the
+ * per-range partial lists plus [nq] uint32 score bits through which the ranges of a query share
+ * their current K-th best (a range skips rows no other range would keep either). */
 int64_t kgrec_eval_workspace_bytes(int64_t nq, int32_t k);
 int kgrec_eval_topk(const kgrec_tables* tables, int model, int side,
                     const void* q, const void* r, int idx_bytes, const float* qvec, int64_t nq,
