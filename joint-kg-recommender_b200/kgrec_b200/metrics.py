@@ -45,10 +45,17 @@ def _kg_side(model, side, eval_dict, all_dicts, topn, batch):
     """[(hit, rank)] for every (query, gold id) of one side.  eval_dict: {(q, r): set(gold)}."""
     dev = model._require_cuda()
     from . import _lib
-    if model.MODEL == _lib.TRANSR:
-        raise NotImplementedError("evaluate_kg: TransR ranks go through evaluateHead / evaluateTail")
     kg = _lib.TRANSH if model.MODEL == _lib.KTUP else model.MODEL
     sd = _lib.SIDE_HEAD if side == "head" else _lib.SIDE_TAIL
+    transr = model.MODEL == _lib.TRANSR
+
+    def sub_scores(qq, rr, rows, ids):
+        """[len(qq), len(ids)] scores against gathered catalog rows, by the catalog pass's own arithmetic (bit-identical
+        to the scores the rank-count kernel compares).  TransR projects the gathered rows per distinct relation
+        (TransRModel._scores -> csrc/eval_transr.cu)."""
+        if transr:
+            return model._scores(sd, qq, rr, catalog=rows, cat_ids=ids)
+        return model._eval(kg, sd, qq, rr, "scores", catalog=rows, cat_ids=ids)
     queries = [k for k, gold in eval_dict.items() if len(gold) > 0]
     results = []
     catalog = model.ent_embeddings.weight.detach()
@@ -77,10 +84,11 @@ def _kg_side(model, side, eval_dict, all_dicts, topn, batch):
         gs = torch.empty(gt.numel(), dtype=torch.float32, device=dev)
         for glo in range(0, gt.numel(), 512):
             ghi = min(gt.numel(), glo + 512)
-            blk = model._eval(kg, sd, q[glo:ghi], r[glo:ghi], "scores", catalog=catalog[gt[glo:ghi]].contiguous(),
-                              cat_ids=gt[glo:ghi])
-            gs[glo:ghi] = blk.diagonal()
-        counts = model._eval(kg, sd, q, r, "rank", catalog=catalog, gold_scores=gs, gold_ids=gt).to(torch.int64)
+            gs[glo:ghi] = sub_scores(q[glo:ghi], r[glo:ghi], catalog[gt[glo:ghi]].contiguous(), gt[glo:ghi]).diagonal()
+        if transr:
+            counts = model.rank_counts(side, q, r, gt, gold_scores=gs).to(torch.int64)
+        else:
+            counts = model._eval(kg, sd, q, r, "rank", catalog=catalog, gold_scores=gs, gold_ids=gt).to(torch.int64)
         # correction: filtered ids and the other gold ids that sort before the gold do not count.
         # Their scores come from the same evaluation kernel on the gathered rows (bit-identical).
         flat_row = torch.tensor([i for i, e in enumerate(excl) for _ in e], dtype=torch.int64, device=dev)
@@ -94,7 +102,7 @@ def _kg_side(model, side, eval_dict, all_dicts, topn, batch):
                 sel = (flat_row >= qlo) & (flat_row < qhi)
                 if not bool(sel.any()):
                     continue
-                m = model._eval(kg, sd, q[qlo:qhi], r[qlo:qhi], "scores", catalog=sub, cat_ids=uniq)
+                m = sub_scores(q[qlo:qhi], r[qlo:qhi], sub, uniq)
                 rr, cc = flat_row[sel] - qlo, inv[sel]
                 s_e = m[rr, cc]
                 s_g, i_g = gs[flat_row[sel]], gt[flat_row[sel]]

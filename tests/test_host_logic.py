@@ -311,3 +311,94 @@ def test_device_gumbel_uniform_stays_inside_the_unit_interval():
         g = -np.log(-np.log(u.astype(np.float64)))
         assert np.isfinite(g)
     assert (f(0xffffffff >> 8) + f(0.5)) * f(1.0 / 16777216.0) == f(1.0)       # the 24-bit form that was shipped before
+
+
+class _FakeKGEngine:
+    """Stands in for a model's evaluation kernels in the host-logic test of kgrec_b200.metrics: the same entry points
+    `_kg_side` calls (`_eval` for TransE / TransH / KTUP, `_scores` + `rank_counts` for TransR), answered on the CPU
+    from one fixed [n_query_keys, n_ent] score table looked up by (q, r) -- every (query, row) score is the same number
+    wherever the row sits, which is the property the real kernels guarantee (bit-identical scores on gathered rows)."""
+
+    def __init__(self, model_const, scores_by_key, n_ent, n_rel):
+        import types
+        self.MODEL = model_const
+        self.table = scores_by_key                        # {(q, r): float32 [n_ent]}
+        self.ent_embeddings = types.SimpleNamespace(weight=torch.arange(n_ent, dtype=torch.float32).view(-1, 1))
+        self.calls = {"_eval": 0, "_scores": 0, "rank_counts": 0}
+
+    def _require_cuda(self):
+        return torch.device("cpu")
+
+    def _rows(self, q, r, cols):
+        return torch.from_numpy(np.stack([self.table[(int(a), int(b))][cols] for a, b in zip(q.tolist(), r.tolist())]))
+
+    def _eval(self, kg, sd, q, r, mode, catalog=None, cat_ids=None, gold_scores=None, gold_ids=None):
+        self.calls["_eval"] += 1
+        if mode == "scores":                               # gathered sub-catalog: its first column carries the row ids
+            assert torch.equal(catalog[:, 0].long(), cat_ids.long())
+            return self._rows(q, r, cat_ids.numpy())
+        assert mode == "rank" and catalog.shape[0] == self.ent_embeddings.weight.shape[0]
+        return self._count(q, r, gold_scores, gold_ids)
+
+    def _scores(self, sd, q, r, catalog=None, id_base=0, cat_ids=None):
+        self.calls["_scores"] += 1
+        assert torch.equal(catalog[:, 0].long(), cat_ids.long())
+        return self._rows(q, r, cat_ids.numpy())
+
+    def rank_counts(self, side, q, r, gold_ids, gold_scores=None):
+        self.calls["rank_counts"] += 1
+        assert side in ("head", "tail")
+        return self._count(q, r, gold_scores, gold_ids)
+
+    def _count(self, q, r, gs, gi):
+        full = self._rows(q, r, slice(None)).numpy()
+        ids = np.arange(full.shape[1])
+        g, i = gs.numpy()[:, None], gi.numpy()[:, None]
+        return torch.from_numpy(((full < g) | ((full == g) & (ids[None, :] < i))).sum(1).astype(np.int32))
+
+
+@pytest.mark.parametrize("family", ["TRANSE", "TRANSR"])
+def test_driver_level_kg_metrics_host_logic(family):
+    """kgrec_b200.metrics.evaluate_kg: rank = on-chip count of everything sorting before the gold, minus the filtered
+    ids and the other gold ids among them; gold ids inside the filter set are skipped; ties by (score, id).  Host
+    arithmetic only, against the reference's walk (oracle restatement of utils/misc.py:125-146) on scores WITH ties;
+    the TransR branch goes through TransRModel's own entry points (native per-relation projection on the GPU)."""
+    from kgrec_b200 import _lib, metrics as KM
+    rng = np.random.RandomState(4)
+    E, R, topn = 120, 3, 5
+
+    def rand_dict(n_keys):
+        out = {}
+        while len(out) < n_keys:
+            out[(int(rng.randint(0, E)), int(rng.randint(0, R)))] = set(int(x) for x in rng.choice(E, rng.randint(1, 4), replace=False))
+        return out
+    head_eval, tail_eval = rand_dict(20), rand_dict(25)
+    head_eval[(E + 5, 0)] = set()                                   # empty gold set: skipped (misc.py:169)
+    # few distinct values -> many exact ties
+    table = {k: (rng.randint(0, 12, E) / 4).astype(np.float32) for k in list(head_eval) + list(tail_eval)}
+    head_all = [{k: set(int(x) for x in rng.choice(E, 10, replace=False)) for k in list(head_eval)[::2]}]
+    tail_all = [{k: set(int(x) for x in rng.choice(E, 20, replace=False)) for k in list(tail_eval)[::3]}, {}]
+    k0 = next(iter(tail_eval))
+    tail_all[1][k0] = {next(iter(tail_eval[k0]))}                   # a gold id that is itself filtered
+    eng = _FakeKGEngine(getattr(_lib, family), table, E, R)
+    got = KM.evaluate_kg(eng, head_eval, tail_eval, head_all, tail_all, topn=topn, batch=7)
+    want = {}
+    for side, ev, alld in (("head", head_eval, head_all), ("tail", tail_eval, tail_all)):
+        res = []
+        for key, gold in ev.items():
+            if not gold:
+                continue
+            filt = set()
+            for dct in alld:
+                filt |= dct.get(key, set())
+            res.extend(O.kg_ranks(table[key], gold, filt, topn).values())
+        want[side] = np.asarray(res, dtype=np.float64)
+    np.testing.assert_allclose(got[2], want["head"].mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(got[3], want["tail"].mean(axis=0), rtol=1e-12)
+    tot = len(want["head"]) + len(want["tail"])
+    np.testing.assert_allclose(got[0], (want["head"][:, 0].sum() + want["tail"][:, 0].sum()) / tot, rtol=1e-12)
+    np.testing.assert_allclose(got[1], (want["head"][:, 1].sum() + want["tail"][:, 1].sum()) / tot, rtol=1e-12)
+    if family == "TRANSR":
+        assert eng.calls["_eval"] == 0 and eng.calls["_scores"] > 0 and eng.calls["rank_counts"] > 0
+    else:
+        assert eng.calls["_scores"] == 0 and eng.calls["rank_counts"] == 0 and eng.calls["_eval"] > 0
