@@ -55,7 +55,7 @@ class TripleNegativeSampler(_Checked):
         out = torch.empty(h.numel() * n_neg, dtype=torch.int32, device=self.device)
         tab = self.known
         _lib.check(_lib.load().kgrec_sample_corrupt(
-            KF._ptr(h), KF._ptr(t), KF._ptr(r), h.element_size(), h.numel(), n_neg, self.n_ent, self.n_rel,
+            KF._ptr(h), KF._ptr(t), KF._ptr(r), KF._idx_bytes(h, t, r), h.numel(), n_neg, self.n_ent, self.n_rel,
             KF._ptr(tab.table) if tab else None, tab.capacity if tab else 0, int(seed) & 0xFFFFFFFFFFFFFFFF,
             KF._ptr(out), KF._ptr(self._status()), KF._stream()))
         KF.count_launches(1)
@@ -77,7 +77,7 @@ class RatingNegativeSampler(_Checked):
         out = torch.empty(u.numel() * n_neg, dtype=torch.int32, device=self.device)
         tab = self.known
         _lib.check(_lib.load().kgrec_sample_neg_items(
-            KF._ptr(u), KF._ptr(pi), u.element_size(), u.numel(), n_neg, self.n_item,
+            KF._ptr(u), KF._ptr(pi), KF._idx_bytes(u, pi), u.numel(), n_neg, self.n_item,
             KF._ptr(tab.table) if tab else None, tab.capacity if tab else 0, int(seed) & 0xFFFFFFFFFFFFFFFF,
             KF._ptr(out), KF._ptr(self._status()), KF._stream()))
         KF.count_launches(1)
