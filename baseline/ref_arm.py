@@ -80,6 +80,11 @@ def pick_threads(torch, fn, counts=None):
     return best, cores
 
 
+def tried_counts(cores, counts=None):
+    """The thread counts pick_threads times on a host with `cores` cores, as text."""
+    return "/".join(str(x) for x in sorted({min(cores, x) for x in (counts or (8, 16, 32, 64, cores))}))
+
+
 def _best_of(fn, reps=3, warm=1):
     for _ in range(warm):
         fn()
@@ -238,9 +243,9 @@ def time_headline(steps, warmup, batches_per_step, budget_s=None):
             break
     dt = (time.perf_counter() - t0) / n
     sample = ("%d step(s) of %d batch(es) of 1024 pos + 10240 neg: model(pos.repeat_interleave(10)) + model(neg) + marginLoss "
-              "+ backward (dense [rows, d] gradients) through %s; fastest of 8/16/32/64/%d threads on the %d-core host"
+              "+ backward (dense [rows, d] gradients) through %s; fastest of %s threads on the %d-core host"
               % (n, batches_per_step, "the unmodified reference classes (baseline/_ref)" if st.kind == "reference"
-                 else "oracle/torch_port.py (baseline/_ref absent)", host, host))
+                 else "oracle/torch_port.py (baseline/_ref absent)", tried_counts(host), host))
     return {"value": batches_per_step * st.units / dt, "unit": "triples/s", "cores": cores, "kind": st.kind,
             "sample": sample, "ms_per_step": dt * 1e3, "steps_run": n}
 

@@ -402,3 +402,26 @@ def test_driver_level_kg_metrics_host_logic(family):
         assert eng.calls["_eval"] == 0 and eng.calls["_scores"] > 0 and eng.calls["rank_counts"] > 0
     else:
         assert eng.calls["_scores"] == 0 and eng.calls["rank_counts"] == 0 and eng.calls["_eval"] > 0
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: one JSON line with the contract's keys, timed on the host cores through the
+    reference's own classes when baseline/_ref exists (kind "reference"), else the torch-CPU port (kind "port");
+    ranks other than 0 print nothing and exit 0 (the driver launches the arm under torchrun at N > 1)."""
+    import json
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--ref-batches-per-step", "1", "--no-regions", "--gpus", "2"]
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["unit"] == "triples/s" and d["n_gpus"] == 2
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("configs[1]") and d["dtype"] == "f32" and d["data"] == "synthetic"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=dict(env, RANK="1"), cwd=ROOT)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
