@@ -425,3 +425,24 @@ def test_bench_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env=dict(env, RANK="1"), cwd=ROOT)
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_bench_region_bookkeeping():
+    """bench.add_region_aliases: the configs[3] / configs[4] GPU numbers of the `joint_train_cfg4` and `eval` legs listed
+    under `regions` beside the configs[1..2] keys; bookkeeping on measured values only, tolerant of missing legs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("kgrec_bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    out = {"regions": {"cfg2_transe_forward": 1.0},
+           "joint_train_cfg4": {"rec_pairs_per_s": 2.0, "kg_triples_per_s": 3.0},
+           "eval": {"kg_top10": {"queries": 8, "catalog_rows": 50, "pairs_per_s": 4.0},
+                    "rec_top10": {"users_scored": 6, "items": 70, "pairs_per_s": 5.0}, "sharding": "x"}}
+    reg = b.add_region_aliases(out)["regions"]
+    assert reg["cfg2_transe_forward"] == 1.0
+    assert reg["cfg4_ktup_rec_step_forward_backward_regularisers_clip_update"] == 2.0
+    assert reg["cfg4_ktup_kg_step_forward_backward_regularisers_clip_update"] == 3.0
+    assert reg["cfg5_transe_evaluateTail_top10_8q_x_50_d128"] == 4.0
+    assert reg["cfg5_tup_soft_evaluate_top10_6u_x_70_d128"] == 5.0
+    assert b.add_region_aliases({"value": 1}) == {"value": 1}                       # N > 1 lines carry no regions
+    assert b.add_region_aliases({"regions": {}, "eval": {"kg_top10": {}}}) == {"regions": {}, "eval": {"kg_top10": {}}}
