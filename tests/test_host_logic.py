@@ -446,3 +446,79 @@ def test_bench_region_bookkeeping():
     assert reg["cfg5_tup_soft_evaluate_top10_6u_x_70_d128"] == 5.0
     assert b.add_region_aliases({"value": 1}) == {"value": 1}                       # N > 1 lines carry no regions
     assert b.add_region_aliases({"regions": {}, "eval": {"kg_top10": {}}}) == {"regions": {}, "eval": {"kg_top10": {}}}
+
+
+def test_c_abi_argument_validation_without_a_gpu():
+    """Error behaviour of the C ABI (include/kgrec_b200.h: "return value: KGREC_OK or an error code; kgrec_last_error() has
+    the text"): every rejection below happens on the host BEFORE any kernel launch, so it is checked here without a GPU;
+    so are the size / layout queries the bindings allocate from.  Pointers are fake but well-formed (16-byte aligned,
+    never dereferenced on the host)."""
+    import ctypes as C
+    from kgrec_b200 import _lib
+    lib = _lib.load()
+    FAKE = 0x7000_0000_1000
+
+    def err():
+        return lib.kgrec_last_error().decode()
+
+    def tables(**kw):
+        t = _lib.Tables(dim=100, ld=100, n_ent=50, n_rel=7, ent=FAKE, rel=FAKE + 0x100000)
+        for k, v in kw.items():
+            setattr(t, k, v)
+        return t
+
+    def score(t, model=_lib.TRANSE, idx_bytes=8, n=4, a=FAKE, scores=FAKE):
+        return lib.kgrec_score_fwd(C.byref(t) if t is not None else None, model, a, FAKE, FAKE, idx_bytes, n, None, 0, scores, None, None)
+    assert score(None) != 0 and "tables is NULL" in err()
+    assert score(tables(dim=0)) != 0 and "bad dim/ld" in err()
+    assert score(tables(dim=100, ld=96)) != 0 and "bad dim/ld" in err()
+    assert score(tables(dim=600, ld=600)) != 0 and "> 512" in err()
+    assert score(tables(), model=99) != 0 and "unknown model" in err()
+    assert score(tables(ent=None)) != 0 and "needs table 'ent'" in err()
+    assert score(tables(), model=_lib.TRANSH) != 0 and "needs table 'norm'" in err()
+    assert score(tables(), model=_lib.TRANSR) != 0 and "needs table 'proj'" in err()
+    assert score(tables(), idx_bytes=3) != 0 and "idx_bytes must be 4 or 8" in err()
+    assert score(tables(), a=None) != 0 and "index array is NULL" in err()
+    assert score(tables(), n=-1) != 0 and score(tables(), scores=None) != 0
+    assert score(tables(), n=0) == 0                                       # empty batch: accepted, nothing launched
+    # TUP / KTUP table requirements (transUP.py:46-60, jTransUP.py:64-103)
+    rec = dict(user=FAKE, item=FAKE, pref=FAKE, pref_norm=FAKE, n_user=10, n_item=10)
+    assert score(tables(**rec, n_pref=0), model=_lib.TUP) != 0 and "preference_total" in err()
+    assert score(tables(**rec, n_pref=4, norm=FAKE), model=_lib.KTUP) != 0 and "item2ent" in err()
+    assert score(tables(**rec, n_pref=4, norm=FAKE, item2ent=FAKE), model=_lib.KTUP) != 0 and "n_pref == n_rel" in err()
+    # fused ranking loss: loss kind and shape checks (loss.py:8-16, 29-31)
+    t = tables()
+
+    def rank_loss(loss_kind=_lib.LOSS_MARGIN, n_pos=4, n_neg=2, batch_pos=4, ws=FAKE):
+        return lib.kgrec_rank_loss_fwd(C.byref(t), _lib.TRANSE, FAKE, FAKE, FAKE, FAKE, FAKE, FAKE, 8, n_pos, n_neg, batch_pos,
+                                       loss_kind, 1.0, None, 0, FAKE, FAKE, FAKE, ws, None, None)
+    assert rank_loss(loss_kind=7) != 0 and "unknown loss" in err()
+    assert rank_loss(n_neg=0) != 0 and rank_loss(batch_pos=0) != 0 and rank_loss(n_pos=-1) != 0
+    assert rank_loss(ws=None) != 0 and "NULL" in err()
+    assert rank_loss(n_pos=0) == 0
+    g = _lib.Grads(mode=0, ent=FAKE)                                       # rel gradient buffer missing
+    assert lib.kgrec_score_bwd(C.byref(t), _lib.TRANSE, FAKE, FAKE, FAKE, 8, 4, None, 0, FAKE, C.byref(g), None) != 0
+    assert "gradient buffer" in err()
+    g = _lib.Grads(mode=5, ent=FAKE, rel=FAKE)
+    assert lib.kgrec_score_bwd(C.byref(t), _lib.TRANSE, FAKE, FAKE, FAKE, 8, 4, None, 0, FAKE, C.byref(g), None) != 0
+    # negative samplers (utils/data.py:12-85)
+    assert lib.kgrec_hashset_capacity(0) == 1024 and lib.kgrec_hashset_capacity(1000) == 2048
+    assert lib.kgrec_hashset_capacity(1 << 20) == 1 << 21
+    assert lib.kgrec_hashset_build(FAKE, 10, FAKE, 1000, None) != 0 and "power of two" in err()
+    assert lib.kgrec_hashset_build(FAKE, 600, FAKE, 1024, None) != 0                     # load factor > 1/2
+    assert lib.kgrec_sample_corrupt(FAKE, FAKE, FAKE, 8, 4, 1, 1, 3, None, 0, 0, FAKE, None, None) != 0      # one entity: no negative exists
+    assert lib.kgrec_sample_corrupt(FAKE, FAKE, None, 8, 4, 1, 50, 3, None, 0, 0, FAKE, None, None) != 0 and "relations" in err()
+    assert lib.kgrec_sample_corrupt(FAKE, FAKE, FAKE, 8, 0, 1, 50, 3, None, 0, 0, FAKE, None, None) == 0
+    assert lib.kgrec_sample_neg_items(FAKE, FAKE, 8, 4, 0, 50, None, 0, 0, FAKE, None, None) != 0
+    assert lib.kgrec_sample_neg_items(FAKE, FAKE, 8, 4, 1, 50, FAKE, 1000, 0, FAKE, None, None) != 0 and "capacity" in err()
+    # layout / size queries the bindings allocate from
+    assert lib.kgrec_rank_loss_workspace_bytes(0) == 4 and lib.kgrec_rank_loss_workspace_bytes(1000) == 4000
+    assert lib.kgrec_pref_aug_ld(100) == 308 and lib.kgrec_pref_aug_ld(128) == 388        # 3 d + pad, (ld / 4) odd
+    for d in (4, 20, 64, 100, 128, 200, 256):
+        ld = lib.kgrec_pref_aug_ld(d)
+        assert ld > 3 * d and ld % 4 == 0 and (ld // 4) % 2 == 1
+    assert lib.kgrec_gumbel_aug_ld(100, 20) == 140 and lib.kgrec_gumbel_aug_ld(128, 7) == 144
+    assert lib.kgrec_eval_workspace_bytes(4096, 10) >= 4096 * 10 * 8
+    assert lib.kgrec_eval_workspace_bytes(8192, 10) > lib.kgrec_eval_workspace_bytes(4096, 10)
+    assert lib.kgrec_transr_workspace_floats(64, 1000, 100) >= 1000 * 100
+    assert lib.kgrec_abi_version() == _lib.ABI_VERSION and lib.kgrec_sm_count() > 0
