@@ -1539,6 +1539,7 @@ extern "C" int kgrec_eval_scores(const kgrec_tables* tables, int model, int side
   if (rc) return rc;
   if (!out || ld_out < n_cat) { set_error("bad out / ld_out"); return KGREC_ERR_INVALID; }
   if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
+  if (!qvec && idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 4 or 8"); return KGREC_ERR_INVALID; }
   A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
   A.qvec_ld = pl.kind == KIND_GUMBEL_L2 ? cat_ld : 2 * static_cast<int64_t>(tables->dim);
   A.gconst = pl.kind == KIND_GUMBEL_L2 ? qvec + nq * cat_ld : nullptr;     // the constants follow the query rows
@@ -1559,6 +1560,7 @@ extern "C" int kgrec_eval_topk(const kgrec_tables* tables, int model, int side, 
   if (rc) return rc;
   if (!out_keys) { set_error("out_keys is NULL"); return KGREC_ERR_INVALID; }
   if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
+  if (!qvec && idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 4 or 8"); return KGREC_ERR_INVALID; }
   if (id_base < 0 || id_base + n_cat > 0xffffffffll) { set_error("catalog ids must fit 32 bits"); return KGREC_ERR_INVALID; }
   const int64_t need = static_cast<int64_t>(pl.n_splits) * nq * k * static_cast<int64_t>(sizeof(uint64_t));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1610,7 +1612,9 @@ extern "C" int kgrec_eval_rank_count(const kgrec_tables* tables, int model, int 
   if (rc) return rc;
   if (!gold_scores || !gold_ids || !counts) { set_error("rank_count: NULL argument"); return KGREC_ERR_INVALID; }
   if (!qvec && (!q || (side != KGREC_SIDE_REC && !r))) { set_error("query ids are NULL"); return KGREC_ERR_INVALID; }
+  if (!qvec && idx_bytes != 4 && idx_bytes != 8) { set_error("idx_bytes must be 4 or 8"); return KGREC_ERR_INVALID; }
   A.q = q; A.r = r; A.is64 = idx_bytes == 8; A.qvec = qvec;
+  if (id_base < 0 || id_base + n_cat > 0xffffffffll) { set_error("catalog ids must fit 32 bits"); return KGREC_ERR_INVALID; }
   A.qvec_ld = 2 * static_cast<int64_t>(tables->dim);
   A.id_base = id_base; A.seed = 0;
   A.gold_scores = gold_scores; A.gold_ids = gold_ids; A.counts = counts;

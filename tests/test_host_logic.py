@@ -522,3 +522,80 @@ def test_c_abi_argument_validation_without_a_gpu():
     assert lib.kgrec_eval_workspace_bytes(8192, 10) > lib.kgrec_eval_workspace_bytes(4096, 10)
     assert lib.kgrec_transr_workspace_floats(64, 1000, 100) >= 1000 * 100
     assert lib.kgrec_abi_version() == _lib.ABI_VERSION and lib.kgrec_sm_count() > 0
+
+
+def test_c_abi_eval_argument_validation_without_a_gpu():
+    """The evaluation entry points' host-side rejections (eval.cu: eval_plan and the three callers), no GPU involved."""
+    import ctypes as C
+    from kgrec_b200 import _lib
+    lib = _lib.load()
+    FAKE = 0x7000_0000_1000
+
+    def err():
+        return lib.kgrec_last_error().decode()
+
+    def tables(**kw):
+        t = _lib.Tables(dim=100, ld=100, n_ent=5000, n_rel=7, ent=FAKE, rel=FAKE, norm=FAKE)
+        for k, v in kw.items():
+            setattr(t, k, v)
+        return t
+
+    def scores(t=None, model=_lib.TRANSE, side=_lib.SIDE_TAIL, q=FAKE, r=FAKE, idx_bytes=8, qvec=None, nq=16, cat=FAKE,
+               cat_ld=100, n_cat=5000, out=FAKE, ld_out=5000, cat_ids=None):
+        t = tables() if t is None else t
+        return lib.kgrec_eval_scores(C.byref(t), model, side, q, r, idx_bytes, qvec, nq, cat, cat_ld, n_cat, 0, cat_ids, None, 0,
+                                     out, ld_out, None)
+    assert lib.kgrec_eval_scores(None, 0, 1, FAKE, FAKE, 8, None, 16, FAKE, 100, 5000, 0, None, None, 0, FAKE, 5000, None) != 0
+    assert "tables is NULL" in err()
+    assert scores(nq=0) != 0 and "empty catalog / query set" in err()
+    assert scores(n_cat=0) != 0 and scores(cat=None) != 0
+    assert scores(t=tables(dim=300, ld=300), cat_ld=300) != 0 and "outside [1, 256]" in err()
+    assert scores(t=tables(dim=50, ld=50), cat_ld=50) != 0 and "multiples of 4" in err()            # evaluate* needs d % 4 == 0
+    assert scores(cat=FAKE + 4) != 0 and "16-byte aligned" in err()
+    assert scores(cat_ld=96) != 0                                                                     # leading dimension < d
+    assert scores(model=42) != 0 and "unknown model" in err()
+    assert scores(model=_lib.TRANSR) != 0 and "explicit query vectors" in err()                        # transR.py:80-128 via kgrec_transr_eval_*
+    assert scores(side=_lib.SIDE_REC) != 0 and "does not fit model" in err()                           # a KG model has no rec side
+    assert scores(t=tables(ent=None)) != 0 and "NULL or not 16-byte aligned" in err()
+    assert scores(model=_lib.TRANSH, t=tables(norm=None)) != 0
+    assert scores(out=None) != 0 and "bad out / ld_out" in err()
+    assert scores(ld_out=100) != 0
+    assert scores(q=None) != 0 and "query ids are NULL" in err()
+    assert scores(r=None) != 0
+    assert scores(idx_bytes=2) != 0 and "idx_bytes must be 4 or 8" in err()
+
+    def topk(k=10, id_base=0, n_cat=5000, out=FAKE, ws=FAKE, ws_bytes=1 << 40, idx_bytes=4):
+        t = tables()
+        return lib.kgrec_eval_topk(C.byref(t), _lib.TRANSE, _lib.SIDE_HEAD, FAKE, FAKE, idx_bytes, None, 16, FAKE, 100, n_cat, id_base, k,
+                                   None, None, None, 0, out, ws, ws_bytes, None)
+    assert topk(k=0) != 0 and "topn" in err()
+    assert topk(k=129) != 0 and "[1, 128]" in err()
+    assert topk(out=None) != 0 and "out_keys is NULL" in err()
+    assert topk(id_base=-1) != 0 and "fit 32 bits" in err()
+    assert topk(id_base=(1 << 32) - 10) != 0 and "fit 32 bits" in err()                                # ids are the low half of the keys
+    assert topk(ws_bytes=64) != 0 and "workspace too small" in err()
+    assert topk(ws=None) != 0
+    assert topk(idx_bytes=16) != 0 and "idx_bytes" in err()
+
+    def rank(gold_scores=FAKE, gold_ids=FAKE, counts=FAKE, id_base=0):
+        t = tables()
+        return lib.kgrec_eval_rank_count(C.byref(t), _lib.TRANSH, _lib.SIDE_TAIL, FAKE, FAKE, 8, None, 16, FAKE, 100, 5000, id_base,
+                                         gold_scores, gold_ids, counts, None)
+    assert rank(gold_scores=None) != 0 and "NULL argument" in err()
+    assert rank(counts=None) != 0 and rank(gold_ids=None) != 0
+    assert rank(id_base=1 << 32) != 0 and "fit 32 bits" in err()
+    # merge of per-shard lists; augmented-row builders; KTUP catalog
+    assert lib.kgrec_merge_topk(None, 2, 16, 10, FAKE, None) != 0 and "merge_topk" in err()
+    assert lib.kgrec_merge_topk(FAKE, 0, 16, 10, FAKE, None) != 0 and lib.kgrec_merge_topk(FAKE, 2, 16, 200, FAKE, None) != 0
+    assert lib.kgrec_merge_topk(FAKE, 2, 0, 10, FAKE, None) == 0                                        # no queries: nothing to do
+    rt = tables(user=FAKE, item=FAKE, pref=FAKE, pref_norm=FAKE, n_pref=20)
+    assert lib.kgrec_pref_aug_rows(C.byref(rt), _lib.TRANSE, 0, None, 8, FAKE, 100, 10, FAKE, 308, None) != 0
+    assert lib.kgrec_pref_aug_rows(C.byref(rt), _lib.TUP, 0, None, 8, FAKE, 100, 10, FAKE, 300, None) != 0 and "ld_out = 308" in err()
+    assert lib.kgrec_pref_aug_rows(C.byref(tables(user=FAKE, item=FAKE, n_pref=20)), _lib.TUP, 0, None, 8, FAKE, 100, 10, FAKE, 308, None) != 0
+    assert lib.kgrec_pref_aug_rows(C.byref(rt), _lib.TUP, 0, None, 8, FAKE, 100, 0, FAKE, 308, None) == 0
+    assert lib.kgrec_gumbel_aug_rows(C.byref(rt), _lib.TUP, None, 8, FAKE, 100, 10, FAKE, 128, None, None) != 0 and "ld_out = 140" in err()
+    assert lib.kgrec_gumbel_aug_rows(C.byref(rt), _lib.TUP, FAKE, 3, FAKE, 100, 10, FAKE, 140, None, None) != 0 and "idx_bytes" in err()
+    assert lib.kgrec_gumbel_aug_supported(100, 20, 10) == 1 and lib.kgrec_gumbel_aug_supported(100, 20, 0) == 1
+    assert lib.kgrec_gumbel_aug_supported(50, 20, 10) == 0 and lib.kgrec_gumbel_aug_supported(100, 65, 10) == 0
+    assert lib.kgrec_ktup_item_table(C.byref(tables(item=FAKE)), 0, 10, FAKE, 100, None) != 0 and "ktup_item_table" in err()
+    assert lib.kgrec_ktup_item_table(C.byref(tables(item=FAKE, item2ent=FAKE)), 0, 0, FAKE, 100, None) == 0
