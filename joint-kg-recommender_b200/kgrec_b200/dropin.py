@@ -42,11 +42,19 @@ def install():
 
 
 def uninstall(saved):
+    """Undo install(): sys.modules entries AND the attributes install() set on the `jTransUP.models` package
+    (`from jTransUP.models import transE` reads the attribute before sys.modules)."""
     for full, old in saved.items():
+        pkg_name, _, leaf = full.rpartition(".")
+        pkg = sys.modules.get(pkg_name)
         if old is None:
             sys.modules.pop(full, None)
+            if pkg is not None and leaf in _NAMES and hasattr(pkg, leaf):
+                delattr(pkg, leaf)
         else:
             sys.modules[full] = old
+            if pkg is not None and leaf in _NAMES:
+                setattr(pkg, leaf, old)
 
 
 def main(argv=None):

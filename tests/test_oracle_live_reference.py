@@ -42,8 +42,22 @@ def ref():
         if p not in sys.path:
             sys.path.insert(0, p)
     import gflags  # noqa: F401  (the shim; restores numpy.asfarray)
+    import importlib
     warnings.filterwarnings("ignore")
-    from jTransUP.models import transE, transH, transR, transUP, jTransUP
+    mods = {}
+    for name in ("transE", "transH", "transR", "transUP", "jTransUP"):
+        full = "jTransUP.models." + name
+        m = importlib.import_module(full)
+        if not os.path.realpath(getattr(m, "__file__", "")).startswith(os.path.realpath(make_ref.DEST)):
+            # an earlier test left the CUDA overlay (kgrec_b200.dropin) under the reference's module name: drop it
+            sys.modules.pop(full, None)
+            pkg = sys.modules.get("jTransUP.models")
+            if pkg is not None and getattr(pkg, name, None) is m:
+                delattr(pkg, name)
+            m = importlib.import_module(full)
+        assert os.path.realpath(m.__file__).startswith(os.path.realpath(make_ref.DEST)), m.__file__
+        mods[name] = m
+    transE, transH, transR, transUP, jTransUP = (mods[n] for n in ("transE", "transH", "transR", "transUP", "jTransUP"))
     from jTransUP.utils import loss, misc
     torch.set_num_threads(2)
     return {"transe": transE.TransEModel, "transh": transH.TransHModel, "transr": transR.TransRModel,
