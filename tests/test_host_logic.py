@@ -599,3 +599,55 @@ def test_c_abi_eval_argument_validation_without_a_gpu():
     assert lib.kgrec_gumbel_aug_supported(50, 20, 10) == 0 and lib.kgrec_gumbel_aug_supported(100, 65, 10) == 0
     assert lib.kgrec_ktup_item_table(C.byref(tables(item=FAKE)), 0, 10, FAKE, 100, None) != 0 and "ktup_item_table" in err()
     assert lib.kgrec_ktup_item_table(C.byref(tables(item=FAKE, item2ent=FAKE)), 0, 0, FAKE, 100, None) == 0
+
+
+def test_c_abi_optimizer_argument_validation_without_a_gpu():
+    """Host-side rejections of the sparse-row optimizer / regulariser entry points (optim.cu, reg.cu): segment and table
+    counts, missing state for Adagrad / Adam (utils/trainer.py:63-81 builds exactly one of SGD / Adagrad / Adam)."""
+    import ctypes as C
+    from kgrec_b200 import _lib
+    lib = _lib.load()
+    FAKE = 0x7000_0000_1000
+
+    def err():
+        return lib.kgrec_last_error().decode()
+    seg = _lib.MarkSeg(ids=FAKE, n=10, idx_bytes=4, compact=0, remap=None, n_remap=0, marks=FAKE, rows=100)
+    arr = (_lib.MarkSeg * 9)(*([seg] * 9))
+    assert lib.kgrec_rows_mark(arr, 0, 1, None, None) != 0 and "id segments per call" in err()
+    assert lib.kgrec_rows_mark(arr, 9, 1, None, None) != 0
+    assert lib.kgrec_rows_mark(None, 1, 1, None, None) != 0
+    bad = (_lib.MarkSeg * 1)(_lib.MarkSeg(ids=FAKE, n=10, idx_bytes=2, marks=FAKE, rows=100))
+    assert lib.kgrec_rows_mark(bad, 1, 1, None, None) != 0 and "bad segment 0" in err()
+    bad = (_lib.MarkSeg * 1)(_lib.MarkSeg(ids=None, n=10, idx_bytes=4, marks=FAKE, rows=100))
+    assert lib.kgrec_rows_mark(bad, 1, 1, None, None) != 0
+    empty = (_lib.MarkSeg * 1)(_lib.MarkSeg(ids=None, n=0, idx_bytes=8, marks=None, rows=100))
+    assert lib.kgrec_rows_mark(empty, 1, 1, None, None) == 0                   # an empty step marks nothing
+
+    def tab(**kw):
+        t = _lib.OptTable(table=FAKE, acc=FAKE, state1=FAKE, state2=FAKE, marks=FAKE, rows=100, dim=100, keep_acc=0)
+        for k, v in kw.items():
+            setattr(t, k, v)
+        return t
+    one = (_lib.OptTable * 1)(tab())
+    nine = (_lib.OptTable * 9)(*([tab()] * 9))
+    assert lib.kgrec_rows_sqnorm(nine, 9, 1, FAKE, None) != 0 and "tables per call" in err()
+    assert lib.kgrec_rows_sqnorm(one, 0, 1, FAKE, None) != 0
+    assert lib.kgrec_rows_sqnorm(one, 1, 1, None, None) != 0 and "sqnorm is NULL" in err()
+    noacc = (_lib.OptTable * 1)(tab(acc=None))
+    assert lib.kgrec_rows_sqnorm(noacc, 1, 1, FAKE, None) != 0 and "no accumulator" in err()
+
+    def update(tabs, kind):
+        return lib.kgrec_rows_update(tabs, 1, 1, kind, 0.01, 1e-10, 0.9, 0.999, 1, 0.0, None, 0.0, None)
+    assert update(one, 3) != 0 and "unknown kind" in err()
+    assert update(one, -1) != 0
+    assert update((_lib.OptTable * 1)(tab(state1=None)), 1) != 0 and "state missing" in err()      # Adagrad needs its sum
+    assert update((_lib.OptTable * 1)(tab(state2=None)), 2) != 0 and "state missing" in err()      # Adam needs m and v
+    assert update((_lib.OptTable * 1)(tab(table=None)), 0) != 0
+    assert update((_lib.OptTable * 1)(tab(rows=0)), 0) != 0
+    # regularisers (utils/loss.py:18-23)
+    assert lib.kgrec_reg_norm_rows(None, 10, 100, None, 8, 10, 1.0, None, None, None, None) != 0
+    assert lib.kgrec_reg_norm_rows(FAKE, 10, 100, None, 8, 11, 1.0, None, None, None, None) != 0 and "n > rows" in err()
+    assert lib.kgrec_reg_norm_rows(FAKE, 10, 100, FAKE, 5, 10, 1.0, None, None, None, None) != 0
+    assert lib.kgrec_reg_norm_rows(FAKE, 10, 100, FAKE, 8, 0, 1.0, None, None, None, None) == 0
+    assert lib.kgrec_reg_orth_tables(FAKE, None, 10, 100, 1.0, None, None, None, None) != 0 and "reg_orth" in err()
+    assert lib.kgrec_reg_orth_tables(FAKE, FAKE, 0, 100, 1.0, None, None, None, None) != 0
