@@ -651,3 +651,53 @@ def test_c_abi_optimizer_argument_validation_without_a_gpu():
     assert lib.kgrec_reg_norm_rows(FAKE, 10, 100, FAKE, 8, 0, 1.0, None, None, None, None) == 0
     assert lib.kgrec_reg_orth_tables(FAKE, None, 10, 100, 1.0, None, None, None, None) != 0 and "reg_orth" in err()
     assert lib.kgrec_reg_orth_tables(FAKE, FAKE, 0, 100, 1.0, None, None, None, None) != 0
+
+
+def test_c_abi_group_format_argument_validation_without_a_gpu():
+    """Host-side rejections of the group-compact (corrupted-id) ranking-loss entry points (train_group.cu: group_check):
+    the format the reference's sampler produces -- head OR tail of the positive replaced, utils/data.py:12-56 -- exists
+    for the KG families only and holds entity ids in 31 bits."""
+    import ctypes as C
+    from kgrec_b200 import _lib
+    lib = _lib.load()
+    FAKE = 0x7000_0000_1000
+
+    def err():
+        return lib.kgrec_last_error().decode()
+
+    def tables(**kw):
+        t = _lib.Tables(dim=100, ld=100, n_ent=50, n_rel=7, ent=FAKE, rel=FAKE, norm=FAKE)
+        for k, v in kw.items():
+            setattr(t, k, v)
+        return t
+
+    def fwd(t=None, model=_lib.TRANSE, idx_bytes=4, n_pos=4, corrupt=FAKE, n_neg=2, batch_pos=4, loss_kind=_lib.LOSS_MARGIN, ws=FAKE):
+        t = tables() if t is None else t
+        return lib.kgrec_corrupt_loss_fwd(C.byref(t), model, FAKE, FAKE, FAKE, idx_bytes, n_pos, corrupt, n_neg, batch_pos, loss_kind,
+                                          1.0, FAKE, FAKE, FAKE, ws, None, None)
+    rec = dict(user=FAKE, item=FAKE, pref=FAKE, pref_norm=FAKE, n_pref=4, n_user=9, n_item=9)
+    assert fwd(t=tables(**rec), model=_lib.TUP) != 0 and "TransE / TransH" in err()
+    assert fwd(t=tables(proj=FAKE), model=_lib.TRANSR) != 0 and "TransE / TransH" in err()        # TransR: the step entry point only
+    assert fwd(t=tables(dim=50, ld=50)) != 0 and "embedding_size % 4 == 0" in err()
+    assert fwd(t=tables(ent=FAKE + 4)) != 0 and "16-byte aligned" in err()
+    assert fwd(idx_bytes=1) != 0 and "idx_bytes" in err()
+    assert fwd(corrupt=None) != 0 and "index array is NULL" in err()
+    assert fwd(loss_kind=9) != 0 and "unknown loss" in err()
+    assert fwd(n_neg=0) != 0 and fwd(batch_pos=0) != 0 and fwd(n_pos=1 << 31) != 0
+    assert fwd(t=tables(n_ent=1 << 31)) != 0 and "31 bits" in err()
+    assert fwd(ws=None) != 0
+    assert fwd(n_pos=0) == 0
+    # the single-pass step: the same checks + gradient descriptor; workspace sizes the bindings allocate
+    g = _lib.Grads(mode=1, ent=FAKE, rel=FAKE)
+
+    def step(t=None, model=_lib.TRANSE, grads=g, n_neg=2, reg=0):
+        t = tables() if t is None else t
+        return lib.kgrec_corrupt_loss_step(C.byref(t), model, FAKE, FAKE, FAKE, 4, 4, FAKE, n_neg, 4, _lib.LOSS_MARGIN, 1.0, 1.0, reg,
+                                           FAKE, FAKE, FAKE, C.byref(grads) if grads is not None else None, None, None, FAKE, None, None)
+    assert step(model=_lib.TUP, t=tables(**rec)) != 0
+    assert step(grads=None) != 0
+    assert step(model=_lib.TRANSH, grads=_lib.Grads(mode=1, ent=FAKE, rel=FAKE)) != 0            # TransH needs the norm gradient too
+    t = tables(n_rel=500)
+    assert lib.kgrec_corrupt_loss_step_workspace_bytes(C.byref(t), _lib.TRANSE, 1024) == 4096
+    assert lib.kgrec_corrupt_loss_step_workspace_bytes(C.byref(t), _lib.TRANSR, 1024) == 4 * (2 * 1024 + 501)
+    assert lib.kgrec_corrupt_loss_step_workspace_bytes(C.byref(t), _lib.TRANSE, 0) == 4
