@@ -119,10 +119,20 @@ def save_checkpoint(path, model, optimizer=None, step=0, best_step=0, best_dev_p
                 "optimizer_state_dict": optimizer.state_dict() if optimizer is not None else {}}, path)
 
 
-def load_checkpoint(path, model, optimizer=None):
+def load_checkpoint(path, model, optimizer=None, trusted=True):
     """ModelTrainer.load (utils/trainer.py:128-142): strict=False state_dict load; returns the
-    bookkeeping fields.  Works on checkpoints written by the reference trainer as well."""
-    ck = torch.load(path, map_location="cpu")
+    bookkeeping fields.  Works on checkpoints written by the reference trainer as well: those carry
+    `best_dev_performance` as a numpy scalar (trainer.py:115-122 saves what np.mean returned), which
+    torch >= 2.6's default weights-only unpickler refuses -- the reference's own trainer unpickles the
+    file in full, and so does this function for a `trusted` (local, self-written) file after the safe
+    attempt fails.  trusted=False keeps the weights-only behaviour and raises on such files."""
+    import pickle
+    try:
+        ck = torch.load(path, map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError:
+        if not trusted:
+            raise
+        ck = torch.load(path, map_location="cpu", weights_only=False)
     model.load_state_dict(ck["model_state_dict"], strict=False)
     if optimizer is not None and ck.get("optimizer_state_dict"):
         optimizer.load_state_dict(ck["optimizer_state_dict"])

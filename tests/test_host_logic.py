@@ -232,6 +232,15 @@ def test_dataio_round_trip(tmp_path):
     dataio.save_checkpoint(str(ck), e)
     dataio.load_checkpoint(str(ck), m2)
     assert torch.equal(m2.ent_embeddings.weight, e.ent_embeddings.weight)
+    # a checkpoint as the REFERENCE trainer writes it (utils/trainer.py:115-122): best_dev_performance is whatever
+    # np.mean returned -- a numpy scalar, which torch >= 2.6's weights-only unpickler refuses
+    torch.save({"step": 7, "best_step": 5, "best_dev_performance": np.float64(0.25),
+                "model_state_dict": {k: v.detach().cpu() for k, v in m.state_dict().items()}, "optimizer_state_dict": {}}, str(ck))
+    m3 = K.TransHModel(False, 8, 50, 5)
+    assert dataio.load_checkpoint(str(ck), m3) == (7, 5, 0.25)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m3.state_dict().values()))
+    with pytest.raises(Exception):
+        dataio.load_checkpoint(str(ck), m3, trusted=False)
 
 
 def test_corrupt_format_encoding_round_trip():
