@@ -21,7 +21,7 @@ from . import evaluation as KE
 from . import functional as KF
 
 
-def evaluate_rec(model, eval_dict, all_dicts=None, topn=10, batch=4096, gumbel_seeded=True):
+def evaluate_rec(model, eval_dict, all_dicts=None, topn=10, batch=4096):
     """Mean (f1, precision, recall, hit, ndcg) over the users of eval_dict.
 
     eval_dict: {user: set(gold items)}; all_dicts: dicts whose items are filtered per user
