@@ -88,3 +88,57 @@ class DevicePrefetcher:
             done = torch.cuda.Event()          # the consumer has enqueued its work on this batch by now
             done.record(torch.cuda.current_stream(self.device))
             self.ring["done"][s] = done
+
+
+class DeviceTrainIterator:
+    """The reference's endless training iterator (``MakeTrainIterator``, utils/data.py:87-110) with the training set
+    resident on the device: no Python lists, no per-step host -> device copies.
+
+    Same epoch rule as the reference, including its quirk: the visiting order is ``range(n)`` repeated
+    ``negtive_samples`` times and shuffled, a batch is ``order[start : start + batch_size]``, and a new epoch (a fresh
+    shuffle, ``start = 0``) begins as soon as ``start > n - batch_size`` -- so an epoch yields
+    ``(n - batch_size) // batch_size + 1`` batches drawn from the first ``n`` entries of the shuffled order whatever
+    ``negtive_samples`` is.  The shuffle is ``torch.randperm`` on the data's device from a private generator
+    (reproducible per seed; not the reference's ``random.shuffle`` stream).
+
+    data: [n, c] integer tensor or array (triples ``h, t, r`` / ratings ``u, i``).  Yields a tuple of ``c`` contiguous
+    device index tensors of ``batch_size`` entries -- what ``SparseRowOptimizer.step_corrupt`` / ``step_pairs`` and the
+    negative samplers (kgrec_b200.sampling) consume."""
+
+    def __init__(self, data, batch_size, negtive_samples=1, device="cuda", seed=0, dtype=torch.int32):
+        rows = torch.as_tensor(data)
+        if rows.dim() != 2 or rows.shape[0] == 0:
+            raise ValueError("DeviceTrainIterator: data must be a non-empty [n, columns] integer array")
+        if batch_size < 1 or negtive_samples < 1:
+            raise ValueError("DeviceTrainIterator: batch_size and negtive_samples must be >= 1")
+        self.device = torch.device(device)
+        self.cols = [rows[:, c].to(self.device, dtype).contiguous() for c in range(rows.shape[1])]   # column-major: one gather each
+        self.n = rows.shape[0]
+        self.batch_size = int(batch_size)
+        self.repeat = int(negtive_samples)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed))
+        self.epoch = 0
+        self.start = -self.batch_size
+        self._shuffle()
+
+    def _shuffle(self):
+        # list(range(n)) * k shuffled == a random permutation of the multiset: permute k*n slots, fold by n
+        perm = torch.randperm(self.n * self.repeat, generator=self.gen, device=self.device)
+        self.order = perm % self.n if self.repeat > 1 else perm
+
+    @property
+    def batches_per_epoch(self):
+        return max(0, (self.n - self.batch_size)) // self.batch_size + 1
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        self.start += self.batch_size
+        if self.start > self.n - self.batch_size:
+            self.start = 0
+            self.epoch += 1
+            self._shuffle()
+        idx = self.order[self.start:self.start + self.batch_size]
+        return tuple(c.index_select(0, idx) for c in self.cols)

@@ -710,3 +710,48 @@ def test_c_abi_group_format_argument_validation_without_a_gpu():
     assert lib.kgrec_corrupt_loss_step_workspace_bytes(C.byref(t), _lib.TRANSE, 1024) == 4096
     assert lib.kgrec_corrupt_loss_step_workspace_bytes(C.byref(t), _lib.TRANSR, 1024) == 4 * (2 * 1024 + 501)
     assert lib.kgrec_corrupt_loss_step_workspace_bytes(C.byref(t), _lib.TRANSE, 0) == 4
+
+
+def test_device_train_iterator_follows_the_reference_epoch_rule():
+    """kgrec_b200.data.DeviceTrainIterator vs MakeTrainIterator (utils/data.py:87-110): same batch size, same number
+    of batches per epoch (the reference restarts as soon as start > n - batch_size, whatever -negtive_samples is), every
+    batch made of rows of the data, no row twice within an epoch when negtive_samples = 1, a fresh order every epoch,
+    reproducible per seed.  Plumbing only (torch index ops on the data's device): runs on the CPU here."""
+    from kgrec_b200.data import DeviceTrainIterator
+    rng = np.random.RandomState(0)
+    n, bs = 103, 10
+    data = np.stack([np.arange(n), rng.randint(0, 50, n), rng.randint(0, 5, n)], axis=1)      # column 0 identifies the row
+    it = DeviceTrainIterator(data, bs, device="cpu", seed=5)
+    assert it.batches_per_epoch == (n - bs) // bs + 1 == 10
+    epochs = []
+    for _ in range(3):
+        seen = []
+        for _ in range(it.batches_per_epoch):
+            h, t, r = next(it)
+            assert h.shape == t.shape == r.shape == (bs,) and h.dtype == torch.int32 and h.is_contiguous()
+            assert np.array_equal(data[h.numpy(), 1], t.numpy()) and np.array_equal(data[h.numpy(), 2], r.numpy())
+            seen.extend(h.tolist())
+        assert len(set(seen)) == len(seen) == 100                      # a permutation prefix: no row twice in an epoch
+        epochs.append(seen)
+    assert it.epoch == 2 and epochs[0] != epochs[1] != epochs[2]
+    # the reference's own iterator yields the same count before it reshuffles: compare with its arithmetic on a python list
+    start, count = -bs, 0
+    while True:
+        start += bs
+        if start > n - bs:
+            break
+        count += 1
+    assert count == it.batches_per_epoch
+    again = DeviceTrainIterator(data, bs, device="cpu", seed=5)
+    assert [next(again)[0].tolist() for _ in range(10)] == [epochs[0][i * bs:(i + 1) * bs] for i in range(10)]
+    # -negtive_samples k: the order is range(n) * k shuffled; rows may repeat inside an epoch, all ids stay in range
+    it3 = DeviceTrainIterator(data[:, :2], 25, negtive_samples=3, device="cpu", seed=1)
+    assert it3.order.numel() == 3 * n and int(it3.order.max()) < n and it3.batches_per_epoch == (n - 25) // 25 + 1
+    assert torch.equal(torch.bincount(it3.order, minlength=n), torch.full((n,), 3))
+    u, i = next(it3)
+    assert u.shape == (25,) and np.array_equal(data[u.numpy(), 1], i.numpy())
+    # a batch larger than the data set: the reference yields the whole (short) shuffled prefix every time
+    small = DeviceTrainIterator(data[:7], 10, device="cpu")
+    assert small.batches_per_epoch == 1 and next(small)[0].numel() == 7 and next(small)[0].numel() == 7
+    with pytest.raises(ValueError):
+        DeviceTrainIterator(np.zeros((0, 3), np.int64), 4, device="cpu")
