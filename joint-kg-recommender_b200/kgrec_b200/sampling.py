@@ -63,7 +63,12 @@ class TripleNegativeSampler(_Checked):
 
 
 class RatingNegativeSampler(_Checked):
-    """known_ratings: [n, 2] (u, i) pairs negatives must avoid (train + eval dicts), or None."""
+    """known_ratings: [n, 2] (u, i) pairs negatives must avoid (train + eval dicts), or None.
+
+    One deliberate difference from getNegRatings (utils/data.py:64-85): the reference also refuses an item already
+    drawn as a negative earlier in the SAME batch (`neg_set`, data.py:66,79-82 -- SURVEY appendix B: with more
+    positives than items it never returns).  The device sampler draws every negative independently: a batch-wide
+    set would serialise the batch, and for I >> B the two distributions differ by O(B / I)."""
 
     def __init__(self, n_item, known_ratings=None, device="cuda"):
         self.n_item, self.device = int(n_item), torch.device(device)
