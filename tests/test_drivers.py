@@ -190,3 +190,69 @@ def test_bprmf_runs_beside_the_dropin(dataset, tmp_path):
                    "-eval_interval_steps", "30")
     log, _, _ = H.run_driver("rec", flags, str(tmp_path), "bprmf_dropin", dropin=True)
     assert len(log["rec"]) == 2
+
+
+@needs_ref
+def test_reference_trainer_checkpoints_and_warm_starts_the_cuda_modules(tmp_path, monkeypatch):
+    """The unchanged ModelTrainer (utils/trainer.py) around the drop-in modules, on the host (no scoring call is made):
+    `save` / `load` round-trip their state_dict (trainer.py:109-142) and `loadEmbedding` (144-205) -- the `-load_ckpt_file`
+    warm start of the joint model from a pre-trained TransH -- assigns rows through `.weight.data[mapped, :]` with the
+    entity remap, which requires the tables to be ordinary nn.Embedding weights under the reference's state_dict keys."""
+    import logging
+    import sys
+    import types
+    for p in reversed(H.make_ref.env_paths()):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import gflags  # noqa: F401
+    monkeypatch.setenv("TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD", "1")          # the trainer reloads numpy scalars with a bare torch.load
+    from jTransUP.utils.trainer import ModelTrainer
+    import kgrec_b200 as K
+    flags = types.SimpleNamespace(model_type="transh", optimizer_type="Adagrad", l2_lambda=0.0, learning_rate=0.05,
+                                  learning_rate_decay_when_no_progress=0.5, momentum=0.9, eval_interval_steps=10,
+                                  ckpt_path=str(tmp_path), experiment_name="pre", eval_only_mode=False, load_experiment_name="")
+    log = logging.getLogger("kgrec_test")
+    torch.manual_seed(3)
+    E, R, d = 40, 5, 16
+    pre = K.TransHModel(True, d, E, R)
+    tr = ModelTrainer(pre, log, 10, flags)
+    tr.step, tr.best_step, tr.best_dev_performance = 30, 20, np.float64(0.4)
+    tr.checkpoint()
+    ck = os.path.join(str(tmp_path), "pre.ckpt")
+    assert os.path.exists(ck)
+    # plain reload into a second instance through the trainer
+    other = K.TransHModel(True, d, E, R)
+    tr2 = ModelTrainer(other, log, 10, flags)
+    tr2.load(ck, cpu=True)
+    assert (tr2.step, tr2.best_step, float(tr2.best_dev_performance)) == (30, 20, 0.4)
+    for k, v in pre.state_dict().items():
+        assert torch.equal(v.cpu(), other.state_dict()[k].cpu()), k
+    # warm start of the joint model (-load_ckpt_file).  A pre-trained table with exactly one row less than the joint
+    # model's (E vs E + 1 with the padding row) takes the trainer's "cke" branch: rows copied in place, no remap.
+    U, I = 7, 9
+    i_map = {i: i for i in range(I)}
+    new_map = {i: ((i * 3) % E if i % 2 else -1, i) for i in range(I)}
+    names = ["ent_embeddings.weight", "rel_embeddings.weight", "norm_embeddings.weight"]
+    jflags = types.SimpleNamespace(**dict(vars(flags), model_type="jtransup", experiment_name="joint"))
+    joint = K.jTransUPModel(True, d, U, I, E, R, i_map, new_map, False, False)
+    before_user = joint.user_embeddings.weight.detach().clone()
+    ModelTrainer(joint, log, 10, jflags).loadEmbedding(ck, names, cpu=True, e_remap={e: (e * 7) % E for e in range(E)})
+    ent_pre = pre.ent_embeddings.weight.detach().cpu()
+    ent_new = joint.ent_embeddings.weight.detach().cpu()
+    assert ent_new.shape[0] == E + 1 and torch.equal(ent_new[:E], ent_pre)
+    assert not ent_new[E].any()                                       # the padding row stays zero (jTransUP.py:96-100)
+    assert torch.equal(joint.rel_embeddings.weight.detach().cpu(), pre.rel_embeddings.weight.detach().cpu())
+    assert torch.equal(joint.norm_embeddings.weight.detach().cpu(), pre.norm_embeddings.weight.detach().cpu())
+    assert torch.equal(joint.user_embeddings.weight.detach().cpu(), before_user.cpu())
+    # a joint vocabulary that is larger than the pre-trained one: rows go through e_remap (trainer.py:176-186)
+    E2 = E + 6
+    big = K.jTransUPModel(True, d, U, I, E2, R, i_map, new_map, False, False)
+    untouched = big.ent_embeddings.weight.detach().clone()
+    e_remap = {e: (e * 7) % E2 for e in range(E)}                     # old entity id -> joint index (injective: gcd(7, 46) = 1)
+    assert len(set(e_remap.values())) == E
+    ModelTrainer(big, log, 10, jflags).loadEmbedding(ck, names, cpu=True, e_remap=e_remap)
+    ent_big = big.ent_embeddings.weight.detach().cpu()
+    for e, m in e_remap.items():
+        assert torch.equal(ent_big[m], ent_pre[e])
+    rest = sorted(set(range(E2 + 1)) - set(e_remap.values()))
+    assert torch.equal(ent_big[rest], untouched.cpu()[rest])          # rows without a pre-trained counterpart keep their init
