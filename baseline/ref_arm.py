@@ -68,6 +68,8 @@ def pick_threads(torch, fn, counts=None):
     a handful of thread counts and keep the fastest (reported as `cores`)."""
     cores = os.cpu_count() or 1
     best, best_t = cores, None
+    for _ in range(2):          # the first two passes over fresh tables are far off the steady state: not charged to a count
+        fn()
     for nt in sorted({min(cores, x) for x in (counts or (8, 16, 32, 64, cores))}):
         torch.set_num_threads(nt)
         fn()
