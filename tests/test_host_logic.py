@@ -755,3 +755,69 @@ def test_device_train_iterator_follows_the_reference_epoch_rule():
     assert small.batches_per_epoch == 1 and next(small)[0].numel() == 7 and next(small)[0].numel() == 7
     with pytest.raises(ValueError):
         DeviceTrainIterator(np.zeros((0, 3), np.int64), 4, device="cpu")
+
+
+def test_sharding_host_logic_properties():
+    """Property tests (hypothesis) of the multi-GPU host logic around the one collective: contiguous row shards tile the
+    catalog for any (rows, world); per-shard top-K lists merged by the host statement of kgrec_merge_topk equal the
+    top-K of the whole catalog, ties included ((score, id) order == integer order of the 64-bit keys); the filter CSR
+    restricted to the shards partitions the unrestricted one."""
+    from hypothesis import given, settings, strategies as st
+    from kgrec_b200 import evaluation as KE
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 5000), st.integers(1, 16))
+    def shards_tile(n, world):
+        bounds = [KE.shard_bounds(n, world, r) for r in range(world)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == n
+        for (lo, hi), (lo2, _) in zip(bounds, bounds[1:]):
+            assert lo <= hi == lo2
+        per = (n + world - 1) // world
+        assert all(hi - lo <= per for lo, hi in bounds)
+    shards_tile()
+
+    def keys_of(scores, ids):
+        bits = np.asarray(scores, np.float32).view(np.uint32).astype(np.uint64)
+        return (bits << np.uint64(32)) | np.asarray(ids, np.uint64)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 300), st.integers(1, 6), st.integers(1, 12), st.integers(0, 2 ** 31 - 1))
+    def merged_equals_global(n, world, k, seed):
+        rng = np.random.RandomState(seed)
+        nq = 3
+        scores = (rng.randint(0, 7, (nq, n)) / 4).astype(np.float32)            # few distinct values: many ties
+        lists = np.full((world, nq, k), np.iinfo(np.uint64).max, dtype=np.uint64)
+        for g in range(world):
+            lo, hi = KE.shard_bounds(n, world, g)
+            for q in range(nq):
+                ks = np.sort(keys_of(scores[q, lo:hi], np.arange(lo, hi)))[:k]
+                lists[g, q, :len(ks)] = ks
+        merged = KE.merge_topk_host(torch.from_numpy(lists.view(np.int64)))
+        ids, sc = KE.keys_to_ids_scores(merged)
+        for q in range(nq):
+            want = O.rec_topk(scores[q], None, k)                                   # stable argsort: (score, id)
+            got = [int(x) for x in ids[q] if x >= 0]
+            assert got == want
+            assert np.array_equal(sc[q].numpy()[:len(want)], scores[q][want])
+            assert (ids[q][len(want):] == -1).all()
+    merged_equals_global()
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 200), st.integers(1, 5), st.integers(0, 2 ** 31 - 1))
+    def filter_partitions(n, world, seed):
+        rng = np.random.RandomState(seed)
+        keys = list(range(6))
+        dicts = [{q: set(int(x) for x in rng.choice(n, rng.randint(0, min(n, 9) + 1), replace=False)) for q in keys[::2]},
+                 {q: set(int(x) for x in rng.choice(n, rng.randint(0, min(n, 5) + 1), replace=False)) for q in keys}]
+        ptr, ids = KE.build_filter_csr(keys, dicts, torch.device("cpu"))
+        whole = [sorted(ids[int(ptr[i]):int(ptr[i + 1])].tolist()) for i in range(len(keys))]
+        parts = [[] for _ in keys]
+        for g in range(world):
+            lo, hi = KE.shard_bounds(n, world, g)
+            p, i_ = KE.build_filter_csr(keys, dicts, torch.device("cpu"), lo, hi)
+            for q in range(len(keys)):
+                row = i_[int(p[q]):int(p[q + 1])].tolist() if int(p[q + 1]) > int(p[q]) else []
+                assert all(lo <= x < hi for x in row) and row == sorted(row)
+                parts[q].extend(row)
+        assert parts == whole
+    filter_partitions()
